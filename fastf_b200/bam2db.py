@@ -1,0 +1,300 @@
+"""Host side of `fastF bam2db`, mirroring the reference operator
+
+    int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, char *features_file,
+               float rate_cell, float rate_depth, unsigned int seed)          (reference src/bam2db_ds.h:62-70)
+
+Same arguments, same return convention (0 ok / 1 failure + message on stderr), same stdout/stderr lines and the
+same output files.  The per-read hot loop (reference src/bam2db_ds.c:360-438) and the sqlite aggregation
+(src/bam2db_ds.c:480-483) run on the GPU through libfastf_gpu.so; this module only reads the two small list files,
+draws the cell sample, and writes sqlite + .gz files from the device result.  No CPU implementation of the hot
+path exists here."""
+import ctypes as C
+import gzip
+import os
+import sqlite3
+import sys
+
+import numpy as np
+
+from . import _lib
+
+_umi_copies_flag = 0   # reference global `_umi_copies_flag` (src/bam2db_ds.c:3), set by `-u`
+
+
+def gzgets_lines(data, buflen=1024):
+    """Lines as successive gzgets(fp, buf, buflen) calls return them (at most buflen-1 bytes each)."""
+    out = []
+    pos, n, lim = 0, len(data), buflen - 1
+    while pos < n:
+        nl = data.find(b"\n", pos, pos + lim)
+        end = nl + 1 if nl >= 0 else min(pos + lim, n)
+        out.append(data[pos:end])
+        pos = end
+    return out
+
+
+def _read_maybe_gz(path):
+    with open(path, "rb") as f:
+        raw = f.read()
+    return gzip.decompress(raw) if raw[:2] == b"\x1f\x8b" else raw   # gzopen reads plain files transparently too
+
+
+def _cut(s, delims=b"\n\r\t"):
+    for i, ch in enumerate(s):
+        if ch in delims:
+            return s[:i]
+    return s
+
+
+def _strtok3(line):
+    """First three strtok(.., "\\t") tokens of a feature line + the hash key the reference uses (buffer up to its first NUL)."""
+    line = line.split(b"\0", 1)[0]
+    toks, i, n, key_end = [], 0, len(line), None
+    while len(toks) < 3:
+        while i < n and line[i] == 9:
+            i += 1
+        if i >= n:
+            return None, None
+        j = i
+        while j < n and line[j] != 9:
+            j += 1
+        toks.append(line[i:j])
+        if key_end is None:
+            key_end = j
+        i = j + 1
+    return toks, line[:key_end]
+
+
+class Bam2dbInputs:
+    """Barcode sample + feature table exactly as the reference builds them (src/bam2db_ds.c:229-337)."""
+
+    def __init__(self, lib, barcodes_file, features_file, rate_cell, seed):
+        lines = gzgets_lines(_read_maybe_gz(barcodes_file))
+        self.n_cells = len(lines)
+        samp = np.zeros(max(self.n_cells, 1), dtype=np.uint64)
+        d0 = C.c_uint64(0)
+        ns = lib.fastf_sample_cells(self.n_cells, C.c_float(rate_cell), seed, samp.ctypes.data_as(_lib.c_u64p), C.byref(d0))
+        if ns == 2**64 - 1:
+            raise ValueError("Sample size must be smaller than population size when sampling without replacement.")
+        self.n_cells_sampled = int(ns)
+        self.d0 = int(d0.value)
+        self.duplicate_barcodes = False
+        cells, seen = [], set()
+        cell_index = 1
+        for nth, ln in enumerate(lines):
+            if cell_index > ns:
+                break
+            if nth != int(samp[cell_index - 1]):
+                continue
+            bc = _cut(ln).split(b"\0", 1)[0]
+            if bc not in seen:
+                seen.add(bc)
+                cells.append(bc)
+                cell_index += 1
+            else:
+                self.duplicate_barcodes = True   # index not advanced: no later line can match (src/bam2db_ds.c:260,281-285)
+        self.cells = cells
+        feats, fseen = [], {}
+        self.duplicate_features = False
+        for ln in gzgets_lines(_read_maybe_gz(features_file)):
+            toks, key = _strtok3(ln)
+            if toks is None:
+                raise ValueError("feature line with fewer than three tab-separated fields (the reference dereferences NULL here)")
+            toks[2] = _cut(toks[2])
+            if key not in fseen:
+                fseen[key] = len(feats) + 1
+                feats.append((key, toks[0], toks[1], toks[2]))
+            else:
+                self.duplicate_features = True
+        self.features = feats
+
+
+def _pack_table(keys):
+    off = np.zeros(len(keys) + 1, dtype=np.uint32)
+    if keys:
+        off[1:] = np.cumsum([len(k) for k in keys], dtype=np.uint64).astype(np.uint32)
+    blob = b"".join(keys) + b"\0"
+    return blob, off
+
+
+def decode_rows(row_keys, bits_gene, bits_umi, umi_max_bytes):
+    """packed rows -> (cell, gene, blob_len or -1 for NULL, content as left-aligned integer of umi_max_bytes bytes)"""
+    k = np.asarray(row_keys, dtype=np.uint64)
+    code = k & np.uint64((1 << bits_umi) - 1)
+    gene = ((k >> np.uint64(bits_umi)) & np.uint64((1 << bits_gene) - 1)).astype(np.uint32)
+    cell = (k >> np.uint64(bits_umi + bits_gene)).astype(np.uint32)
+    nn = (code >> np.uint64(bits_umi - 1)) & np.uint64(1)
+    nbytes = (code & np.uint64(7)).astype(np.int64)
+    content = (code >> np.uint64(3)) & np.uint64((1 << (8 * umi_max_bytes)) - 1)
+    nbytes = np.where(nn == 1, nbytes, -1)
+    return cell, gene, nbytes, content
+
+
+def run_device(ctx, bam_bytes, inputs, rate_depth, seed, want_rows=True, inflate_lanes=0, chunk_inflated_bytes=0, feed_piece=0, umi_max_bytes=0):
+    """The C-ABI call sequence for one BAM image in host memory.  Returns (Bam2dbResult, dict of numpy copies)."""
+    lib = ctx.lib
+    ckeys, coff = _pack_table(inputs.cells)
+    gkeys, goff = _pack_table([f[0] for f in inputs.features])
+    p = _lib.Bam2dbParams()
+    p.cell_keys = ckeys
+    p.cell_off = coff.ctypes.data_as(_lib.c_u32p)
+    p.n_cells = len(inputs.cells)
+    p.gene_keys = gkeys
+    p.gene_off = goff.ctypes.data_as(_lib.c_u32p)
+    p.n_genes = len(inputs.features)
+    p.seed = seed
+    p.d0 = inputs.d0
+    p.keep_threshold = lib.fastf_keep_threshold(C.c_float(rate_depth))
+    p.umi_max_bytes = umi_max_bytes
+    p.want_rows = 1 if want_rows else 0
+    p.inflate_lanes = inflate_lanes
+    p.chunk_inflated_bytes = chunk_inflated_bytes
+    job = C.c_void_p()
+    ctx.check(lib.fastf_bam2db_begin(ctx.h, C.byref(p), C.byref(job)), "bam2db_begin")
+    res = _lib.Bam2dbResult()
+    try:
+        buf = np.frombuffer(bam_bytes, dtype=np.uint8)
+        n = buf.size
+        step = feed_piece if feed_piece else max(n, 1)
+        for lo in range(0, n, step):
+            hi = min(n, lo + step)
+            ctx.check(lib.fastf_bam2db_feed(job, C.c_void_p(buf.ctypes.data + lo), hi - lo), "bam2db_feed")
+        ctx.check(lib.fastf_bam2db_finish(job, C.byref(res)), "bam2db_finish")
+        out = {
+            "m_gene": np.ctypeslib.as_array(res.m_gene, (res.nnz,)).copy() if res.nnz else np.zeros(0, np.uint32),
+            "m_cell": np.ctypeslib.as_array(res.m_cell, (res.nnz,)).copy() if res.nnz else np.zeros(0, np.uint32),
+            "m_count": np.ctypeslib.as_array(res.m_count, (res.nnz,)).copy() if res.nnz else np.zeros(0, np.uint32),
+            "row_keys": np.ctypeslib.as_array(res.row_keys, (res.n_rows,)).copy() if (want_rows and res.n_rows) else np.zeros(0, np.uint64),
+        }
+        stats = {f: getattr(res, f) for f, _ in _lib.Bam2dbResult._fields_ if not f.startswith("m_") and f != "row_keys"}
+        lib.fastf_bam2db_result_free(C.byref(res))
+        return stats, out
+    finally:
+        lib.fastf_bam2db_job_free(job)
+
+
+def matrix_header(bam_file, rate_cell, rate_depth, total, sampled, valid):
+    # "%%%M" in the reference's format string prints "%%M" with glibc (src/bam2db_ds.c:500)
+    return ("%%%%MatrixMarket matrix coordinate integer general\n%%metadata_json: \n%%{\n%%\t\"software_version\": \"fastF-1.0.0\",\n"
+            "%%\t\"format_version\": 1,\n%%\t\"parent_bam\": \"%s\",\n%%\t\"rate_cell\": %.3f,\n%%\t\"rate_depth\": %.3f,\n"
+            "%%\t\"total_n_FastQ\": %d,\n%%\t\"sampled_n_FastQ\": %d,\n%%\t\"sampled_valid_n_FastQ\": %d\n%%}\n") % (
+        bam_file, float(np.float32(rate_cell)), float(np.float32(rate_depth)), total, sampled, valid)
+
+
+def _lines_u32(cols, sep):
+    """vectorised "a<sep>b<sep>c\\n" formatting of u32 columns"""
+    if len(cols[0]) == 0:
+        return b""
+    parts = []
+    for i, c in enumerate(cols):
+        parts.append(np.char.mod("%d", c))
+    s = parts[0]
+    for p_ in parts[1:]:
+        s = np.char.add(np.char.add(s, sep), p_)
+    return ("\n".join(s.tolist()) + "\n").encode()
+
+
+def decode_dna10(blob_content, umi_max_bytes):
+    """decode_DNA(blob, 10): the first 10 bases of the 2-bit blob (reference src/bam2db_ds.c:53-93, called at :629)"""
+    out = []
+    for k in range(10):
+        bitpos = 8 * umi_max_bytes - 2 * (k + 1)
+        code = (blob_content >> bitpos) & 3 if bitpos >= 0 else 0
+        out.append("ACGT"[code])
+    return "".join(out)
+
+
+def bam2db(bam_file, db_file, path_out, barcodes_file, features_file, rate_cell, rate_depth, seed=926, device=0, ctx=None):
+    own = ctx is None
+    try:
+        if own:
+            ctx = _lib.Context(device)
+        lib = ctx.lib
+        try:
+            db = sqlite3.connect(db_file, isolation_level=None)
+        except sqlite3.Error as e:
+            sys.stderr.write("Can't open database: %s\n" % e)
+            return 1
+        sys.stderr.write("Opened database successfully\n")
+        for path, what in ((bam_file, "BAM"), (barcodes_file, "cell barcode"), (features_file, "feature name")):
+            if not os.path.exists(path):
+                sys.stderr.write("Can't open %s file %s\n" % (what, path))
+                return 1
+            sys.stderr.write("Opened %s file %s successfully\n" % (what, path))
+        db.execute("CREATE TABLE cell (cell_barcode TEXT);")
+        db.execute("CREATE TABLE feature (feature_id TEXT, feature_name TEXT, feature_type);")
+        db.execute("CREATE TABLE umi (cell_index INTEGER, feature_index INTEGER, encoded_umi TEXT);")
+        inputs = Bam2dbInputs(lib, barcodes_file, features_file, rate_cell, seed)
+        print("Total number of cells: %d" % inputs.n_cells)
+        print("Actual number of sampled cell barcodes: %d" % inputs.n_cells_sampled)
+        if inputs.duplicate_barcodes:
+            print("Warning: Duplicate cell barcodes were found in %s!" % barcodes_file)
+        if inputs.duplicate_features:
+            print("Warning: Duplicate feature names were found in %s!" % features_file)
+        db.execute("BEGIN TRANSACTION")
+        db.executemany("INSERT INTO cell VALUES (?1);", ((c.decode("latin-1"),) for c in inputs.cells))
+        db.execute("END TRANSACTION")
+        db.execute("BEGIN TRANSACTION")
+        db.executemany("INSERT INTO feature VALUES (?1, ?2, ?3);", ((f[1].decode("latin-1"), f[2].decode("latin-1"), f[3].decode("latin-1")) for f in inputs.features))
+        db.execute("END TRANSACTION")
+        print("Start to convert bam file to sqlite3 database...")
+        sys.stdout.flush()
+        bam_bytes = np.fromfile(bam_file, dtype=np.uint8)
+        stats, out = run_device(ctx, bam_bytes, inputs, rate_depth, seed, want_rows=True)
+        cell, gene, nbytes, content = decode_rows(out["row_keys"], stats["bits_gene"], stats["bits_umi"], stats["umi_max_bytes"])
+        mb = stats["umi_max_bytes"]
+
+        def rows():
+            for c, g, nb, ct in zip(cell.tolist(), gene.tolist(), nbytes.tolist(), content.tolist()):
+                yield (c, g, None if nb < 0 else ct.to_bytes(mb, "big")[:nb])
+        db.execute("BEGIN TRANSACTION")
+        db.executemany("INSERT INTO umi VALUES (?1, ?2, ?3);", rows())
+        db.execute("END TRANSACTION")
+        print("In %s, total fastQ reads: %d" % (bam_file, stats["total"]))
+        print("In %s, sampled fastQ reads: %d" % (bam_file, stats["sampled"]))
+        print("In %s, sampled and valid fastQ reads: %d" % (bam_file, stats["valid"]))
+        # table mtx from the device COO, with the schema text sqlite gives `CREATE TABLE mtx AS SELECT ...` (src/bam2db_ds.c:480-483)
+        db.execute("CREATE TABLE mtx(\n  feature_index INT,\n  cell_index INT,\n  expression_level\n)")
+        db.execute("BEGIN TRANSACTION")
+        db.executemany("INSERT INTO mtx VALUES (?1, ?2, ?3);", zip(out["m_gene"].tolist(), out["m_cell"].tolist(), out["m_count"].tolist()))
+        db.execute("END TRANSACTION")
+        try:
+            fb = gzip.open(os.path.join(path_out, "barcodes.tsv.gz"), "wb")
+            ff = gzip.open(os.path.join(path_out, "features.tsv.gz"), "wb")
+            fm = gzip.open(os.path.join(path_out, "matrix.mtx.gz"), "wb")
+        except OSError as e:
+            sys.stderr.write("\x1b[31mError:\x1b[0m can not open file %s\n" % e.filename)
+            return 1
+        fm.write(matrix_header(bam_file, rate_cell, rate_depth, stats["total"], stats["sampled"], stats["valid"]).encode("latin-1"))
+        fm.write(b"%d %d %d\n" % (len(inputs.features), len(inputs.cells), stats["nnz"]))
+        fm.write(_lines_u32([out["m_gene"], out["m_cell"], out["m_count"]], " "))
+        fm.close()
+        print("matrix.mtx.gz is generated.")
+        fb.write(b"".join(c + b"\n" for c in inputs.cells))
+        fb.close()
+        print("barcodes.tsv.gz is generated.")
+        ff.write(b"".join(f[1] + b"\t" + f[2] + b"\t" + f[3] + b"\n" for f in inputs.features))
+        ff.close()
+        print("features.tsv.gz is generated.")
+        if _umi_copies_flag:
+            # numi = copies per distinct (cell, gene, umi): GROUP BY cell_index, feature_index, encoded_umi (src/bam2db_ds.c:539-543)
+            keys = np.sort(out["row_keys"], kind="stable")
+            uniq, counts = np.unique(keys, return_counts=True)
+            c2, g2, nb2, ct2 = decode_rows(uniq, stats["bits_gene"], stats["bits_umi"], stats["umi_max_bytes"])
+            db.execute("CREATE TABLE numi(\n  feature_index INT,\n  cell_index INT,\n  encoded_umi TEXT,\n  n_copy\n)")
+            db.execute("BEGIN TRANSACTION")
+            db.executemany("INSERT INTO numi VALUES (?1, ?2, ?3, ?4);",
+                           ((g, c, None if nb < 0 else ct.to_bytes(mb, "big")[:nb], n) for c, g, nb, ct, n in zip(c2.tolist(), g2.tolist(), nb2.tolist(), ct2.tolist(), counts.tolist())))
+            db.execute("END TRANSACTION")
+            with gzip.open(os.path.join(path_out, "umi.tsv.gz"), "wb") as fu:
+                for c, g, nb, ct, n in zip(c2.tolist(), g2.tolist(), nb2.tolist(), ct2.tolist(), counts.tolist()):
+                    fu.write(("%d\t%d\t%s\t%d\n" % (g, c, "NULL" if nb < 0 else decode_dna10(ct, mb), n)).encode())
+            print("umi.tsv.gz is generated.")
+        db.close()
+        return 0
+    except (_lib.FastfError, ValueError, OSError, sqlite3.Error) as e:
+        sys.stderr.write("bam2db: %s\n" % e)
+        return 1
+    finally:
+        if own and ctx is not None:
+            ctx.close()

@@ -1,0 +1,102 @@
+"""Builds the native pieces in-tree (no JIT cache): the sm_100a CUDA library behind include/fastf_gpu.h,
+the synthetic-data generator and (test infrastructure only) the oracle.  Used by __graft_entry__.build()."""
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "fastf_b200")
+BUILD = os.path.join(PKG, "_build")
+LIB = os.path.join(BUILD, "libfastf_gpu.so")
+SYNTH_LIB = os.path.join(BUILD, "libfastf_synth.so")
+SYNTH_BIN = os.path.join(BUILD, "fastf_synth")
+CLI_BIN = os.path.join(BUILD, "fastF")
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("build step failed: " + " ".join(cmd))
+    return r.stdout
+
+
+def _sources(d, exts):
+    return [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(exts)]
+
+
+def build_cuda(force=False):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    csrc = os.path.join(PKG, "csrc")
+    deps = _sources(csrc, (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "fastf_gpu.h")]
+    if not force and _newer(LIB, deps):
+        return LIB
+    if not os.path.exists(nvcc):
+        if os.path.exists(LIB):
+            return LIB   # GPU box without a changed source tree: the prebuilt library travelled with the snapshot
+        raise RuntimeError("nvcc not found and no prebuilt libfastf_gpu.so")
+    os.makedirs(BUILD, exist_ok=True)
+    _run([nvcc] + NVCC_FLAGS + ["-o", LIB, os.path.join(csrc, "capi.cu")])
+    return LIB
+
+
+def build_synth(force=False):
+    src = os.path.join(PKG, "synth", "synth.c")
+    deps = [src, os.path.join(PKG, "synth", "synth.h")]
+    os.makedirs(BUILD, exist_ok=True)
+    if force or not _newer(SYNTH_LIB, deps):
+        _run(["gcc", "-O2", "-fPIC", "-shared", "-o", SYNTH_LIB, src, "-lz", "-lpthread", "-lm"])
+    if force or not _newer(SYNTH_BIN, deps):
+        _run(["gcc", "-O2", "-DFASTF_SYNTH_MAIN", "-o", SYNTH_BIN, src, "-lz", "-lpthread", "-lm"])
+    return SYNTH_LIB
+
+
+def build_cli(force=False):
+    host = os.path.join(PKG, "host")
+    srcs = _sources(host, (".c",))
+    if not srcs:
+        return None
+    deps = srcs + _sources(host, (".h",)) + [os.path.join(ROOT, "include", "fastf_gpu.h")]
+    if force or not _newer(CLI_BIN, deps):
+        _run(["gcc", "-O2", "-std=gnu11", "-Wall", "-Wno-unused-result", "-I" + os.path.join(ROOT, "include"), "-o", CLI_BIN] + srcs +
+             ["-L" + BUILD, "-lfastf_gpu", "-Wl,-rpath,$ORIGIN", "-lz", "-l:libsqlite3.so.0", "-lm", "-ldl"])
+    return CLI_BIN
+
+
+def build_oracle():
+    """Test infrastructure: the CPU restatement and, when /root/reference exists, the unmodified reference."""
+    _run(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+
+
+def build_emu():
+    """Test infrastructure: the same kernel sources compiled for the host under the SIMT emulator."""
+    out = os.path.join(ROOT, "tests", "emu", "_build", "libfastf_emu.so")
+    csrc = os.path.join(PKG, "csrc")
+    deps = _sources(csrc, (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "fastf_gpu.h"), os.path.join(ROOT, "tests", "emu", "cuda_emu.h")]
+    if _newer(out, deps):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    _run(["g++", "-O1", "-g", "-std=c++17", "-DFASTF_EMU", "-I" + os.path.join(ROOT, "tests", "emu"), "-x", "c++", "-fPIC", "-shared", "-o", out,
+          os.path.join(csrc, "capi.cu"), "-lz"])
+    return out
+
+
+def build_all(force=False):
+    build_cuda(force)
+    build_synth(force)
+    build_cli(force)
+    build_oracle()
+
+
+if __name__ == "__main__":
+    build_all("--force" in sys.argv)
+    print("built", LIB)

@@ -1,0 +1,234 @@
+// K2 -- BAM record-boundary scan + warp-cooperative aux-tag parse.
+//
+// Replaces, for every record, htslib's sam_read1 framing and the reference's per-read tag logic:
+//   bam_aux_get/bam_aux2Z("CB") + hash_table_lookup(ht_cell)      reference src/bam2db_ds.c:366-382
+//   bam_aux_get/bam_aux2i("xf") in {25,17}                         reference src/bam2db_ds.c:394-400
+//   bam_aux_get/bam_aux2Z("GX") + hash_table_lookup(ht_feature)   reference src/bam2db_ds.c:403-411
+//   bam_aux_get/bam_aux2Z("UB") + encode_DNA                       reference src/bam2db_ds.c:412-419, 5-51
+// Aux layout and htslib semantics (first matching tag wins; Z/H only for strings; c C s S i I for ints;
+// a malformed field hides every tag at or after it) are from the SAM/BAM specification, section 4.2.4.
+//
+// Mapping: one warp per BGZF block.  htslib writers never split a record across BGZF blocks, so a
+// block starts on a record boundary; the warp walks the block_size chain (the walk must end exactly
+// at ISIZE, otherwise FASTF_ST_REC_STRADDLE is raised and the host falls back).  All lanes keep the
+// same cursor; string scans (NUL search), hashing, table compares and the 2-bit UMI packing are done
+// one byte per lane with ballots / redux.  The kernel emits, per block, the record count, the number
+// of "CB-valid" records (the ones that consume an MT19937 draw) and one packed u64 candidate per
+// CB-valid record, in file order, into a per-block staging slice.  A later prefix sum over the
+// per-block counts yields the global read ordinal (= MT draw index) of every candidate.
+#pragma once
+#include "common.cuh"
+#include "strtable.h"
+
+struct FastfKeyLayout {
+    u32 umi_max_bytes;   // 1..4 -> UMIs up to 4*umi_max_bytes bases
+    u32 bits_umi;        // 1 (non-NULL flag) + 8*umi_max_bytes + 3 (blob length)
+    u32 bits_gene;
+    u32 bits_cell;       // bits_cell + bits_gene + bits_umi <= 63
+};
+
+#ifndef FASTF_EMU
+__device__ __forceinline__ void fastf_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#else
+inline void fastf_prefetch_l1(const void *) {}
+#endif
+
+// warp-cooperative lookup of s[0..len) in a string table; every lane gets the value (0 = absent)
+__device__ __forceinline__ u32 fastf_table_lookup(const FastfStrTableView &T, u32 my_pw1, u32 my_pw2, const u8 *__restrict__ s, u32 len, u32 lane)
+{
+    u32 h1 = 0, h2 = 0;
+    u32 c = 0;
+    do {
+        u32 i = c + lane;
+        u32 byte = (i < len) ? (u32)s[i] + 1u : 0u;
+        u32 s1 = __reduce_add_sync(FASTF_FULL_MASK, byte * my_pw1);
+        u32 s2 = __reduce_add_sync(FASTF_FULL_MASK, byte * my_pw2);
+        h1 = h1 * FASTF_H1_Q + s1;
+        h2 = h2 * FASTF_H2_Q + s2;
+        c += 32;
+    } while (c < len);
+    u32 slot = fastf_hash_finalize(h1) & T.mask;
+    for (;;) {
+        FastfStrSlot e = T.slots[slot];
+        if (e.value == 0) return 0;
+        if (e.tag == h2 && e.len == len) {
+            bool same = true;
+            for (u32 c2 = 0; c2 < len; c2 += 32) {
+                u32 i = c2 + lane;
+                bool ok = (i >= len) || (s[i] == T.pool[e.off + i]);
+                same = same && __all_sync(FASTF_FULL_MASK, ok);
+            }
+            if (same) return e.value;
+        }
+        slot = (slot + 1) & T.mask;
+    }
+}
+
+struct FastfAuxHit { u32 off; u32 len; u32 type; };   // off = offset of the value inside the inflated buffer
+
+#define FASTF_PARSE_WARPS 4
+
+// BAM header walk (what sam_hdr_read does at reference src/bam2db_ds.c:340): "BAM\1", l_text, text, n_ref,
+// (l_name, name, l_ref) x n_ref.  One thread; writes the inflated offset of the first alignment record.
+__global__ void fastf_bam_header_kernel(const u8 *__restrict__ infl, u64 n, u64 *__restrict__ first_record_off, u32 *__restrict__ status)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    *first_record_off = n;
+    if (n < 12 || infl[0] != 'B' || infl[1] != 'A' || infl[2] != 'M' || infl[3] != 1) { *status |= FASTF_ST_BAD_HEADER; return; }
+    u64 p = 8ull + (u64)fastf_ld_u32(infl + 4);
+    if (p + 4 > n) { *status |= FASTF_ST_BAD_HEADER; return; }
+    const u32 n_ref = fastf_ld_u32(infl + p);
+    p += 4;
+    for (u32 i = 0; i < n_ref; i++) {
+        if (p + 4 > n) { *status |= FASTF_ST_BAD_HEADER; return; }
+        p += 8ull + (u64)fastf_ld_u32(infl + p);
+    }
+    if (p > n) { *status |= FASTF_ST_BAD_HEADER; return; }
+    *first_record_off = p;
+}
+
+__global__ void __launch_bounds__(FASTF_PARSE_WARPS * 32)
+fastf_bam_parse_kernel(const u8 *__restrict__ infl, const u64 *__restrict__ blk_off, const u32 *__restrict__ blk_isize, u32 nblocks, const u64 *__restrict__ first_record_off_ptr,
+                       FastfStrTableView cells, FastfStrTableView genes, FastfKeyLayout L,
+                       const u64 *__restrict__ stage_off, u64 *__restrict__ stage, u32 *__restrict__ blk_nrec, u32 *__restrict__ blk_ncbv, u32 *__restrict__ blk_status)
+{
+    const u32 lane = threadIdx.x & 31u;
+    const u32 b = blockIdx.x * FASTF_PARSE_WARPS + (threadIdx.x >> 5);
+    if (b >= nblocks) return;
+    const u32 c_pw1 = cells.pw1[lane], c_pw2 = cells.pw2[lane];
+    const u32 g_pw1 = genes.pw1[lane], g_pw2 = genes.pw2[lane];
+    const u64 bstart = blk_off[b], bend = bstart + blk_isize[b];
+    const u64 first_record_off = *first_record_off_ptr;   // end of the BAM header (chunk 0) or 0
+    u64 p = bstart > first_record_off ? bstart : first_record_off;
+    u64 *out = stage + stage_off[b];
+    u32 nrec = 0, ncbv = 0, status = 0;
+
+    while (p < bend) {
+        if (bend - p < 4) { status |= FASTF_ST_REC_STRADDLE; break; }
+        const u32 bs = fastf_ld_u32(infl + p);
+        if ((i32)bs < 32) { status |= FASTF_ST_REC_CORRUPT; break; }
+        if (p + 4 + (u64)bs > bend) { status |= FASTF_ST_REC_STRADDLE; break; }
+        const u64 rec = p + 4, rend = rec + bs;
+        p = rend;
+        // pull the next record's lines towards L1 while this one is parsed
+        { u64 a = rend + (u64)lane * 128u; if (lane < 4 && a < bend) fastf_prefetch_l1(infl + a); }
+        nrec++;
+        const u32 l_read_name = infl[rec + 8];
+        const u32 n_cigar = fastf_ld_u16(infl + rec + 12);
+        const i32 l_seq = (i32)fastf_ld_u32(infl + rec + 16);
+        const i64 aoff = 32 + (i64)l_read_name + 4 * (i64)n_cigar + (((i64)l_seq + 1) >> 1) + (i64)l_seq;
+        if (l_seq < 0 || aoff > (i64)bs) { status |= FASTF_ST_REC_CORRUPT; break; }
+
+        // ---- aux walk: find the first CB, xf, GX, UB ----
+        FastfAuxHit cb = {0, 0, 0}, xf = {0, 0, 0}, gx = {0, 0, 0}, ub = {0, 0, 0};
+        u32 found = 0;
+        u64 q = rec + (u64)aoff;
+        while (rend - q >= 3 && found != 15u) {
+            const u32 t0 = infl[q], t1 = infl[q + 1], ty = infl[q + 2];
+            const u64 v = q + 3;
+            u64 next;
+            u32 vlen = 0;
+            if (ty == 'Z' || ty == 'H') {
+                bool term = false;
+                u64 s = v;
+                while (s < rend) {
+                    u64 i = s + lane;
+                    bool z = (i < rend) && (infl[i] == 0);
+                    u32 m = __ballot_sync(FASTF_FULL_MASK, z);
+                    if (m) { s += (u32)__ffs((int)m) - 1u; term = true; break; }
+                    s += 32;
+                }
+                if (!term) break;   // htslib: a malformed field hides this and every later tag; not a failure
+                vlen = (u32)(s - v);
+                next = s + 1;
+            } else {
+                u64 sz;
+                switch (ty) {
+                case 'A': case 'c': case 'C': sz = 1; break;
+                case 's': case 'S': sz = 2; break;
+                case 'i': case 'I': case 'f': sz = 4; break;
+                case 'd': sz = 8; break;
+                case 'B': {
+                    if (rend - v < 5) { sz = ~0ull; break; }
+                    u32 sub = infl[v];
+                    u64 cnt = fastf_ld_u32(infl + v + 1);
+                    u64 es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
+                    sz = es ? 5 + es * cnt : ~0ull;
+                    break;
+                }
+                default: sz = ~0ull;
+                }
+                if (sz == ~0ull || sz > rend - v) break;
+                next = v + sz;
+            }
+            if (t0 == 'C' && t1 == 'B' && !(found & 1u)) { cb.off = (u32)(v - bstart); cb.len = vlen; cb.type = ty; found |= 1u; }
+            else if (t0 == 'x' && t1 == 'f' && !(found & 2u)) { xf.off = (u32)(v - bstart); xf.type = ty; found |= 2u; }
+            else if (t0 == 'G' && t1 == 'X' && !(found & 4u)) { gx.off = (u32)(v - bstart); gx.len = vlen; gx.type = ty; found |= 4u; }
+            else if (t0 == 'U' && t1 == 'B' && !(found & 8u)) { ub.off = (u32)(v - bstart); ub.len = vlen; ub.type = ty; found |= 8u; }
+            q = next;
+        }
+
+        // ---- CB gate: present, string-typed, in the sampled-cell table ----
+        if (!(found & 1u) || !(cb.type == 'Z' || cb.type == 'H')) continue;
+        const u32 cidx = fastf_table_lookup(cells, c_pw1, c_pw2, infl + bstart + cb.off, cb.len, lane);
+        if (cidx == 0) continue;
+
+        // ---- this record consumes a draw; decide whether it would be inserted if kept ----
+        u64 key = FASTF_INVALID_KEY;
+        i64 xfv = 0;
+        if (found & 2u) {
+            const u8 *x = infl + bstart + xf.off;
+            switch (xf.type) {
+            case 'c': xfv = (i64)(int8_t)x[0]; break;
+            case 'C': xfv = x[0]; break;
+            case 's': xfv = (i64)(int16_t)fastf_ld_u16(x); break;
+            case 'S': xfv = fastf_ld_u16(x); break;
+            case 'i': xfv = (i64)(i32)fastf_ld_u32(x); break;
+            case 'I': xfv = fastf_ld_u32(x); break;
+            default: xfv = 0;
+            }
+        }
+        const int xfi = (int)xfv;   // the reference stores bam_aux2i() in an int
+        if ((xfi == 25 || xfi == 17) && (found & 4u) && (gx.type == 'Z' || gx.type == 'H') && (found & 8u) && (ub.type == 'Z' || ub.type == 'H')) {
+            const u32 gidx = fastf_table_lookup(genes, g_pw1, g_pw2, infl + bstart + gx.off, gx.len, lane);
+            if (gidx != 0) {
+                if (ub.len > 4u * L.umi_max_bytes) {
+                    status |= FASTF_ST_UMI_TOO_LONG;
+                } else {
+                    const u8 *u = infl + bstart + ub.off;
+                    u32 code = 0, badbase = 0;
+                    if (lane < ub.len) {
+                        u32 ch = u[lane];
+                        code = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
+                        badbase = code > 3u;
+                    }
+                    u32 hi = __reduce_or_sync(FASTF_FULL_MASK, (lane < 16u && !badbase) ? (code << (30u - 2u * lane)) : 0u);
+                    u32 anybad = __any_sync(FASTF_FULL_MASK, badbase);
+                    u64 ucode = 0;   // SQL NULL
+                    if (!anybad) {
+                        u64 content = (u64)(hi >> (32u - 8u * L.umi_max_bytes));
+                        u64 nbytes = (ub.len + 3u) >> 2;
+                        ucode = (1ull << (L.bits_umi - 1u)) | (content << 3) | nbytes;
+                    }
+                    key = ((u64)cidx << (L.bits_gene + L.bits_umi)) | ((u64)gidx << L.bits_umi) | ucode;
+                }
+            }
+        }
+        if (lane == 0) out[ncbv] = key;
+        ncbv++;
+    }
+    if (lane == 0) { blk_nrec[b] = nrec; blk_ncbv[b] = ncbv; blk_status[b] = status; }
+}
+
+// Gather the per-block staging slices into the contiguous, file-ordered candidate array.
+// dst_base[b] = global index of block b's first candidate (exclusive scan of blk_ncbv + running base).
+__global__ void __launch_bounds__(256)
+fastf_stage_gather_kernel(const u64 *__restrict__ stage, const u64 *__restrict__ stage_off, const u32 *__restrict__ blk_ncbv, const u64 *__restrict__ dst_base, u32 nblocks, u64 *__restrict__ cand)
+{
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (warp >= nblocks) return;
+    const u64 *src = stage + stage_off[warp];
+    u64 *dst = cand + dst_base[warp];
+    const u32 n = blk_ncbv[warp];
+    for (u32 i = lane; i < n; i += 32) dst[i] = src[i];
+}

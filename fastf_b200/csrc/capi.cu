@@ -1,0 +1,1493 @@
+// libfastf_gpu.so -- implementation of include/fastf_gpu.h: host orchestration of the sm_100a kernels.
+//
+// Everything that touches read data runs on the device (kernels in the .cuh files next to this one).
+// The host side here only (a) walks the BGZF BSIZE chain (~20 bytes per <= 64 KiB block), (b) moves
+// bytes, (c) sizes buffers from device-side counters and (d) launches.  There is no CPU fallback:
+// without a CUDA device fastf_ctx_create fails and nothing else can be called.
+//
+// Streams: `compute` runs the per-chunk chain  header? -> inflate -> parse -> counts -> gather;
+// `copy` brings the next chunk's compressed bytes in (fastf_bam2db_feed) while the previous chunk is
+// inflating; `mt` extends the MT19937 keep-bit stream while chunks are being parsed.  Per-chunk state
+// is double buffered ("slots"), so the only host wait per chunk is for the previous chunk's 32-byte
+// counter snapshot, which sizes the candidate array.
+#include "../../include/fastf_gpu.h"
+#include "common.cuh"
+#include "bgzf_index.h"
+#include "bgzf_inflate.cuh"
+#include "bam_parse.cuh"
+#include "scan_mt_sample.cuh"
+#include "radix_dedup.cuh"
+#include "freq.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+#define FASTF_ABI_VERSION 1
+
+struct fastf_ctx {
+    int device;
+    cudaStream_t compute, copy, mt;
+    char err[1024];
+    u32 launches;   // kernels launched through this context (bench: gpu_launches)
+};
+
+static int ctx_fail(fastf_ctx *ctx, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    if (ctx) vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+    va_end(ap);
+    if (ctx && getenv("FASTF_VERBOSE")) fprintf(stderr, "fastf_gpu: %s\n", ctx->err);
+    return 1;
+}
+#define CK(call)                                                                                                               \
+    do {                                                                                                                       \
+        cudaError_t e_ = (call);                                                                                               \
+        if (e_ != cudaSuccess) return ctx_fail(ctx, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));     \
+    } while (0)
+#define CKL(name)                                                                                                              \
+    do {                                                                                                                       \
+        ctx->launches++;                                                                                                       \
+        cudaError_t e_ = cudaGetLastError();                                                                                   \
+        if (e_ != cudaSuccess) return ctx_fail(ctx, "%s:%d: launch of %s -> %s", __FILE__, __LINE__, name, cudaGetErrorString(e_)); \
+    } while (0)
+#define TRY(expr)                                                                                                              \
+    do {                                                                                                                       \
+        int r_ = (expr);                                                                                                       \
+        if (r_) return r_;                                                                                                     \
+    } while (0)
+
+static const char *status_string(u32 st, char *buf, size_t n)
+{
+    static const char *names[] = {"bad-btype", "bad-stored", "bad-codelens", "bad-symbol", "bad-distance", "out-overflow", "size-mismatch", "in-overrun",
+                                  "record-straddles-bgzf-block", "record-corrupt", "umi-too-long", "aux-corrupt", "bad-bam-header"};
+    buf[0] = 0;
+    for (u32 b = 0; b < 13; b++)
+        if (st & (1u << b)) { strncat(buf, names[b], n - strlen(buf) - 2); strncat(buf, " ", n - strlen(buf) - 1); }
+    return buf;
+}
+
+// ---- growable device / pinned buffers -------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    template <class T> T *as() const { return (T *)p; }
+};
+static int dev_reserve(fastf_ctx *ctx, DevBuf &b, size_t bytes, size_t keep_bytes = 0, cudaStream_t s = 0)
+{
+    if (bytes <= b.cap) return 0;
+    size_t ncap = std::max(bytes, b.cap + b.cap / 2);
+    ncap = (ncap + 255) & ~(size_t)255;
+    void *np = nullptr;
+    CK(cudaMalloc(&np, ncap));
+    if (keep_bytes && b.p) {
+        CK(cudaMemcpyAsync(np, b.p, keep_bytes, cudaMemcpyDeviceToDevice, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    if (b.p) CK(cudaFree(b.p));
+    b.p = np;
+    b.cap = ncap;
+    return 0;
+}
+static void dev_release(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    template <class T> T *as() const { return (T *)p; }
+};
+static int pin_reserve(fastf_ctx *ctx, PinBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return 0;
+    size_t ncap = std::max(bytes, b.cap * 2);
+    if (b.p) CK(cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    CK(cudaMallocHost(&b.p, ncap));
+    b.cap = ncap;
+    return 0;
+}
+static void pin_release(PinBuf &b)
+{
+    if (b.p) cudaFreeHost(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+struct Timer {   // CUDA-event stopwatch on one stream; accumulates into *acc at collect()
+    cudaEvent_t a = nullptr, b = nullptr;
+    bool armed = false;
+    int init() { return cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess; }
+    void destroy() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); a = b = nullptr; }
+    void start(cudaStream_t s) { cudaEventRecord(a, s); }
+    void stop(cudaStream_t s) { cudaEventRecord(b, s); armed = true; }
+    void collect(float *acc) { if (armed) { float ms = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b); *acc += ms; armed = false; } }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+extern "C" int fastf_abi_version(void) { return FASTF_ABI_VERSION; }
+
+static char g_create_err[512] = "";
+
+extern "C" int fastf_ctx_create(int device, fastf_ctx **out)
+{
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        snprintf(g_create_err, sizeof g_create_err, "no CUDA device (%s); libfastf_gpu has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return 1;
+    }
+    if (device < 0 || device >= n) { snprintf(g_create_err, sizeof g_create_err, "device %d out of range (0..%d)", device, n - 1); return 1; }
+    if (cudaSetDevice(device) != cudaSuccess) { snprintf(g_create_err, sizeof g_create_err, "cudaSetDevice(%d) failed", device); return 1; }
+    fastf_ctx *ctx = (fastf_ctx *)calloc(1, sizeof *ctx);
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->mt, cudaStreamNonBlocking) != cudaSuccess) {
+        snprintf(g_create_err, sizeof g_create_err, "cudaStreamCreate failed");
+        free(ctx);
+        return 1;
+    }
+    *out = ctx;
+    return 0;
+}
+extern "C" void fastf_ctx_destroy(fastf_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamDestroy(ctx->compute);
+    cudaStreamDestroy(ctx->copy);
+    cudaStreamDestroy(ctx->mt);
+    free(ctx);
+}
+extern "C" const char *fastf_last_error(const fastf_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+extern "C" uint32_t fastf_launch_count(const fastf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void *fastf_compute_stream(const fastf_ctx *ctx) { return ctx ? (void *)ctx->compute : nullptr; }
+extern "C" int fastf_host_alloc(fastf_ctx *ctx, size_t bytes, void **out) { CK(cudaSetDevice(ctx->device)); CK(cudaMallocHost(out, bytes ? bytes : 1)); return 0; }
+extern "C" void fastf_host_free(fastf_ctx *ctx, void *p) { (void)ctx; if (p) cudaFreeHost(p); }
+extern "C" int fastf_device_alloc(fastf_ctx *ctx, size_t bytes, void **out) { CK(cudaSetDevice(ctx->device)); CK(cudaMalloc(out, bytes ? bytes : 1)); return 0; }
+extern "C" void fastf_device_free(fastf_ctx *ctx, void *p) { (void)ctx; if (p) cudaFree(p); }
+extern "C" int fastf_memcpy_h2d(fastf_ctx *ctx, void *d, const void *s, size_t n) { CK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, ctx->compute)); CK(cudaStreamSynchronize(ctx->compute)); return 0; }
+extern "C" int fastf_memcpy_d2h(fastf_ctx *ctx, void *d, const void *s, size_t n) { CK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, ctx->compute)); CK(cudaStreamSynchronize(ctx->compute)); return 0; }
+extern "C" int fastf_synchronize(fastf_ctx *ctx) { CK(cudaStreamSynchronize(ctx->copy)); CK(cudaStreamSynchronize(ctx->mt)); CK(cudaStreamSynchronize(ctx->compute)); return 0; }
+extern "C" void fastf_free(void *p) { free(p); }
+
+// ---------------------------------------------------------------------------------------------------
+// host helpers that define the sampling contract
+// ---------------------------------------------------------------------------------------------------
+// keep <=> genrand_real1() < rate  with genrand_real1() = genrand_int32()*(1.0/4294967295.0)
+// (reference src/mt19937ar.c:149-153) and the comparison done in double against the float rate
+// (reference src/bam2db_ds.c:385-390).  The product is monotone in u, so the rule is u < T.
+extern "C" uint64_t fastf_keep_threshold(float rate_depth)
+{
+    const double r = (double)rate_depth;
+    if (!(r > 0.0)) return 0;   // also NaN: every comparison `x >= NaN` is false -> the reference keeps everything... handled below
+    uint64_t lo = 0, hi = 4294967296ull;   // smallest u with u*(1/4294967295) >= r, or 2^32 if none
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        double x = (double)(uint32_t)mid * (1.0 / 4294967295.0);
+        if (x >= r) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+namespace {
+struct HostMT {   // Matsumoto-Nishimura mt19937ar, restated (reference src/mt19937ar.c:60-73,105-140); only for SampleInt's <= n_cells draws
+    u32 mt[624];
+    int mti;
+    void init(u32 s)
+    {
+        mt[0] = s;
+        for (mti = 1; mti < 624; mti++) mt[mti] = 1812433253u * (mt[mti - 1] ^ (mt[mti - 1] >> 30)) + (u32)mti;
+    }
+    u32 next()
+    {
+        if (mti >= 624) {
+            for (int k = 0; k < 624; k++) {
+                u32 y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            mti = 0;
+        }
+        u32 y = mt[mti++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+};
+}   // namespace
+
+// reference src/bam2db_ds.c:240-244 + SampleInt src/utils.c:29-75 (without replacement) + qsort(vsI)
+extern "C" uint64_t fastf_sample_cells(uint64_t n_cells, float rate_cell, uint32_t seed, uint64_t *out, uint64_t *d0)
+{
+    const float prod = (float)n_cells * rate_cell;   // size_t * float -> float arithmetic
+    if (!(prod >= 0.0f) || prod >= 18446744073709551616.0f) return UINT64_MAX;
+    const uint64_t ns = (uint64_t)prod;
+    if (ns > n_cells) return UINT64_MAX;             // the reference prints a message and exit(1)s
+    if (ns == n_cells) {
+        for (uint64_t i = 0; i < n_cells; i++) out[i] = i;
+        if (d0) *d0 = 0;
+        return ns;
+    }
+    HostMT mt;
+    mt.init(seed);
+    std::vector<uint64_t> pool(n_cells);
+    for (uint64_t i = 0; i < n_cells; i++) pool[i] = i;
+    uint64_t ntotal = n_cells;
+    for (uint64_t i = 0; i < ns; i++) {
+        uint64_t idx = (uint64_t)mt.next() % ntotal;
+        out[i] = pool[idx];
+        if (idx != ntotal - 1) pool[idx] = pool[ntotal - 1];
+        ntotal--;
+    }
+    std::sort(out, out + ns);
+    if (d0) *d0 = ns;
+    return ns;
+}
+
+// The reference prints its histogram BST in pre-order (src/filter.c:139-148).  The BST built by inserting keys in read order
+// (src/filter.c:105-124) is the Cartesian tree of `first` (first-occurrence ordinal) over the keys in ascending byte order:
+// the earliest key is the root, smaller keys form its left subtree, larger ones its right subtree, recursively.
+// order_out[k] = index (in ascending key order) of the k-th line of whitelist.txt.  O(n), iterative.
+extern "C" int fastf_cartesian_preorder(const uint32_t *first, uint64_t n, uint64_t *order_out)
+{
+    if (n == 0) return 0;
+    const int64_t NIL = -1;
+    std::vector<int64_t> left(n, NIL), right(n, NIL), stack;
+    stack.reserve(64);
+    for (uint64_t i = 0; i < n; i++) {
+        int64_t last = NIL;
+        while (!stack.empty() && first[stack.back()] > first[i]) { last = stack.back(); stack.pop_back(); }
+        left[i] = last;
+        if (!stack.empty()) right[stack.back()] = (int64_t)i;
+        stack.push_back((int64_t)i);
+    }
+    const int64_t root = stack.front();
+    stack.clear();
+    stack.push_back(root);
+    uint64_t k = 0;
+    while (!stack.empty()) {
+        int64_t v = stack.back();
+        stack.pop_back();
+        order_out[k++] = (uint64_t)v;
+        if (right[v] != NIL) stack.push_back(right[v]);
+        if (left[v] != NIL) stack.push_back(left[v]);
+    }
+    return k == n ? 0 : 1;
+}
+
+extern "C" int64_t fastf_bgzf_index_host(const void *buf, size_t n, uint64_t *in_off, uint32_t *in_len, uint32_t *isize, uint64_t cap, size_t *consumed)
+{
+    std::vector<FastfBgzfBlock> blocks;
+    size_t used = 0;
+    int rc = fastf_bgzf_index((const uint8_t *)buf, n, 0, blocks, &used);
+    if (consumed) *consumed = used;
+    if (rc != FASTF_BGZF_OK && rc != FASTF_BGZF_NEED_MORE) return -1;
+    if (blocks.size() > cap) return -2;
+    for (size_t i = 0; i < blocks.size(); i++) { in_off[i] = blocks[i].in_off; in_len[i] = blocks[i].in_len; isize[i] = blocks[i].isize; }
+    return (int64_t)blocks.size();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------------
+static int launch_inflate(fastf_ctx *ctx, int lanes, const u8 *comp, u64 comp_total, const u64 *in_off, const u32 *in_len, const u64 *out_off, const u32 *isize, u32 nblocks, u8 *out,
+                          u32 *status, cudaStream_t s)
+{
+    if (nblocks == 0) return 0;
+    if (lanes == 8) {
+        FASTF_LAUNCH(fastf_bgzf_inflate_kernel<8>, (nblocks + 3) / 4, 32, 0, s, comp, comp_total, in_off, in_len, out_off, isize, nblocks, out, status);
+    } else if (lanes == 16) {
+        FASTF_LAUNCH(fastf_bgzf_inflate_kernel<16>, (nblocks + 1) / 2, 32, 0, s, comp, comp_total, in_off, in_len, out_off, isize, nblocks, out, status);
+    } else {
+        FASTF_LAUNCH(fastf_bgzf_inflate_kernel<32>, nblocks, 32, 0, s, comp, comp_total, in_off, in_len, out_off, isize, nblocks, out, status);
+    }
+    CKL("bgzf_inflate");
+    return 0;
+}
+
+// exclusive scan of every row of a [nrows][n] u32 matrix in place; totals[nrows]
+static int launch_scan_rows(fastf_ctx *ctx, u32 *data, u64 n, u32 nrows, u32 *totals, cudaStream_t s)
+{
+    FASTF_LAUNCH(fastf_scan_rows_kernel, nrows, FASTF_SCAN_THREADS, 0, s, data, n, totals);
+    CKL("scan_rows");
+    return 0;
+}
+
+// ---- LSD radix sort over a chosen set of 8-bit digit windows --------------------------------------
+struct SortScratch {
+    DevBuf hist, totals, dbase;
+};
+// Windows: greedy cover of the bit positions set in `varying` (bits that differ between keys).
+static int plan_windows(u64 varying, u32 *shifts)
+{
+    int n = 0;
+    u32 b = 0;
+    while (b < 64) {
+        if ((varying >> b) & 1ull) { shifts[n++] = b; b += 8; } else b++;
+    }
+    return n;
+}
+// Sorts n keys (and optional u32 payload).  keys/alt (and vals/vals_alt) are ping-pong buffers of n elements;
+// *sorted_in_alt tells where the result ended up.
+static int sort_keys(fastf_ctx *ctx, SortScratch &S, u64 *keys, u64 *alt, u32 *vals, u32 *vals_alt, u64 n, const u32 *shifts, int npass, bool *sorted_in_alt, cudaStream_t s)
+{
+    *sorted_in_alt = false;
+    if (n == 0 || npass == 0) return 0;
+    if (n >= 0xffffffffull) return ctx_fail(ctx, "sort: %llu keys exceed the 2^32-1 limit of one device sort", (unsigned long long)n);
+    const u32 ntiles = (u32)((n + FASTF_RS_TILE - 1) / FASTF_RS_TILE);
+    TRY(dev_reserve(ctx, S.hist, (size_t)256 * ntiles * sizeof(u32)));
+    TRY(dev_reserve(ctx, S.totals, 256 * sizeof(u32)));
+    TRY(dev_reserve(ctx, S.dbase, 256 * sizeof(u32)));
+    u64 *src = keys, *dst = alt;
+    u32 *vsrc = vals, *vdst = vals_alt;
+    for (int p = 0; p < npass; p++) {
+        FASTF_LAUNCH(fastf_radix_hist_kernel, ntiles, FASTF_RS_THREADS, 0, s, (const u64 *)src, n, shifts[p], S.hist.as<u32>(), ntiles);
+        CKL("radix_hist");
+        TRY(launch_scan_rows(ctx, S.hist.as<u32>(), ntiles, 256, S.totals.as<u32>(), s));
+        FASTF_LAUNCH(fastf_radix_digit_base_kernel, 1, 256, 0, s, (const u32 *)S.totals.as<u32>(), S.dbase.as<u32>());
+        CKL("radix_digit_base");
+        if (vals) {
+            FASTF_LAUNCH(fastf_radix_scatter_kernel<true>, ntiles, FASTF_RS_THREADS, 0, s, (const u64 *)src, (const u32 *)vsrc, dst, vdst, n, shifts[p], (const u32 *)S.hist.as<u32>(),
+                         (const u32 *)S.dbase.as<u32>(), ntiles);
+        } else {
+            FASTF_LAUNCH(fastf_radix_scatter_kernel<false>, ntiles, FASTF_RS_THREADS, 0, s, (const u64 *)src, (const u32 *)nullptr, dst, (u32 *)nullptr, n, shifts[p],
+                         (const u32 *)S.hist.as<u32>(), (const u32 *)S.dbase.as<u32>(), ntiles);
+        }
+        CKL("radix_scatter");
+        std::swap(src, dst);
+        std::swap(vsrc, vdst);
+    }
+    *sorted_in_alt = (src == alt);
+    return 0;
+}
+static void sort_scratch_release(SortScratch &S) { dev_release(S.hist); dev_release(S.totals); dev_release(S.dbase); }
+
+// OR / AND of all keys -> which bit positions vary (device reduction, 16 bytes back)
+__global__ void __launch_bounds__(256) fastf_key_bits_kernel(const u64 *__restrict__ keys, u64 n, u64 *__restrict__ or_and)
+{
+    u64 o = 0, a = ~0ull;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) { u64 k = keys[i]; o |= k; a &= k; }
+    for (int d = 16; d; d >>= 1) { o |= __shfl_xor_sync(FASTF_FULL_MASK, o, d); a &= __shfl_xor_sync(FASTF_FULL_MASK, a, d); }
+    if ((threadIdx.x & 31u) == 0) { atomicOr((unsigned long long *)&or_and[0], (unsigned long long)o); atomicAnd((unsigned long long *)&or_and[1], (unsigned long long)a); }
+}
+
+// ---- run-length / segmented count over sorted keys ------------------------------------------------
+struct RleScratch {
+    DevBuf tile_counts, tile_totals, grp_key, grp_first, grp_dstart, grp_val, count, out_gene, out_cell;
+    PinBuf totals_host;
+};
+static void rle_scratch_release(RleScratch &R)
+{
+    dev_release(R.tile_counts); dev_release(R.tile_totals); dev_release(R.grp_key); dev_release(R.grp_first); dev_release(R.grp_dstart); dev_release(R.grp_val);
+    dev_release(R.count); dev_release(R.out_gene); dev_release(R.out_cell);
+    pin_release(R.totals_host);
+}
+// After this: R.grp_key/grp_first/grp_dstart(/grp_val)/count hold ngroups entries on device; with split_bits_gene > 0
+// R.out_gene / R.out_cell hold the split group key.
+static int rle_groups(fastf_ctx *ctx, RleScratch &R, const u64 *sorted, const u32 *vals, u64 n, u32 group_shift, u32 nn_bit, u32 split_bits_gene, u64 *ngroups_out, u64 *ndistinct_out,
+                      cudaStream_t s)
+{
+    *ngroups_out = 0;
+    if (ndistinct_out) *ndistinct_out = 0;
+    if (n == 0) return 0;
+    if (n >= 0xffffffffull) return ctx_fail(ctx, "rle: %llu keys exceed the 2^32-1 limit", (unsigned long long)n);
+    const u32 ntiles = (u32)((n + FASTF_RLE_TILE - 1) / FASTF_RLE_TILE);
+    TRY(dev_reserve(ctx, R.tile_counts, (size_t)2 * ntiles * sizeof(u32)));
+    TRY(dev_reserve(ctx, R.tile_totals, 2 * sizeof(u32)));
+    TRY(pin_reserve(ctx, R.totals_host, 2 * sizeof(u32)));
+    FASTF_LAUNCH(fastf_rle_count_kernel, ntiles, FASTF_RLE_THREADS, 0, s, sorted, n, group_shift, nn_bit, R.tile_counts.as<u32>(), ntiles);
+    CKL("rle_count");
+    TRY(launch_scan_rows(ctx, R.tile_counts.as<u32>(), ntiles, 2, R.tile_totals.as<u32>(), s));
+    CK(cudaMemcpyAsync(R.totals_host.p, R.tile_totals.p, 2 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const u32 ngroups = R.totals_host.as<u32>()[0], ndistinct = R.totals_host.as<u32>()[1];
+    TRY(dev_reserve(ctx, R.grp_key, (size_t)ngroups * sizeof(u64)));
+    TRY(dev_reserve(ctx, R.grp_first, (size_t)ngroups * sizeof(u32)));
+    TRY(dev_reserve(ctx, R.grp_dstart, (size_t)ngroups * sizeof(u32)));
+    TRY(dev_reserve(ctx, R.count, (size_t)ngroups * sizeof(u32)));
+    if (vals) TRY(dev_reserve(ctx, R.grp_val, (size_t)ngroups * sizeof(u32)));
+    if (split_bits_gene) { TRY(dev_reserve(ctx, R.out_gene, (size_t)ngroups * sizeof(u32))); TRY(dev_reserve(ctx, R.out_cell, (size_t)ngroups * sizeof(u32))); }
+    FASTF_LAUNCH(fastf_rle_emit_kernel, ntiles, FASTF_RLE_THREADS, 0, s, sorted, vals, n, group_shift, nn_bit, (const u32 *)R.tile_counts.as<u32>(), ntiles, R.grp_key.as<u64>(),
+                 R.grp_first.as<u32>(), R.grp_dstart.as<u32>(), vals ? R.grp_val.as<u32>() : (u32 *)nullptr);
+    CKL("rle_emit");
+    if (ngroups) {
+        FASTF_LAUNCH(fastf_rle_finish_kernel, (ngroups + 255) / 256, 256, 0, s, (const u32 *)R.grp_dstart.as<u32>(), ngroups, ndistinct, R.count.as<u32>(), (const u64 *)R.grp_key.as<u64>(),
+                     split_bits_gene, split_bits_gene ? R.out_gene.as<u32>() : (u32 *)nullptr, split_bits_gene ? R.out_cell.as<u32>() : (u32 *)nullptr);
+        CKL("rle_finish");
+    }
+    *ngroups_out = ngroups;
+    if (ndistinct_out) *ndistinct_out = ndistinct;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// string tables -> device
+// ---------------------------------------------------------------------------------------------------
+struct DevTable {
+    DevBuf slots, pool;
+    FastfStrTableView view;
+    u32 count = 0;
+};
+static int table_upload(fastf_ctx *ctx, DevTable &T, const char *keys, const u32 *off, u32 n)
+{
+    FastfStrTableHost H;
+    H.init(n);
+    for (u32 i = 0; i < n; i++) {
+        // first insertion wins; the reference's hash_table_insert refuses duplicates (src/hashtable.c:70-95)
+        H.insert(keys + off[i], off[i + 1] - off[i], i + 1);
+    }
+    H.finish();
+    TRY(dev_reserve(ctx, T.slots, H.slots.size() * sizeof(FastfStrSlot)));
+    TRY(dev_reserve(ctx, T.pool, H.pool.size()));
+    CK(cudaMemcpy(T.slots.p, H.slots.data(), H.slots.size() * sizeof(FastfStrSlot), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(T.pool.p, H.pool.data(), H.pool.size(), cudaMemcpyHostToDevice));
+    T.view.slots = T.slots.as<FastfStrSlot>();
+    T.view.pool = T.pool.as<uint8_t>();
+    T.view.mask = H.mask;
+    memcpy(T.view.pw1, H.pw1, sizeof H.pw1);
+    memcpy(T.view.pw2, H.pw2, sizeof H.pw2);
+    T.count = n;
+    return 0;
+}
+static u32 bits_for(u32 max_value)
+{
+    u32 b = 1;
+    while (b < 32 && (max_value >> b)) b++;
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// chunked BGZF -> inflated bytes machinery shared by bam2db and freq
+// ---------------------------------------------------------------------------------------------------
+struct BlockIndexDev {   // per-chunk block index on device (one allocation, 8-byte fields first)
+    DevBuf buf;
+    PinBuf host;
+    u32 cap_blocks = 0;
+    u64 *in_off, *out_off, *stage_off, *dst_base;
+    u32 *in_len, *isize, *nrec, *ncbv, *st_infl, *st_parse;
+    u64 *h_in_off, *h_out_off, *h_stage_off;
+    u32 *h_in_len, *h_isize;
+};
+static size_t index_bytes_dev(u32 nb) { return (size_t)nb * (4 * sizeof(u64) + 6 * sizeof(u32)); }
+static size_t index_bytes_up(u32 nb) { return (size_t)nb * (3 * sizeof(u64) + 2 * sizeof(u32)); }
+static int index_reserve(fastf_ctx *ctx, BlockIndexDev &I, u32 nb)
+{
+    if (nb <= I.cap_blocks) return 0;
+    u32 cap = std::max(nb, I.cap_blocks * 2);
+    cap = (cap + 63u) & ~63u;
+    TRY(dev_reserve(ctx, I.buf, index_bytes_dev(cap)));
+    TRY(pin_reserve(ctx, I.host, index_bytes_up(cap)));
+    I.cap_blocks = cap;
+    // upload region first (in_off, out_off, stage_off, in_len, isize), device-only region after
+    u8 *d = I.buf.as<u8>();
+    I.in_off = (u64 *)d; d += (size_t)cap * 8;
+    I.out_off = (u64 *)d; d += (size_t)cap * 8;
+    I.stage_off = (u64 *)d; d += (size_t)cap * 8;
+    I.in_len = (u32 *)d; d += (size_t)cap * 4;
+    I.isize = (u32 *)d; d += (size_t)cap * 4;
+    I.dst_base = (u64 *)d; d += (size_t)cap * 8;
+    I.nrec = (u32 *)d; d += (size_t)cap * 4;
+    I.ncbv = (u32 *)d; d += (size_t)cap * 4;
+    I.st_infl = (u32 *)d; d += (size_t)cap * 4;
+    I.st_parse = (u32 *)d;
+    u8 *h = I.host.as<u8>();
+    I.h_in_off = (u64 *)h; h += (size_t)cap * 8;
+    I.h_out_off = (u64 *)h; h += (size_t)cap * 8;
+    I.h_stage_off = (u64 *)h; h += (size_t)cap * 8;
+    I.h_in_len = (u32 *)h; h += (size_t)cap * 4;
+    I.h_isize = (u32 *)h;
+    return 0;
+}
+static int index_upload(fastf_ctx *ctx, BlockIndexDev &I, cudaStream_t s)
+{
+    CK(cudaMemcpyAsync(I.buf.p, I.host.p, index_bytes_up(I.cap_blocks), cudaMemcpyHostToDevice, s));
+    return 0;
+}
+static void index_release(BlockIndexDev &I) { dev_release(I.buf); pin_release(I.host); I.cap_blocks = 0; }
+
+// ---------------------------------------------------------------------------------------------------
+// bam2db job
+// ---------------------------------------------------------------------------------------------------
+#define FASTF_DEFAULT_CHUNK (512ull << 20)
+#define FASTF_MAX_BLOCKS_PER_CHUNK (1u << 22)
+
+struct ChunkSlot {
+    BlockIndexDev idx;
+    DevBuf comp;          // compressed bytes of the chunk (host feeds only)
+    DevBuf stage;         // per-block candidate staging
+    PinBuf snap;          // counters snapshot {n_records, n_candidates, status_or, chunk_candidates}
+    cudaEvent_t ev_copy = nullptr, ev_done = nullptr;
+    u32 nblocks = 0;
+    bool pending = false; // parse launched, gather not yet
+};
+
+struct fastf_bam2db_job {
+    fastf_ctx *ctx;
+    fastf_bam2db_params prm;
+    FastfKeyLayout L;
+    DevTable cells, genes;
+    int lanes;
+    u64 chunk_bytes;
+    ChunkSlot slot[2];
+    u32 next_slot = 0;
+    DevBuf infl;              // inflated bytes of the chunk in flight
+    DevBuf counters;          // u64[4]: n_records, n_candidates, status_or, (unused)
+    DevBuf hdr_off;           // u64: offset of the first alignment record inside the current chunk
+    DevBuf cand;              // all candidates (CB-valid reads) in file order
+    u64 cand_cap = 0;
+    u64 n_records = 0, n_cand = 0;   // host copies after the last finalized chunk
+    u32 status = 0;
+    bool header_done = false;
+    std::vector<u8> carry;    // partial BGZF block left over by fastf_bam2db_feed
+    // MT19937 keep bits
+    DevBuf mt_state, keepbits;
+    u64 mt_pairs_done = 0;
+    cudaEvent_t ev_mt = nullptr;
+    // sampling / sort / count
+    bool sampled_done = false;
+    DevBuf tile_valid, tile_tot, sample_counters, kept, orand;
+    PinBuf small_host;
+    u64 n_sampled = 0, n_valid = 0;
+    SortScratch sortS;
+    RleScratch rleS;
+    // stats
+    u64 n_blocks = 0, comp_bytes = 0, infl_bytes = 0;
+    u32 launches0 = 0;
+    Timer t_infl[2], t_parse[2], t_gather[2], t_mt[2], t_sample, t_sort, t_count;
+    u32 mt_launches = 0;
+    cudaEvent_t ev_first = nullptr, ev_last = nullptr;
+    bool first_recorded = false;
+    float ms_inflate = 0, ms_parse = 0, ms_gather = 0, ms_mt = 0, ms_sample = 0, ms_sort = 0, ms_count = 0;
+};
+
+static u32 stage_cap_for(u32 isize) { return isize / 36u + 1u; }   // a record is >= 4 + 32 bytes
+
+extern "C" void fastf_bam2db_job_free(fastf_bam2db_job *job)
+{
+    if (!job) return;
+    fastf_ctx *ctx = job->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->compute);
+    cudaStreamSynchronize(ctx->copy);
+    cudaStreamSynchronize(ctx->mt);
+    for (int i = 0; i < 2; i++) {
+        ChunkSlot &S = job->slot[i];
+        index_release(S.idx); dev_release(S.comp); dev_release(S.stage); pin_release(S.snap);
+        if (S.ev_copy) cudaEventDestroy(S.ev_copy);
+        if (S.ev_done) cudaEventDestroy(S.ev_done);
+        job->t_infl[i].destroy(); job->t_parse[i].destroy(); job->t_gather[i].destroy();
+    }
+    job->t_mt[0].destroy(); job->t_mt[1].destroy(); job->t_sample.destroy(); job->t_sort.destroy(); job->t_count.destroy();
+    if (job->ev_mt) cudaEventDestroy(job->ev_mt);
+    if (job->ev_first) cudaEventDestroy(job->ev_first);
+    if (job->ev_last) cudaEventDestroy(job->ev_last);
+    dev_release(job->cells.slots); dev_release(job->cells.pool); dev_release(job->genes.slots); dev_release(job->genes.pool);
+    dev_release(job->infl); dev_release(job->counters); dev_release(job->hdr_off); dev_release(job->cand); dev_release(job->mt_state); dev_release(job->keepbits);
+    dev_release(job->tile_valid); dev_release(job->tile_tot); dev_release(job->sample_counters); dev_release(job->kept); dev_release(job->orand);
+    pin_release(job->small_host);
+    sort_scratch_release(job->sortS);
+    rle_scratch_release(job->rleS);
+    delete job;
+}
+
+extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, fastf_bam2db_job **out)
+{
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    if (!p || (p->n_cells && (!p->cell_keys || !p->cell_off)) || (p->n_genes && (!p->gene_keys || !p->gene_off))) return ctx_fail(ctx, "bam2db_begin: null table pointers");
+    if (p->keep_threshold > 4294967296ull) return ctx_fail(ctx, "bam2db_begin: keep_threshold > 2^32");
+    fastf_bam2db_job *job = new fastf_bam2db_job();
+    job->ctx = ctx;
+    job->prm = *p;
+    job->launches0 = ctx->launches;
+    job->lanes = (p->inflate_lanes == 8 || p->inflate_lanes == 16 || p->inflate_lanes == 32) ? (int)p->inflate_lanes : 32;
+    job->chunk_bytes = p->chunk_inflated_bytes ? std::max<u64>(p->chunk_inflated_bytes, 1u << 20) : FASTF_DEFAULT_CHUNK;
+    FastfKeyLayout &L = job->L;
+    L.umi_max_bytes = p->umi_max_bytes ? p->umi_max_bytes : 3;
+    if (L.umi_max_bytes > 4) { delete job; return ctx_fail(ctx, "bam2db_begin: umi_max_bytes must be 1..4 (UMIs up to 16 bases)"); }
+    L.bits_umi = 1 + 8 * L.umi_max_bytes + 3;
+    L.bits_gene = bits_for(p->n_genes);
+    L.bits_cell = bits_for(p->n_cells);
+    if (L.bits_cell + L.bits_gene + L.bits_umi > 63) { delete job; return ctx_fail(ctx, "bam2db_begin: key layout needs %u bits (> 63)", L.bits_cell + L.bits_gene + L.bits_umi); }
+    int rc = 0;
+    rc = rc || table_upload(ctx, job->cells, p->cell_keys, p->cell_off, p->n_cells);
+    rc = rc || table_upload(ctx, job->genes, p->gene_keys, p->gene_off, p->n_genes);
+    rc = rc || dev_reserve(ctx, job->counters, 4 * sizeof(u64));
+    rc = rc || dev_reserve(ctx, job->hdr_off, sizeof(u64));
+    rc = rc || dev_reserve(ctx, job->mt_state, 624 * sizeof(u32));
+    rc = rc || dev_reserve(ctx, job->sample_counters, 2 * sizeof(u64));
+    rc = rc || dev_reserve(ctx, job->orand, 2 * sizeof(u64));
+    rc = rc || pin_reserve(ctx, job->small_host, 64);
+    for (int i = 0; i < 2 && !rc; i++) {
+        rc = rc || pin_reserve(ctx, job->slot[i].snap, 4 * sizeof(u64));
+        rc = rc || cudaEventCreateWithFlags(&job->slot[i].ev_copy, cudaEventDisableTiming) != cudaSuccess;
+        rc = rc || cudaEventCreateWithFlags(&job->slot[i].ev_done, cudaEventDisableTiming) != cudaSuccess;
+        rc = rc || job->t_infl[i].init() || job->t_parse[i].init() || job->t_gather[i].init();
+    }
+    rc = rc || job->t_mt[0].init() || job->t_mt[1].init() || job->t_sample.init() || job->t_sort.init() || job->t_count.init();
+    rc = rc || cudaEventCreateWithFlags(&job->ev_mt, cudaEventDisableTiming) != cudaSuccess;
+    rc = rc || cudaEventCreate(&job->ev_first) != cudaSuccess || cudaEventCreate(&job->ev_last) != cudaSuccess;
+    if (!rc) rc = cudaMemsetAsync(job->counters.p, 0, 4 * sizeof(u64), ctx->compute) != cudaSuccess;
+    if (rc) { if (!ctx->err[0]) ctx_fail(ctx, "bam2db_begin: resource setup failed"); fastf_bam2db_job_free(job); return 1; }
+    *out = job;
+    return 0;
+}
+
+// Extend the keep-bit stream so that it covers stream indices [0, n_draws).  Runs on the mt stream.
+static int mt_extend(fastf_bam2db_job *job, u64 n_draws)
+{
+    fastf_ctx *ctx = job->ctx;
+    const u64 pairs = (n_draws + 1247) / 1248;
+    if (pairs <= job->mt_pairs_done) return 0;
+    const size_t need = (size_t)pairs * 39 * sizeof(u32);
+    if (need > job->keepbits.cap) {
+        // grow geometrically; the copy keeps the bits produced so far
+        size_t want = std::max(need + need / 2, (size_t)(64u << 20));
+        TRY(dev_reserve(ctx, job->keepbits, want, (size_t)job->mt_pairs_done * 39 * sizeof(u32), ctx->mt));
+    }
+    Timer &tm = job->t_mt[job->mt_launches++ & 1u];   // the launch two extensions back has long finished
+    tm.collect(&job->ms_mt);
+    tm.start(ctx->mt);
+    FASTF_LAUNCH(fastf_mt19937_kernel, 1, FASTF_MT_THREADS, 0, ctx->mt, job->prm.seed, job->mt_state.as<u32>(), job->mt_pairs_done, pairs - job->mt_pairs_done, job->prm.keep_threshold,
+                 (u32 *)nullptr, job->keepbits.as<u32>());
+    CKL("mt19937");
+    tm.stop(ctx->mt);
+    job->mt_pairs_done = pairs;
+    return 0;
+}
+
+// Wait for the slot's counters, size the candidate array, gather the slot's staged candidates.
+static int finalize_slot(fastf_bam2db_job *job, u32 si)
+{
+    fastf_ctx *ctx = job->ctx;
+    ChunkSlot &S = job->slot[si];
+    if (!S.pending) return 0;
+    CK(cudaEventSynchronize(S.ev_done));
+    const u64 *snap = S.snap.as<u64>();
+    const u64 n_records = snap[0], n_cand = snap[1];
+    job->status |= (u32)snap[2];
+    if (job->status) {
+        char buf[256];
+        return ctx_fail(ctx, "bam2db: malformed input in chunk ending at block %llu: %s", (unsigned long long)job->n_blocks, status_string(job->status, buf, sizeof buf));
+    }
+    if (n_cand > job->cand_cap) {
+        u64 want = std::max<u64>(n_cand + n_cand / 2, 1u << 20);
+        TRY(dev_reserve(ctx, job->cand, want * sizeof(u64), job->n_cand * sizeof(u64), ctx->compute));
+        job->cand_cap = job->cand.cap / sizeof(u64);
+    }
+    job->t_gather[si].collect(&job->ms_gather);
+    job->t_gather[si].start(ctx->compute);
+    if (S.nblocks) {
+        FASTF_LAUNCH(fastf_stage_gather_kernel, (S.nblocks + 7) / 8, 256, 0, ctx->compute, (const u64 *)S.stage.as<u64>(), (const u64 *)S.idx.stage_off, (const u32 *)S.idx.ncbv,
+                     (const u64 *)S.idx.dst_base, S.nblocks, job->cand.as<u64>());
+        CKL("stage_gather");
+    }
+    job->t_gather[si].stop(ctx->compute);
+    CK(cudaEventRecord(job->ev_last, ctx->compute));
+    job->n_records = n_records;
+    job->n_cand = n_cand;
+    S.pending = false;
+    // let the MT19937 stream run ahead on its own stream (single-GPU case: ordinal base 0)
+    TRY(mt_extend(job, job->prm.d0 + n_cand));
+    return 0;
+}
+
+// One chunk: blocks[b0, b1) with payload offsets relative to `comp_dev` (device) -- or, when host_src != null,
+// relative to host_src, which is first copied into the slot's comp buffer.
+static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb, const u8 *comp_dev, u64 comp_total, const u8 *host_src, u64 host_bytes)
+{
+    fastf_ctx *ctx = job->ctx;
+    const u32 si = job->next_slot;
+    ChunkSlot &S = job->slot[si];
+    // the slot was used two chunks ago: its gather must have been issued (finalize) before we reuse its buffers
+    TRY(finalize_slot(job, si));
+    TRY(index_reserve(ctx, S.idx, nb));
+    u64 out_total = 0, stage_total = 0;
+    for (u32 i = 0; i < nb; i++) {
+        S.idx.h_in_off[i] = blocks[i].in_off;
+        S.idx.h_in_len[i] = blocks[i].in_len;
+        S.idx.h_isize[i] = blocks[i].isize;
+        S.idx.h_out_off[i] = out_total;
+        S.idx.h_stage_off[i] = stage_total;
+        out_total += blocks[i].isize;
+        stage_total += stage_cap_for(blocks[i].isize);
+    }
+    if (host_src) {
+        const u64 padded = (host_bytes + 3) & ~3ull;
+        TRY(dev_reserve(ctx, S.comp, padded + 16));
+        // the previous user of S.comp (chunk i-2) finished inflating: its ev_done was waited for in finalize_slot
+        CK(cudaMemcpyAsync(S.comp.p, host_src, host_bytes, cudaMemcpyHostToDevice, ctx->copy));
+        CK(cudaEventRecord(S.ev_copy, ctx->copy));
+        CK(cudaStreamWaitEvent(ctx->compute, S.ev_copy, 0));
+        comp_dev = S.comp.as<u8>();
+        comp_total = padded;
+    }
+    // infl / stage are written by this chunk; infl is shared by both slots (same stream -> ordered)
+    TRY(dev_reserve(ctx, job->infl, out_total + 64));
+    TRY(dev_reserve(ctx, S.stage, stage_total * sizeof(u64) + 64));
+    if (!job->first_recorded) { CK(cudaEventRecord(job->ev_first, ctx->compute)); job->first_recorded = true; }
+    TRY(index_upload(ctx, S.idx, ctx->compute));
+    job->t_infl[si].collect(&job->ms_inflate);
+    job->t_infl[si].start(ctx->compute);
+    TRY(launch_inflate(ctx, job->lanes, comp_dev, comp_total, S.idx.in_off, S.idx.in_len, S.idx.out_off, S.idx.isize, nb, job->infl.as<u8>(), S.idx.st_infl, ctx->compute));
+    job->t_infl[si].stop(ctx->compute);
+    job->t_parse[si].collect(&job->ms_parse);
+    job->t_parse[si].start(ctx->compute);
+    if (!job->header_done) {
+        FASTF_LAUNCH(fastf_bam_header_kernel, 1, 32, 0, ctx->compute, (const u8 *)job->infl.as<u8>(), out_total, job->hdr_off.as<u64>(), (u32 *)(job->counters.as<u64>() + 2));
+        CKL("bam_header");
+        job->header_done = true;
+    } else {
+        CK(cudaMemsetAsync(job->hdr_off.p, 0, sizeof(u64), ctx->compute));
+    }
+    if (nb) {
+        FASTF_LAUNCH(fastf_bam_parse_kernel, (nb + FASTF_PARSE_WARPS - 1) / FASTF_PARSE_WARPS, FASTF_PARSE_WARPS * 32, 0, ctx->compute, (const u8 *)job->infl.as<u8>(),
+                     (const u64 *)S.idx.out_off, (const u32 *)S.idx.isize, nb, (const u64 *)job->hdr_off.as<u64>(), job->cells.view, job->genes.view, job->L, (const u64 *)S.idx.stage_off,
+                     S.stage.as<u64>(), S.idx.nrec, S.idx.ncbv, S.idx.st_parse);
+        CKL("bam_parse");
+    }
+    FASTF_LAUNCH(fastf_chunk_counts_kernel, 1, FASTF_SCAN_THREADS, 0, ctx->compute, (const u32 *)S.idx.nrec, (const u32 *)S.idx.ncbv, (const u32 *)S.idx.st_infl, (const u32 *)S.idx.st_parse, nb,
+                 S.idx.dst_base, job->counters.as<u64>());
+    CKL("chunk_counts");
+    job->t_parse[si].stop(ctx->compute);
+    CK(cudaMemcpyAsync(S.snap.p, job->counters.p, 4 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->compute));
+    CK(cudaEventRecord(S.ev_done, ctx->compute));
+    S.nblocks = nb;
+    S.pending = true;
+    job->n_blocks += nb;
+    job->infl_bytes += out_total;
+    job->next_slot ^= 1u;
+    // now that this chunk is queued, gather the previous one (its counters are long done)
+    TRY(finalize_slot(job, si ^ 1u));
+    return 0;
+}
+
+// split a run of indexed blocks into chunks and run them
+static int run_blocks(fastf_bam2db_job *job, const std::vector<FastfBgzfBlock> &blocks, const u8 *comp_dev, u64 comp_total, const u8 *host_base)
+{
+    size_t i = 0;
+    const size_t n = blocks.size();
+    std::vector<FastfBgzfBlock> rel;
+    while (i < n) {
+        size_t j = i;
+        u64 infl = 0;
+        const u64 byte0 = blocks[i].in_off;
+        while (j < n && (j == i || (infl + blocks[j].isize <= job->chunk_bytes && blocks[j].in_off + blocks[j].in_len - byte0 <= job->chunk_bytes && j - i < FASTF_MAX_BLOCKS_PER_CHUNK))) {
+            infl += blocks[j].isize;
+            j++;
+        }
+        if (host_base) {
+            // copy [start of first payload rounded down to 4, end of last payload) and rebase the offsets
+            const u64 lo = byte0 & ~3ull, hi = blocks[j - 1].in_off + blocks[j - 1].in_len;
+            rel.assign(blocks.begin() + i, blocks.begin() + j);
+            for (auto &b : rel) b.in_off -= lo;
+            TRY(run_chunk(job, rel.data(), (u32)(j - i), nullptr, 0, host_base + lo, hi - lo));
+        } else {
+            TRY(run_chunk(job, blocks.data() + i, (u32)(j - i), comp_dev, comp_total, nullptr, 0));
+        }
+        i = j;
+    }
+    return 0;
+}
+
+extern "C" int fastf_bam2db_feed(fastf_bam2db_job *job, const void *host_bytes, size_t n)
+{
+    fastf_ctx *ctx = job->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (job->sampled_done) return ctx_fail(ctx, "bam2db_feed: job already sampled");
+    const u8 *p = (const u8 *)host_bytes;
+    job->comp_bytes += n;
+    std::vector<FastfBgzfBlock> blocks;
+    // 1. complete a partial block left over from the previous call
+    while (!job->carry.empty() && n) {
+        std::vector<u8> &c = job->carry;
+        size_t want = 18;
+        if (c.size() >= 18) {
+            blocks.clear();
+            size_t used = 0;
+            int rc = fastf_bgzf_index(c.data(), c.size(), 0, blocks, &used);
+            if (rc != FASTF_BGZF_OK && rc != FASTF_BGZF_NEED_MORE) return ctx_fail(ctx, "bam2db_feed: not a BGZF block (index error %d)", rc);
+            if (!blocks.empty()) {
+                // run the completed block(s) out of the carry buffer (pageable copy; rare path).  The copy must finish
+                // before the carry buffer is edited, so drain the copy stream here.
+                TRY(run_blocks(job, blocks, nullptr, 0, c.data()));
+                CK(cudaStreamSynchronize(ctx->copy));
+                c.erase(c.begin(), c.begin() + used);
+                continue;
+            }
+            // header visible: total block size = BSIZE+1 (read it the same way the indexer does)
+            u32 xlen = (u32)c[10] | ((u32)c[11] << 8);
+            want = 12 + (size_t)xlen;
+            if (c.size() >= want) {
+                u32 bsize = 0;
+                for (u32 x = 0; x + 4 <= xlen;) {
+                    const u8 *sf = c.data() + 12 + x;
+                    u32 slen = (u32)sf[2] | ((u32)sf[3] << 8);
+                    if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && x + 6 <= xlen) bsize = ((u32)sf[4] | ((u32)sf[5] << 8)) + 1;
+                    x += 4 + slen;
+                }
+                if (!bsize) return ctx_fail(ctx, "bam2db_feed: gzip member without a BGZF BC field");
+                want = bsize;
+            }
+        }
+        size_t take = std::min(n, want > c.size() ? want - c.size() : (size_t)1);
+        c.insert(c.end(), p, p + take);
+        p += take;
+        n -= take;
+    }
+    if (!job->carry.empty()) {
+        // n == 0: maybe the carry became a whole block exactly
+        blocks.clear();
+        size_t used = 0;
+        int rc = fastf_bgzf_index(job->carry.data(), job->carry.size(), 0, blocks, &used);
+        if (rc != FASTF_BGZF_OK && rc != FASTF_BGZF_NEED_MORE) return ctx_fail(ctx, "bam2db_feed: not a BGZF block (index error %d)", rc);
+        if (!blocks.empty()) {
+            TRY(run_blocks(job, blocks, nullptr, 0, job->carry.data()));
+            CK(cudaStreamSynchronize(ctx->copy));
+            job->carry.erase(job->carry.begin(), job->carry.begin() + used);
+        }
+        return 0;
+    }
+    if (!n) return 0;
+    // 2. whole blocks straight out of the caller's buffer
+    blocks.clear();
+    size_t used = 0;
+    int rc = fastf_bgzf_index(p, n, 0, blocks, &used);
+    if (rc != FASTF_BGZF_OK && rc != FASTF_BGZF_NEED_MORE) return ctx_fail(ctx, "bam2db_feed: not a BGZF stream at byte %zu (index error %d)", used, rc);
+    if (!blocks.empty()) TRY(run_blocks(job, blocks, nullptr, 0, p));
+    // 3. keep the tail.  The caller may reuse its buffer after we return: wait for the copies.
+    if (used < n) job->carry.assign(p + used, p + n);
+    CK(cudaStreamSynchronize(ctx->copy));
+    return 0;
+}
+
+extern "C" int fastf_bam2db_feed_device(fastf_bam2db_job *job, const void *dev_bytes, size_t nbytes, const uint64_t *in_off, const uint32_t *in_len, const uint32_t *isize, uint64_t nblocks)
+{
+    fastf_ctx *ctx = job->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (job->sampled_done) return ctx_fail(ctx, "bam2db_feed_device: job already sampled");
+    if (((uintptr_t)dev_bytes & 3u) != 0) return ctx_fail(ctx, "bam2db_feed_device: dev_bytes must be 4-byte aligned");
+    std::vector<FastfBgzfBlock> blocks(nblocks);
+    for (u64 i = 0; i < nblocks; i++) {
+        if (in_off[i] + in_len[i] + 8 > nbytes || isize[i] > 65536) return ctx_fail(ctx, "bam2db_feed_device: block %llu outside the buffer", (unsigned long long)i);
+        blocks[i].in_off = in_off[i]; blocks[i].in_len = in_len[i]; blocks[i].isize = isize[i]; blocks[i].crc32 = 0;
+    }
+    job->comp_bytes += nbytes;
+    return run_blocks(job, blocks, (const u8 *)dev_bytes, nbytes & ~(u64)3, nullptr);
+}
+
+static int drain_chunks(fastf_bam2db_job *job)
+{
+    fastf_ctx *ctx = job->ctx;
+    if (!job->carry.empty()) return ctx_fail(ctx, "bam2db: input ends inside a BGZF block (%zu trailing bytes)", job->carry.size());
+    TRY(finalize_slot(job, job->next_slot));        // older one first (file order of the gathers does not matter, bases are absolute)
+    TRY(finalize_slot(job, job->next_slot ^ 1u));
+    return 0;
+}
+
+extern "C" int fastf_bam2db_counts(fastf_bam2db_job *job, uint64_t *n_records, uint64_t *n_cb_valid)
+{
+    fastf_ctx *ctx = job->ctx;
+    CK(cudaSetDevice(ctx->device));
+    TRY(drain_chunks(job));
+    if (n_records) *n_records = job->n_records;
+    if (n_cb_valid) *n_cb_valid = job->n_cand;
+    return 0;
+}
+
+extern "C" int fastf_bam2db_sample(fastf_bam2db_job *job, uint64_t ordinal_base)
+{
+    fastf_ctx *ctx = job->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (job->sampled_done) return ctx_fail(ctx, "bam2db_sample: already sampled");
+    TRY(drain_chunks(job));
+    const u64 n = job->n_cand;
+    const u64 first_draw = job->prm.d0 + ordinal_base;
+    job->n_sampled = job->n_valid = 0;
+    if (n >= 0xffffffffull) return ctx_fail(ctx, "bam2db_sample: %llu CB-valid reads exceed the 2^32-1 limit of one device; shard over more GPUs", (unsigned long long)n);
+    if (n) {
+        TRY(mt_extend(job, first_draw + n));
+        CK(cudaEventRecord(job->ev_mt, ctx->mt));
+        CK(cudaStreamWaitEvent(ctx->compute, job->ev_mt, 0));
+        const u32 ntiles = (u32)((n + FASTF_SAMPLE_TILE - 1) / FASTF_SAMPLE_TILE);
+        TRY(dev_reserve(ctx, job->tile_valid, (size_t)ntiles * sizeof(u32)));
+        TRY(dev_reserve(ctx, job->tile_tot, sizeof(u32)));
+        CK(cudaMemsetAsync(job->sample_counters.p, 0, 2 * sizeof(u64), ctx->compute));
+        job->t_sample.start(ctx->compute);
+        FASTF_LAUNCH(fastf_sample_count_kernel, ntiles, FASTF_SAMPLE_THREADS, 0, ctx->compute, (const u64 *)job->cand.as<u64>(), n, (const u32 *)job->keepbits.as<u32>(), first_draw,
+                     job->tile_valid.as<u32>(), job->sample_counters.as<u64>());
+        CKL("sample_count");
+        TRY(launch_scan_rows(ctx, job->tile_valid.as<u32>(), ntiles, 1, job->tile_tot.as<u32>(), ctx->compute));
+        CK(cudaMemcpyAsync(job->small_host.p, job->sample_counters.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->compute));
+        CK(cudaStreamSynchronize(ctx->compute));
+        job->n_sampled = job->small_host.as<u64>()[0];
+        job->n_valid = job->small_host.as<u64>()[1];
+        TRY(dev_reserve(ctx, job->kept, std::max<u64>(job->n_valid, 1) * sizeof(u64)));
+        FASTF_LAUNCH(fastf_sample_scatter_kernel, ntiles, FASTF_SAMPLE_THREADS, 0, ctx->compute, (const u64 *)job->cand.as<u64>(), n, (const u32 *)job->keepbits.as<u32>(), first_draw,
+                     (const u32 *)job->tile_valid.as<u32>(), job->kept.as<u64>());
+        CKL("sample_scatter");
+        job->t_sample.stop(ctx->compute);
+        CK(cudaEventRecord(job->ev_last, ctx->compute));
+    }
+    job->sampled_done = true;
+    return 0;
+}
+
+extern "C" int fastf_bam2db_kept_device(fastf_bam2db_job *job, uint64_t **dev_keys, uint64_t *n)
+{
+    fastf_ctx *ctx = job->ctx;
+    if (!job->sampled_done) return ctx_fail(ctx, "bam2db_kept_device: call fastf_bam2db_sample first");
+    *dev_keys = job->kept.as<u64>();
+    *n = job->n_valid;
+    return 0;
+}
+
+extern "C" int fastf_bam2db_key_layout(fastf_bam2db_job *job, uint32_t *bits_cell, uint32_t *bits_gene, uint32_t *bits_umi)
+{
+    *bits_cell = job->L.bits_cell; *bits_gene = job->L.bits_gene; *bits_umi = job->L.bits_umi;
+    return 0;
+}
+
+// sorted-unaware front half shared by finish and the device-level entry points: figure out which bits vary
+static int varying_bits(fastf_ctx *ctx, DevBuf &orand, PinBuf &host, const u64 *keys, u64 n, u64 *varying, cudaStream_t s)
+{
+    u64 init[2] = {0ull, ~0ull};
+    CK(cudaMemcpyAsync(orand.p, init, sizeof init, cudaMemcpyHostToDevice, s));
+    u32 grid = (u32)std::min<u64>((n + 255) / 256, 148 * 8);
+    FASTF_LAUNCH(fastf_key_bits_kernel, grid ? grid : 1, 256, 0, s, keys, n, orand.as<u64>());
+    CKL("key_bits");
+    CK(cudaMemcpyAsync(host.p, orand.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *varying = host.as<u64>()[0] ^ host.as<u64>()[1];
+    return 0;
+}
+
+static int coo_to_host(fastf_ctx *ctx, RleScratch &R, u64 nnz, u32 **m_gene, u32 **m_cell, u32 **m_count, cudaStream_t s)
+{
+    *m_gene = (u32 *)malloc(std::max<u64>(nnz, 1) * sizeof(u32));
+    *m_cell = (u32 *)malloc(std::max<u64>(nnz, 1) * sizeof(u32));
+    *m_count = (u32 *)malloc(std::max<u64>(nnz, 1) * sizeof(u32));
+    if (!*m_gene || !*m_cell || !*m_count) return ctx_fail(ctx, "out of host memory for %llu COO rows", (unsigned long long)nnz);
+    if (nnz) {
+        CK(cudaMemcpyAsync(*m_gene, R.out_gene.p, nnz * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(*m_cell, R.out_cell.p, nnz * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(*m_count, R.count.p, nnz * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+extern "C" int fastf_bam2db_finish(fastf_bam2db_job *job, fastf_bam2db_result *res)
+{
+    fastf_ctx *ctx = job->ctx;
+    CK(cudaSetDevice(ctx->device));
+    memset(res, 0, sizeof *res);
+    if (!job->sampled_done) TRY(fastf_bam2db_sample(job, 0));
+    const u64 n = job->n_valid;
+    const FastfKeyLayout &L = job->L;
+    if (job->prm.want_rows) {
+        res->row_keys = (u64 *)malloc(std::max<u64>(n, 1) * sizeof(u64));
+        if (!res->row_keys) return ctx_fail(ctx, "out of host memory for %llu rows", (unsigned long long)n);
+        if (n) CK(cudaMemcpyAsync(res->row_keys, job->kept.p, n * sizeof(u64), cudaMemcpyDeviceToHost, ctx->compute));
+        res->n_rows = n;
+    }
+    u64 nnz = 0;
+    if (n) {
+        u64 varying = 0;
+        job->t_sort.start(ctx->compute);
+        TRY(varying_bits(ctx, job->orand, job->small_host, job->kept.as<u64>(), n, &varying, ctx->compute));
+        u32 shifts[8];
+        const int npass = plan_windows(varying, shifts);
+        bool in_alt = false;
+        // the candidate array is dead after sampling and at least as large as `kept`: reuse it as the ping-pong buffer
+        TRY(sort_keys(ctx, job->sortS, job->kept.as<u64>(), job->cand.as<u64>(), nullptr, nullptr, n, shifts, npass, &in_alt, ctx->compute));
+        job->t_sort.stop(ctx->compute);
+        const u64 *sorted = in_alt ? job->cand.as<u64>() : job->kept.as<u64>();
+        job->t_count.start(ctx->compute);
+        TRY(rle_groups(ctx, job->rleS, sorted, nullptr, n, L.bits_umi, L.bits_umi - 1, L.bits_gene, &nnz, nullptr, ctx->compute));
+        job->t_count.stop(ctx->compute);
+        CK(cudaEventRecord(job->ev_last, ctx->compute));
+    }
+    TRY(coo_to_host(ctx, job->rleS, nnz, &res->m_gene, &res->m_cell, &res->m_count, ctx->compute));
+    CK(cudaStreamSynchronize(ctx->compute));
+    CK(cudaStreamSynchronize(ctx->mt));
+    res->total = job->n_records;
+    res->cb_valid = job->n_cand;
+    res->sampled = job->n_sampled;
+    res->valid = job->n_valid;
+    res->nnz = nnz;
+    res->bits_cell = L.bits_cell; res->bits_gene = L.bits_gene; res->bits_umi = L.bits_umi; res->umi_max_bytes = L.umi_max_bytes;
+    res->n_blocks = job->n_blocks; res->compressed_bytes = job->comp_bytes; res->inflated_bytes = job->infl_bytes;
+    res->status = job->status;
+    for (int i = 0; i < 2; i++) { job->t_infl[i].collect(&job->ms_inflate); job->t_parse[i].collect(&job->ms_parse); job->t_gather[i].collect(&job->ms_gather); }
+    job->t_mt[0].collect(&job->ms_mt); job->t_mt[1].collect(&job->ms_mt); job->t_sample.collect(&job->ms_sample); job->t_sort.collect(&job->ms_sort); job->t_count.collect(&job->ms_count);
+    res->ms_inflate = job->ms_inflate; res->ms_parse = job->ms_parse; res->ms_gather = job->ms_gather; res->ms_mt = job->ms_mt;
+    res->ms_sample = job->ms_sample; res->ms_sort = job->ms_sort; res->ms_count = job->ms_count;
+    if (job->first_recorded) {
+        CK(cudaEventRecord(job->ev_last, ctx->compute));
+        CK(cudaEventSynchronize(job->ev_last));
+        CK(cudaEventElapsedTime(&res->ms_device_total, job->ev_first, job->ev_last));
+    }
+    res->n_launches = ctx->launches - job->launches0;
+    return 0;
+}
+
+extern "C" void fastf_bam2db_result_free(fastf_bam2db_result *res)
+{
+    if (!res) return;
+    free(res->m_gene); free(res->m_cell); free(res->m_count); free(res->row_keys);
+    res->m_gene = res->m_cell = res->m_count = nullptr;
+    res->row_keys = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device-level building blocks
+// ---------------------------------------------------------------------------------------------------
+extern "C" int fastf_sort_u64_device(fastf_ctx *ctx, uint64_t *dev_keys, uint32_t *dev_vals, uint64_t n, uint32_t key_bits)
+{
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return 0;
+    SortScratch S;
+    DevBuf alt, valt;
+    int rc = dev_reserve(ctx, alt, n * sizeof(u64));
+    if (!rc && dev_vals) rc = dev_reserve(ctx, valt, n * sizeof(u32));
+    u32 shifts[8];
+    int npass = 0;
+    for (u32 b = 0; b < key_bits && npass < 8; b += 8) shifts[npass++] = b;
+    bool in_alt = false;
+    if (!rc) rc = sort_keys(ctx, S, dev_keys, alt.as<u64>(), dev_vals, valt.as<u32>(), n, shifts, npass, &in_alt, ctx->compute);
+    if (!rc && in_alt) {
+        rc = cudaMemcpyAsync(dev_keys, alt.p, n * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->compute) != cudaSuccess;
+        if (!rc && dev_vals) rc = cudaMemcpyAsync(dev_vals, valt.p, n * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->compute) != cudaSuccess;
+    }
+    if (cudaStreamSynchronize(ctx->compute) != cudaSuccess && !rc) rc = ctx_fail(ctx, "sort_u64_device: stream error");
+    sort_scratch_release(S);
+    dev_release(alt);
+    dev_release(valt);
+    return rc;
+}
+
+extern "C" int fastf_dedup_count_device(fastf_ctx *ctx, const uint64_t *dev_sorted_keys, uint64_t n, uint32_t bits_gene, uint32_t bits_umi, uint64_t *nnz, uint32_t **m_gene, uint32_t **m_cell,
+                                        uint32_t **m_count)
+{
+    CK(cudaSetDevice(ctx->device));
+    RleScratch R;
+    u64 ng = 0;
+    int rc = rle_groups(ctx, R, dev_sorted_keys, nullptr, n, bits_umi, bits_umi - 1, bits_gene, &ng, nullptr, ctx->compute);
+    if (!rc) rc = coo_to_host(ctx, R, ng, m_gene, m_cell, m_count, ctx->compute);
+    *nnz = ng;
+    rle_scratch_release(R);
+    return rc;
+}
+
+// destination of a cell for the multi-GPU exchange: all keys of one (cell, gene) group must meet on one rank
+static inline __host__ __device__ u32 fastf_cell_dest(u32 cell, u32 nparts) { return fastf_hash_finalize(cell * 0x9e3779b1u + 0x7f4a7c15u) % nparts; }
+
+__global__ void __launch_bounds__(256) fastf_tag_dest_kernel(u64 *__restrict__ keys, u64 n, u32 cell_shift, u32 key_bits, u32 nparts)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 k = keys[i];
+    keys[i] = k | ((u64)fastf_cell_dest((u32)(k >> cell_shift), nparts) << key_bits);
+}
+// heads of runs of equal keys -> compacted, with the destination tag stripped; part boundaries by binary search
+__global__ void __launch_bounds__(256) fastf_part_bounds_kernel(const u64 *__restrict__ keys, u64 n, u32 key_bits, u32 nparts, u64 *__restrict__ bounds)
+{
+    u32 p = threadIdx.x;
+    if (p > nparts) return;
+    u64 lo = 0, hi = n;
+    while (lo < hi) { u64 mid = (lo + hi) >> 1; if ((keys[mid] >> key_bits) < (u64)p) lo = mid + 1; else hi = mid; }
+    bounds[p] = lo;
+}
+__global__ void __launch_bounds__(256) fastf_strip_tag_kernel(u64 *__restrict__ keys, u64 n, u32 key_bits)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] &= (1ull << key_bits) - 1ull;
+}
+
+extern "C" int fastf_unique_partition_device(fastf_ctx *ctx, uint64_t *dev_keys, uint64_t n, uint32_t key_bits, uint32_t bits_gene, uint32_t bits_umi, uint32_t nparts, uint64_t *dev_out_keys,
+                                             uint64_t *part_counts)
+{
+    CK(cudaSetDevice(ctx->device));
+    for (u32 p = 0; p < nparts; p++) part_counts[p] = 0;
+    if (n == 0) return 0;
+    if (nparts == 0 || nparts > 255 || key_bits + 8 > 64) return ctx_fail(ctx, "unique_partition: bad nparts/key_bits");
+    cudaStream_t s = ctx->compute;
+    SortScratch S;
+    RleScratch R;
+    DevBuf alt, orand, bounds;
+    PinBuf host;
+    int rc = 0;
+    auto body = [&]() -> int {
+        TRY(dev_reserve(ctx, alt, n * sizeof(u64)));
+        TRY(dev_reserve(ctx, orand, 2 * sizeof(u64)));
+        TRY(dev_reserve(ctx, bounds, 257 * sizeof(u64)));
+        TRY(pin_reserve(ctx, host, 257 * sizeof(u64)));
+        FASTF_LAUNCH(fastf_tag_dest_kernel, (u32)((n + 255) / 256), 256, 0, s, dev_keys, n, bits_gene + bits_umi, key_bits, nparts);
+        CKL("tag_dest");
+        u64 varying = 0;
+        TRY(varying_bits(ctx, orand, host, dev_keys, n, &varying, s));
+        u32 shifts[8];
+        const int npass = plan_windows(varying, shifts);
+        bool in_alt = false;
+        TRY(sort_keys(ctx, S, dev_keys, alt.as<u64>(), nullptr, nullptr, n, shifts, npass, &in_alt, s));
+        const u64 *sorted = in_alt ? alt.as<u64>() : dev_keys;
+        // unique: every key is its own group (group_shift 0); grp_key = the distinct keys in sorted order
+        u64 nuniq = 0;
+        TRY(rle_groups(ctx, R, sorted, nullptr, n, 0, 64, 0, &nuniq, nullptr, s));
+        FASTF_LAUNCH(fastf_part_bounds_kernel, 1, 256, 0, s, (const u64 *)R.grp_key.as<u64>(), nuniq, key_bits, nparts, bounds.as<u64>());
+        CKL("part_bounds");
+        CK(cudaMemcpyAsync(dev_out_keys, R.grp_key.p, nuniq * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        FASTF_LAUNCH(fastf_strip_tag_kernel, (u32)((nuniq + 255) / 256), 256, 0, s, dev_out_keys, nuniq, key_bits);
+        CKL("strip_tag");
+        CK(cudaMemcpyAsync(host.p, bounds.p, (nparts + 1) * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (u32 p = 0; p < nparts; p++) part_counts[p] = host.as<u64>()[p + 1] - host.as<u64>()[p];
+        return 0;
+    };
+    rc = body();
+    cudaStreamSynchronize(s);
+    sort_scratch_release(S);
+    rle_scratch_release(R);
+    dev_release(alt); dev_release(orand); dev_release(bounds);
+    pin_release(host);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-buffer wrappers around single kernels (tests, smoke)
+// ---------------------------------------------------------------------------------------------------
+struct InflatedFile {
+    DevBuf comp, infl;
+    BlockIndexDev idx;
+    u64 n_blocks = 0, infl_bytes = 0;
+    u32 status = 0;
+};
+static void inflated_release(InflatedFile &F) { dev_release(F.comp); dev_release(F.infl); index_release(F.idx); }
+
+// Inflate a whole BGZF image (host bytes, or device bytes + host index) into F.infl in one launch.
+static int inflate_whole(fastf_ctx *ctx, InflatedFile &F, const void *host_bytes, size_t n, const u8 *dev_bytes, const std::vector<FastfBgzfBlock> *pre, int lanes, float *ms, cudaStream_t s)
+{
+    std::vector<FastfBgzfBlock> local;
+    const std::vector<FastfBgzfBlock> *blocks = pre;
+    if (!pre) {
+        size_t used = 0;
+        int rc = fastf_bgzf_index((const u8 *)host_bytes, n, 0, local, &used);
+        if (rc != FASTF_BGZF_OK) return ctx_fail(ctx, "inflate: not a whole BGZF stream (index error %d at byte %zu of %zu)", rc, used, n);
+        blocks = &local;
+    }
+    const size_t nb = blocks->size();
+    if (nb >= 0xffffffffull) return ctx_fail(ctx, "inflate: too many blocks");
+    TRY(index_reserve(ctx, F.idx, (u32)std::max<size_t>(nb, 1)));
+    u64 total = 0;
+    for (size_t i = 0; i < nb; i++) {
+        F.idx.h_in_off[i] = (*blocks)[i].in_off; F.idx.h_in_len[i] = (*blocks)[i].in_len; F.idx.h_isize[i] = (*blocks)[i].isize;
+        F.idx.h_out_off[i] = total; F.idx.h_stage_off[i] = 0;
+        total += (*blocks)[i].isize;
+    }
+    const u8 *comp = dev_bytes;
+    u64 comp_total = n & ~(u64)3;
+    if (!dev_bytes) {
+        const u64 padded = ((u64)n + 3) & ~3ull;
+        TRY(dev_reserve(ctx, F.comp, padded + 16));
+        CK(cudaMemcpyAsync(F.comp.p, host_bytes, n, cudaMemcpyHostToDevice, s));
+        comp = F.comp.as<u8>();
+        comp_total = padded;
+    }
+    TRY(dev_reserve(ctx, F.infl, total + 64));
+    TRY(index_upload(ctx, F.idx, s));
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (ms) { CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); CK(cudaEventRecord(a, s)); }
+    TRY(launch_inflate(ctx, lanes, comp, comp_total, F.idx.in_off, F.idx.in_len, F.idx.out_off, F.idx.isize, (u32)nb, F.infl.as<u8>(), F.idx.st_infl, s));
+    if (ms) { CK(cudaEventRecord(b, s)); }
+    // OR of the per-block status words
+    std::vector<u32> st(nb);
+    if (nb) CK(cudaMemcpyAsync(st.data(), F.idx.st_infl, nb * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (ms) { CK(cudaEventElapsedTime(ms, a, b)); cudaEventDestroy(a); cudaEventDestroy(b); }
+    F.status = 0;
+    for (size_t i = 0; i < nb; i++) F.status |= st[i];
+    F.n_blocks = nb;
+    F.infl_bytes = total;
+    if (F.status) {
+        char buf[256];
+        return ctx_fail(ctx, "inflate: malformed deflate data: %s", status_string(F.status, buf, sizeof buf));
+    }
+    return 0;
+}
+
+extern "C" int fastf_inflate_host(fastf_ctx *ctx, const void *bgzf_bytes, size_t n, int lanes, void **out, size_t *out_n, float *ms)
+{
+    CK(cudaSetDevice(ctx->device));
+    *out = nullptr;
+    *out_n = 0;
+    InflatedFile F;
+    int rc = inflate_whole(ctx, F, bgzf_bytes, n, nullptr, nullptr, lanes ? lanes : 32, ms, ctx->compute);
+    if (!rc) {
+        *out = malloc(F.infl_bytes ? F.infl_bytes : 1);
+        if (!*out) rc = ctx_fail(ctx, "inflate_host: out of host memory");
+        if (!rc && F.infl_bytes) rc = fastf_memcpy_d2h(ctx, *out, F.infl.p, F.infl_bytes);
+        *out_n = F.infl_bytes;
+    }
+    inflated_release(F);
+    return rc;
+}
+
+static int mt_host_common(fastf_ctx *ctx, uint32_t seed, uint64_t n, uint64_t threshold, uint32_t *out_words, uint32_t *out_bits)
+{
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return 0;
+    const u64 pairs = (n + 1247) / 1248;
+    DevBuf state, out;
+    int rc = dev_reserve(ctx, state, 624 * sizeof(u32));
+    const size_t out_bytes = out_words ? (size_t)pairs * 1248 * sizeof(u32) : (size_t)pairs * 39 * sizeof(u32);
+    if (!rc) rc = dev_reserve(ctx, out, out_bytes);
+    if (!rc) {
+        FASTF_LAUNCH(fastf_mt19937_kernel, 1, FASTF_MT_THREADS, 0, ctx->compute, seed, state.as<u32>(), (u64)0, pairs, threshold, out_words ? out.as<u32>() : (u32 *)nullptr,
+                     out_words ? (u32 *)nullptr : out.as<u32>());
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = ctx_fail(ctx, "mt19937 launch failed");
+    }
+    if (!rc) rc = out_words ? fastf_memcpy_d2h(ctx, out_words, out.p, (size_t)n * sizeof(u32)) : fastf_memcpy_d2h(ctx, out_bits, out.p, (size_t)((n + 31) / 32) * sizeof(u32));
+    dev_release(state);
+    dev_release(out);
+    return rc;
+}
+extern "C" int fastf_mt19937_host(fastf_ctx *ctx, uint32_t seed, uint64_t n, uint32_t *out_words) { return mt_host_common(ctx, seed, n, 0, out_words, nullptr); }
+extern "C" int fastf_mt19937_keepbits_host(fastf_ctx *ctx, uint32_t seed, uint64_t n, uint64_t threshold, uint32_t *out_bits) { return mt_host_common(ctx, seed, n, threshold, nullptr, out_bits); }
+
+extern "C" int fastf_sort_u64_host(fastf_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t n, uint32_t key_bits)
+{
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return 0;
+    DevBuf dk, dv;
+    int rc = dev_reserve(ctx, dk, n * sizeof(u64));
+    if (!rc && vals) rc = dev_reserve(ctx, dv, n * sizeof(u32));
+    if (!rc) rc = fastf_memcpy_h2d(ctx, dk.p, keys, n * sizeof(u64));
+    if (!rc && vals) rc = fastf_memcpy_h2d(ctx, dv.p, vals, n * sizeof(u32));
+    if (!rc) rc = fastf_sort_u64_device(ctx, dk.as<u64>(), vals ? dv.as<u32>() : nullptr, n, key_bits);
+    if (!rc) rc = fastf_memcpy_d2h(ctx, keys, dk.p, n * sizeof(u64));
+    if (!rc && vals) rc = fastf_memcpy_d2h(ctx, vals, dv.p, n * sizeof(u32));
+    dev_release(dk);
+    dev_release(dv);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// freq
+// ---------------------------------------------------------------------------------------------------
+static int freq_on_text(fastf_ctx *ctx, const u8 *text, u64 n, u32 key_len, fastf_freq_result *res, cudaStream_t s)
+{
+    if (n >= (1ull << 40)) return ctx_fail(ctx, "freq: input too large for one pass");
+    DevBuf tiles, tot, keys, exc_cnt, exc_ord, exc_bytes, ckeys, cidx, kalt, valt, orand;
+    PinBuf host;
+    SortScratch S;
+    RleScratch R;
+    Timer t_keys, t_sort, t_rle;
+    auto cleanup = [&]() {
+        dev_release(tiles); dev_release(tot); dev_release(keys); dev_release(exc_cnt); dev_release(exc_ord); dev_release(exc_bytes); dev_release(ckeys); dev_release(cidx);
+        dev_release(kalt); dev_release(valt); dev_release(orand);
+        pin_release(host);
+        sort_scratch_release(S);
+        rle_scratch_release(R);
+        t_keys.destroy(); t_sort.destroy(); t_rle.destroy();
+    };
+    auto body = [&]() -> int {
+        if (t_keys.init() || t_sort.init() || t_rle.init()) return ctx_fail(ctx, "freq: event creation failed");
+        TRY(pin_reserve(ctx, host, 64));
+        TRY(dev_reserve(ctx, orand, 2 * sizeof(u64)));
+        // ---- newline scan -> number of lines -> keys ----
+        const u64 ntiles64 = (n + FASTF_NL_TILE - 1) / FASTF_NL_TILE;
+        if (ntiles64 >= 0xffffffffull) return ctx_fail(ctx, "freq: too many tiles");
+        const u32 ntiles = (u32)std::max<u64>(ntiles64, 1);
+        TRY(dev_reserve(ctx, tiles, (size_t)ntiles * sizeof(u32)));
+        TRY(dev_reserve(ctx, tot, sizeof(u32)));
+        t_keys.start(s);
+        FASTF_LAUNCH(fastf_nl_count_kernel, ntiles, FASTF_NL_THREADS, 0, s, text, n, tiles.as<u32>());
+        CKL("nl_count");
+        TRY(launch_scan_rows(ctx, tiles.as<u32>(), ntiles, 1, tot.as<u32>(), s));
+        CK(cudaMemcpyAsync(host.p, tot.p, sizeof(u32), cudaMemcpyDeviceToHost, s));
+        u8 last = '\n';
+        if (n) CK(cudaMemcpyAsync(host.as<u8>() + 8, text + n - 1, 1, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const u64 n_newlines = host.as<u32>()[0];
+        if (n) last = host.as<u8>()[8];
+        const u64 n_lines = n_newlines + ((n && last != '\n') ? 1 : 0);
+        // get_fastq reads four lines per record; a record exists as soon as its id line does (reference src/filter.c:22-34)
+        const u64 n_reads = (n_lines + 3) / 4;
+        res->n_lines = n_lines;
+        res->last_byte_is_newline = (u8)(n == 0 || last == '\n');
+        res->n_reads = n_reads;
+        // records whose sequence line starts after newline 4r: r = 0 .. n_keys_dev-1 where newline 4r exists
+        const u64 n_keys_dev = n_newlines ? (n_newlines - 1) / 4 + 1 : 0;
+        // a trailing record whose id line is not newline-terminated has an empty key (NUL immediately): host handles it
+        TRY(dev_reserve(ctx, keys, std::max<u64>(n_keys_dev, 1) * sizeof(u64)));
+        TRY(dev_reserve(ctx, exc_cnt, sizeof(u32)));
+        u32 exc_cap = (u32)std::min<u64>(std::max<u64>(n_keys_dev / 16, 1u << 16), n_keys_dev ? n_keys_dev : 1);
+        u32 n_exc = 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            TRY(dev_reserve(ctx, exc_ord, (size_t)exc_cap * sizeof(u32)));
+            TRY(dev_reserve(ctx, exc_bytes, (size_t)exc_cap * FASTF_FREQ_EXC_STRIDE));
+            CK(cudaMemsetAsync(exc_cnt.p, 0, sizeof(u32), s));
+            FASTF_LAUNCH(fastf_freq_keys_kernel, ntiles, FASTF_NL_THREADS, 0, s, text, n, (const u32 *)tiles.as<u32>(), key_len, keys.as<u64>(), n_keys_dev, exc_cnt.as<u32>(), exc_cap,
+                         exc_ord.as<u32>(), exc_bytes.as<u8>());
+            CKL("freq_keys");
+            CK(cudaMemcpyAsync(host.p, exc_cnt.p, sizeof(u32), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            n_exc = host.as<u32>()[0];
+            if (n_exc <= exc_cap) break;
+            exc_cap = n_exc;   // rerun with room for every exceptional read
+        }
+        t_keys.stop(s);
+        // ---- compact good keys with their read ordinal ----
+        u64 n_good = n_keys_dev - n_exc;
+        res->n_keys = 0;
+        u64 ngroups = 0;
+        if (n_keys_dev >= 0xffffffffull) return ctx_fail(ctx, "freq: more than 2^32-1 reads in one pass");
+        if (n_good) {
+            const u32 ctiles = (u32)((n_keys_dev + FASTF_CP_TILE - 1) / FASTF_CP_TILE);
+            TRY(dev_reserve(ctx, tiles, (size_t)std::max(ctiles, ntiles) * sizeof(u32)));
+            TRY(dev_reserve(ctx, ckeys, n_good * sizeof(u64)));
+            TRY(dev_reserve(ctx, cidx, n_good * sizeof(u32)));
+            TRY(dev_reserve(ctx, kalt, n_good * sizeof(u64)));
+            TRY(dev_reserve(ctx, valt, n_good * sizeof(u32)));
+            t_sort.start(s);
+            FASTF_LAUNCH(fastf_compact_count_kernel, ctiles, FASTF_CP_THREADS, 0, s, (const u64 *)keys.as<u64>(), n_keys_dev, tiles.as<u32>());
+            CKL("compact_count");
+            TRY(launch_scan_rows(ctx, tiles.as<u32>(), ctiles, 1, tot.as<u32>(), s));
+            FASTF_LAUNCH(fastf_compact_scatter_kernel, ctiles, FASTF_CP_THREADS, 0, s, (const u64 *)keys.as<u64>(), n_keys_dev, (const u32 *)tiles.as<u32>(), ckeys.as<u64>(), cidx.as<u32>());
+            CKL("compact_scatter");
+            u64 varying = 0;
+            TRY(varying_bits(ctx, orand, host, ckeys.as<u64>(), n_good, &varying, s));
+            u32 shifts[8];
+            const int npass = plan_windows(varying, shifts);
+            bool in_alt = false;
+            TRY(sort_keys(ctx, S, ckeys.as<u64>(), kalt.as<u64>(), cidx.as<u32>(), valt.as<u32>(), n_good, shifts, npass, &in_alt, s));
+            t_sort.stop(s);
+            t_rle.start(s);
+            u64 nd = 0;
+            TRY(rle_groups(ctx, R, in_alt ? kalt.as<u64>() : ckeys.as<u64>(), in_alt ? valt.as<u32>() : cidx.as<u32>(), n_good, 0, 64, 0, &ngroups, &nd, s));
+            t_rle.stop(s);
+        }
+        // ---- results to host ----
+        res->n_keys = ngroups;
+        res->key = (u64 *)malloc(std::max<u64>(ngroups, 1) * sizeof(u64));
+        res->count = (u32 *)malloc(std::max<u64>(ngroups, 1) * sizeof(u32));
+        res->first = (u32 *)malloc(std::max<u64>(ngroups, 1) * sizeof(u32));
+        res->n_exceptions = n_exc;
+        res->exc_stride = FASTF_FREQ_EXC_STRIDE;
+        res->exc_ordinal = (u32 *)malloc(std::max<u64>(n_exc, 1) * sizeof(u32));
+        res->exc_bytes = (u8 *)malloc(std::max<u64>(n_exc, 1) * FASTF_FREQ_EXC_STRIDE);
+        if (!res->key || !res->count || !res->first || !res->exc_ordinal || !res->exc_bytes) return ctx_fail(ctx, "freq: out of host memory");
+        if (ngroups) {
+            // with group_shift 0 every distinct key is a group and counts all its copies: count = next first - first
+            CK(cudaMemcpyAsync(res->key, R.grp_key.p, ngroups * sizeof(u64), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(res->first, R.grp_val.p, ngroups * sizeof(u32), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(res->count, R.grp_first.p, ngroups * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        }
+        if (n_exc) {
+            CK(cudaMemcpyAsync(res->exc_ordinal, exc_ord.p, (size_t)n_exc * sizeof(u32), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(res->exc_bytes, exc_bytes.p, (size_t)n_exc * FASTF_FREQ_EXC_STRIDE, cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaStreamSynchronize(s));
+        // grp_first[g] = index of the group's first element in the sorted array -> multiplicity by differencing
+        for (u64 g = 0; g < ngroups; g++) {
+            u64 nxt = (g + 1 < ngroups) ? res->count[g + 1] : n_good;
+            res->count[g] = (u32)(nxt - res->count[g]);
+        }
+        t_keys.collect(&res->ms_keys);
+        t_sort.collect(&res->ms_sort);
+        t_rle.collect(&res->ms_rle);
+        return 0;
+    };
+    int rc = body();
+    cudaStreamSynchronize(s);
+    cleanup();
+    return rc;
+}
+
+static bool looks_like_gzip(const u8 *p, size_t n) { return n >= 2 && p[0] == 0x1f && p[1] == 0x8b; }
+
+static int freq_common(fastf_ctx *ctx, const void *host_bytes, size_t n, const u8 *dev_bytes, const std::vector<FastfBgzfBlock> *pre, uint32_t key_len, uint32_t lanes, fastf_freq_result *res)
+{
+    CK(cudaSetDevice(ctx->device));
+    memset(res, 0, sizeof *res);
+    if (key_len == 0 || key_len > FASTF_FREQ_MAX_KEY) return ctx_fail(ctx, "freq: len_cellbarcode + len_umi must be 1..%d (got %u)", FASTF_FREQ_MAX_KEY, key_len);
+    const u32 l0 = ctx->launches;
+    cudaStream_t s = ctx->compute;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    InflatedFile F;
+    int rc = 0;
+    const u8 *text = nullptr;
+    u64 text_n = 0;
+    DevBuf plain;
+    if (dev_bytes || looks_like_gzip((const u8 *)host_bytes, n)) {
+        if (!dev_bytes) {
+            // plain (non-BGZF) gzip cannot be inflated block-parallel: refuse loudly rather than fall back to the CPU
+            const u8 *h = (const u8 *)host_bytes;
+            if (n < 18 || !(h[3] & 4)) { cudaEventDestroy(e0); cudaEventDestroy(e1); return ctx_fail(ctx, "freq: input is single-member gzip, not BGZF; recompress with bgzip (no CPU fallback)"); }
+        }
+        // the inflate launch is timed separately; the device-total clock starts before it
+        cudaEventRecord(e0, s);
+        rc = inflate_whole(ctx, F, host_bytes, n, dev_bytes, pre, lanes ? (int)lanes : 32, &res->ms_inflate, s);
+        text = F.infl.as<u8>();
+        text_n = F.infl_bytes;
+        res->n_blocks = F.n_blocks;
+        res->status = F.status;
+    } else {
+        rc = dev_reserve(ctx, plain, n + 64);
+        cudaEventRecord(e0, s);
+        if (!rc && n) rc = cudaMemcpyAsync(plain.p, host_bytes, n, cudaMemcpyHostToDevice, s) != cudaSuccess;
+        text = plain.as<u8>();
+        text_n = n;
+    }
+    res->compressed_bytes = n;
+    res->inflated_bytes = text_n;
+    if (!rc) rc = freq_on_text(ctx, text, text_n, key_len, res, s);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&res->ms_device_total, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    inflated_release(F);
+    dev_release(plain);
+    res->n_launches = ctx->launches - l0;
+    if (rc) fastf_freq_result_free(res);
+    return rc;
+}
+
+extern "C" int fastf_freq_gpu(fastf_ctx *ctx, const void *host_bytes, size_t n, uint32_t key_len, uint32_t inflate_lanes, fastf_freq_result *res)
+{
+    return freq_common(ctx, host_bytes, n, nullptr, nullptr, key_len, inflate_lanes, res);
+}
+extern "C" int fastf_freq_gpu_device(fastf_ctx *ctx, const void *dev_bytes, size_t nbytes, const uint64_t *in_off, const uint32_t *in_len, const uint32_t *isize, uint64_t nblocks, uint32_t key_len,
+                                     uint32_t inflate_lanes, fastf_freq_result *res)
+{
+    if (((uintptr_t)dev_bytes & 3u) != 0) return ctx_fail(ctx, "freq_gpu_device: dev_bytes must be 4-byte aligned");
+    std::vector<FastfBgzfBlock> blocks(nblocks);
+    for (u64 i = 0; i < nblocks; i++) {
+        if (in_off[i] + in_len[i] + 8 > nbytes || isize[i] > 65536) return ctx_fail(ctx, "freq_gpu_device: block %llu outside the buffer", (unsigned long long)i);
+        blocks[i].in_off = in_off[i]; blocks[i].in_len = in_len[i]; blocks[i].isize = isize[i]; blocks[i].crc32 = 0;
+    }
+    return freq_common(ctx, nullptr, nbytes, (const u8 *)dev_bytes, &blocks, key_len, inflate_lanes, res);
+}
+extern "C" void fastf_freq_result_free(fastf_freq_result *res)
+{
+    if (!res) return;
+    free(res->key); free(res->count); free(res->first); free(res->exc_ordinal); free(res->exc_bytes);
+    res->key = nullptr; res->count = nullptr; res->first = nullptr; res->exc_ordinal = nullptr; res->exc_bytes = nullptr;
+}
