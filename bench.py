@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- `fastF bam2db` hot path on B200: reads/s through libfastf_gpu.so, roofline of the dominant kernel, the
+reference's CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--reads R] [--base-reads B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2]): synthetic 10x-v3 BAM, 10k cells, 36k genes, `-c 1.0 -r 0.3 -s 926`, R reads per GPU
+(default 500M).  The BAM is a zlib-6 BGZF image of B reads (default 8M, ~1.2 GB compressed / 3.3 GB inflated, generated on
+the host cores at start-up) whose record blocks are streamed T = ceil(R/B) times through the same job; the MT19937 draw
+ordinal keeps running across tiles, so every tile keeps a different 30 % of its reads.  One step = one whole job
+(begin -> feed all tiles -> sample -> sort -> dedup/count -> COO on the host).
+
+  value : reads/s with the compressed bytes + block index already resident in HBM (fastf_bam2db_feed_device)
+  e2e   : the same job fed from pinned HOST memory through fastf_bam2db_feed (H2D of every compressed byte inside the timed
+          region, COO + counters copied back)
+  roofline : the dominant kernel (bgzf_inflate): algorithmic bytes = compressed read + inflated written per launch, over the
+          launch's CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : oracle/_ref/fastF_ref (the unmodified reference compiled against the header shims) on a bounded prefix of the
+          same BAM, 1 core (the reference path is single-threaded)
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_CELLS, N_GENES, RATE_CELL, RATE_DEPTH, SEED, DATA_SEED = 10000, 36000, 1.0, 0.3, 926, 11
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_base(base_reads, threads):
+    """Synthetic base segment + barcode / feature lists.  Returns dict with the BGZF image (numpy u8) and text lists."""
+    import synth_binding
+    S = synth_binding.load()
+    p = S.params(n_reads=base_reads, n_cells=N_CELLS, n_genes=N_GENES, seed=DATA_SEED)
+    t = time.time()
+    bam, st = S.bam(p, threads)
+    log(f"[bench] generated {base_reads} reads: {st.compressed_bytes / 1e6:.0f} MB BGZF, {st.inflated_bytes / 1e6:.0f} MB inflated, {st.n_blocks} blocks in {time.time() - t:.1f}s on {threads} threads")
+    return {"bam": bam, "barcodes": S.barcodes(p), "features": S.features(p), "reads": base_reads, "n_blocks": st.n_blocks,
+            "inflated": st.inflated_bytes, "compressed": st.compressed_bytes}
+
+
+def write_inputs(base, d, prefix_reads=None):
+    """files for the reference CLI; with prefix_reads a BAM holding only about that many reads (whole blocks)"""
+    import gzip
+    paths = {"bam": os.path.join(d, "synth.bam"), "barcodes": os.path.join(d, "barcodes.tsv.gz"), "features": os.path.join(d, "features.tsv.gz")}
+    with gzip.open(paths["barcodes"], "wb", compresslevel=1) as f:
+        f.write(base["barcodes"])
+    with gzip.open(paths["features"], "wb", compresslevel=1) as f:
+        f.write(base["features"])
+    bam = base["bam"]
+    reads = base["reads"]
+    if prefix_reads and prefix_reads < base["reads"]:
+        # cut at a block boundary in proportion; the EOF block (28 bytes) is re-appended
+        from fastf_b200 import _lib
+        lib = _lib.load()
+        buf = np.frombuffer(bam, dtype=np.uint8)
+        cap = base["n_blocks"] + 8
+        in_off, in_len, isz = np.zeros(cap, np.uint64), np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+        used = C.c_size_t()
+        nb = lib.fastf_bgzf_index_host(C.c_void_p(buf.ctypes.data), buf.size, in_off.ctypes.data_as(_lib.c_u64p), in_len.ctypes.data_as(_lib.c_u32p), isz.ctypes.data_as(_lib.c_u32p), cap, C.byref(used))
+        k = max(2, int(nb * prefix_reads / base["reads"]))
+        cut = int(in_off[k]) - 18
+        bam = bam[:cut] + bam[-28:]
+        reads = None   # counted by the reference itself
+    with open(paths["bam"], "wb") as f:
+        f.write(bam)
+    return paths, reads
+
+
+def run_reference_cli(paths, outdir, rate_cell, rate_depth, seed):
+    """One run of the unmodified reference (oracle/_ref/fastF_ref).  Returns (seconds, total reads)."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "fastF_ref")
+    kind = "reference"
+    shutil.rmtree(outdir, ignore_errors=True)
+    os.makedirs(outdir)
+    db = os.path.join(outdir, "ref.db")
+    if os.path.exists(ref):
+        cmd = [ref, "bam2db", "-b", paths["bam"], "-f", paths["features"], "-a", paths["barcodes"], "-d", db, "-c", str(rate_cell), "-r", str(rate_depth), "-o", outdir, "-s", str(seed)]
+    else:
+        kind = "port"
+        cmd = [os.path.join(ROOT, "oracle", "_build", "oracle_cli"), "bam2db", paths["bam"], paths["barcodes"], paths["features"], str(rate_cell), str(rate_depth), str(seed), outdir]
+    t = time.time()
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    dt = time.time() - t
+    if r.returncode != 0:
+        raise RuntimeError("reference run failed: " + r.stderr[-400:])
+    total = None
+    for ln in r.stdout.splitlines():
+        if "total fastQ reads:" in ln:
+            total = int(ln.rsplit(":", 1)[1])
+        if ln.startswith("total="):
+            total = int(ln.split()[0].split("=")[1])
+    return dt, total, kind
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=500_000_000, help="reads per GPU per step")
+    ap.add_argument("--base-reads", type=int, default=8_000_000, help="reads in the generated BGZF segment that is tiled")
+    ap.add_argument("--ref-sample-reads", type=int, default=5_000_000)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--chunk-mb", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    threads = os.cpu_count() or 1
+    workload = f"bam2db synthetic 10x-v3 BAM: {args.reads} reads/GPU, {N_CELLS} cells, {N_GENES} genes, -c {RATE_CELL} -r {RATE_DEPTH} -s {SEED} (BASELINE.json configs[2])"
+
+    # ------------------------------------------------------------------ reference arm: the reference's own CPU path
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from fastf_b200 import build
+        build.build_synth()
+        base = make_base(min(args.base_reads, args.ref_sample_reads), threads)
+        tmp = tempfile.mkdtemp(prefix="fastf_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            paths, _ = write_inputs(base, tmp)
+            times, total, kind = [], None, "reference"
+            for i in range(args.warmup + args.steps):
+                dt, total, kind = run_reference_cli(paths, os.path.join(tmp, "out"), RATE_CELL, RATE_DEPTH, SEED)
+                if i >= args.warmup:
+                    times.append(dt)
+                log(f"[bench] reference step {i}: {dt:.2f}s for {total} reads")
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        ms = 1e3 * sum(times) / len(times)
+        v = total / (ms / 1e3)
+        sample = f"{total}-read prefix of the same synthetic BAM per step (whole run of the unmodified reference CLI: inflate, parse, sample, sqlite insert + GROUP BY, gz output; wall clock)"
+        print(json.dumps({"impl": "reference", "metric": "bam2db reads/sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": workload, "sample": sample},
+                          "cpu_baseline": {"value": v, "unit": "reads/s", "cores": 1, "kind": kind, "sample": sample, "cpu": cpu_model(), "host_cores": threads},
+                          "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    from fastf_b200 import _lib
+    from fastf_b200 import bam2db_host as B
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = _lib.Context(local_rank)
+    lib = ctx.lib
+    base = make_base(args.base_reads, max(1, threads // max(1, world)))
+    tmp = tempfile.mkdtemp(prefix=f"fastf_bench_{rank}_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        paths, _ = write_inputs(base, tmp)
+        inputs = B.Bam2dbInputs(lib, paths["barcodes"], paths["features"], RATE_CELL, SEED)
+        bam = np.frombuffer(base["bam"], dtype=np.uint8)
+        nbytes = bam.size
+        # block index of the image (host, once)
+        cap = base["n_blocks"] + 8
+        in_off, in_len, isz = np.zeros(cap, np.uint64), np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+        used = C.c_size_t()
+        nb = lib.fastf_bgzf_index_host(C.c_void_p(bam.ctypes.data), nbytes, in_off.ctypes.data_as(_lib.c_u64p), in_len.ctypes.data_as(_lib.c_u32p), isz.ctypes.data_as(_lib.c_u32p), cap, C.byref(used))
+        assert nb == base["n_blocks"] and used.value == nbytes, (nb, used.value, nbytes)
+        in_off, in_len, isz = in_off[:nb].copy(), in_len[:nb].copy(), isz[:nb].copy()
+        # block 0 = BAM header (own block), block nb-1 = EOF; record blocks are 1..nb-2
+        rec_lo, rec_hi = 1, nb - 1
+        tiles = max(1, -(-args.reads // base["reads"]))
+        reads_per_step = tiles * base["reads"]
+        comp_rec_bytes = int(in_off[rec_hi] - 18 - (in_off[rec_lo] - 18))
+        infl_rec_bytes = int(isz[rec_lo:rec_hi].sum())
+        # device copy of the image (value leg) and pinned host copy (e2e leg)
+        dptr = C.c_void_p()
+        ctx.check(lib.fastf_device_alloc(ctx.h, nbytes + 64, C.byref(dptr)), "device_alloc")
+        ctx.check(lib.fastf_memcpy_h2d(ctx.h, dptr, C.c_void_p(bam.ctypes.data), nbytes), "h2d")
+        hptr = C.c_void_p()
+        ctx.check(lib.fastf_host_alloc(ctx.h, nbytes, C.byref(hptr)), "host_alloc")
+        C.memmove(hptr, bam.ctypes.data, nbytes)
+        hdr_end = int(in_off[rec_lo]) - 18          # first byte of the first record block
+        eof_start = int(in_off[rec_hi]) - 18
+        chunk = args.chunk_mb << 20
+
+        def one_job(device_resident, want_copy=False):
+            with B.Bam2dbJob(ctx, inputs, RATE_DEPTH, SEED, want_rows=False, inflate_lanes=args.lanes, chunk_inflated_bytes=chunk) as job:
+                for t in range(tiles):
+                    if device_resident:
+                        lo = 0 if t == 0 else rec_lo
+                        job.feed_device(dptr.value, nbytes, in_off[lo:rec_hi], in_len[lo:rec_hi], isz[lo:rec_hi])
+                    else:
+                        lo = 0 if t == 0 else hdr_end
+                        job.feed(hptr.value + lo, eof_start - lo)
+                if world > 1:
+                    n_rec, n_cbv = job.counts()
+                    cnt = torch.tensor([n_rec, n_cbv], dtype=torch.int64, device="cuda")
+                    allc = [torch.zeros_like(cnt) for _ in range(world)]
+                    dist.all_gather(allc, cnt)
+                    base_ord = int(sum(int(c[1]) for c in allc[:rank]))
+                    job.sample(base_ord)
+                    return multi_gpu_tail(job, dist, torch, ctx, rank, world, inputs)
+                return job.finish(copy=want_copy)
+
+        def timed(device_resident, steps, warmup, sampler=None):
+            for _ in range(warmup):
+                one_job(device_resident)
+            if dist:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ctx.check(lib.fastf_synchronize(ctx.h), "sync")
+            l0 = ctx.launches
+            if sampler:
+                sampler.start()
+            # CUDA events on the stream the library launches its kernels on (torch's current stream would see nothing)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.time()
+            e0.record(lib_stream)
+            stats_all = []
+            for _ in range(steps):
+                st, _out = one_job(device_resident)
+                stats_all.append(st)
+            e1.record(lib_stream)
+            ctx.check(lib.fastf_synchronize(ctx.h), "sync")
+            torch.cuda.synchronize()
+            if dist:
+                dist.barrier()
+            wall = time.time() - t0
+            clocks = sampler.stop() if sampler else None
+            return wall, stats_all, ctx.launches - l0, clocks, e0.elapsed_time(e1)
+
+        lib_stream = torch.cuda.ExternalStream(lib.fastf_compute_stream(ctx.h), device=torch.device("cuda", local_rank))
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        wall, stats_all, launches, clocks, dev_ms_total = timed(True, args.steps, args.warmup, sampler)
+        ms_step = dev_ms_total / args.steps
+        ms_step_wall = 1e3 * wall / args.steps
+        ms_job_dev = float(np.mean([s["ms_device_total"] for s in stats_all]))   # library's own first-chunk -> last-kernel clock
+        if dist:
+            tt = torch.tensor([ms_step, ms_step_wall], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_step, ms_step_wall = float(tt[0]), float(tt[1])
+        value = world * reads_per_step / (ms_step / 1e3)
+        st = stats_all[-1]
+        e2e = None
+        if not args.no_e2e:
+            ew, estats, _, _, _ = timed(False, args.e2e_steps, 1)
+            e_ms = 1e3 * ew / args.e2e_steps
+            if dist:
+                tt = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                e_ms = float(tt[0])
+            d2h = int(estats[-1]["nnz"]) * 12 + 64
+            e2e = {"value": world * reads_per_step / (e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(tiles * comp_rec_bytes + hdr_end), "d2h_bytes_per_step": d2h,
+                   "ms_per_step": e_ms, "steps": args.e2e_steps, "timing": "host wall clock around begin..finish (pinned host BGZF bytes in, COO out)"}
+        if rank != 0:
+            return 0
+        peak, peak_src = measured_peak()
+        n_chunks = max(1, st["n_chunks"])
+        infl_ms_launch = st["ms_inflate"] / n_chunks
+        alg_bytes_launch = (st["compressed_bytes"] + st["inflated_bytes"]) / n_chunks
+        achieved = alg_bytes_launch / (infl_ms_launch * 1e-3) / 1e9
+        stages = {}
+        for k, bytes_ in (("inflate", st["compressed_bytes"] + st["inflated_bytes"]), ("parse", st["inflated_bytes"] + 8 * st["total"]), ("mt", st["cb_valid"] / 8.0 + 0),
+                          ("sample", st["cb_valid"] * 8 * 2 + st["valid"] * 8), ("sort", st["valid"] * 16 * 7), ("count", st["valid"] * 8 + st["nnz"] * 12)):
+            ms = st["ms_" + k]
+            stages[k] = {"ms": round(ms, 3), "alg_GBps": round(bytes_ / (ms * 1e-3) / 1e9, 1) if ms > 0 else None}
+        line = {"metric": "bam2db reads/sec (device-timed)", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": workload, "tiling": f"{base['reads']}-read zlib-6 BGZF segment ({base['compressed'] / 1e6:.0f} MB compressed, {base['inflated'] / 1e6:.0f} MB inflated) streamed {tiles}x per step",
+                           "l2": "inputs larger than L2 (compressed segment >> 126 MB); no explicit flush", "timing": "CUDA events on the library's launching stream around the K timed jobs, barrier + synchronize on both sides; max over ranks",
+                           "ms_per_step_wall": ms_step_wall, "ms_per_job_library_clock": ms_job_dev, "counters": {k: st[k] for k in ("total", "cb_valid", "sampled", "valid", "nnz", "n_blocks", "n_chunks")}},
+                "roofline": {"bound": "hbm", "kernel": "fastf_bgzf_inflate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg_bytes_launch, "ms_per_launch": infl_ms_launch},
+                "stages": stages, "gpu_launches": launches, "clocks": clocks, "e2e": e2e}
+        if not args.no_cpu_baseline:
+            d2 = os.path.join(tmp, "refin")
+            os.makedirs(d2, exist_ok=True)
+            p2, _ = write_inputs(base, d2, prefix_reads=args.ref_sample_reads)
+            dt, total, kind = run_reference_cli(p2, os.path.join(tmp, "refout"), RATE_CELL, RATE_DEPTH, SEED)
+            line["cpu_baseline"] = {"value": total / dt, "unit": "reads/s", "cores": 1, "kind": kind, "cpu": cpu_model(), "host_cores": threads,
+                                    "sample": f"one run of the unmodified reference CLI on a {total}-read prefix of the same synthetic BAM ({dt:.1f}s wall; inflate via zlib shim, sqlite on /dev/shm)"}
+        print(json.dumps(line))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return 0
+
+
+def multi_gpu_tail(job, dist, torch, ctx, rank, world, inputs):
+    raise SystemExit("bench.py: multi-GPU tail not wired yet")
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -4,5 +4,5 @@
     fastf_b200.cell_counts(R1, l, u) / print_tree(hist, fp) / freq(R1, out_dir, l, u)      reference src/count.h:6, src/filter.h:77
 """
 from ._lib import Context, FastfError, load   # noqa: F401
-from .bam2db import bam2db   # noqa: F401
-from .freq import cell_counts, freq, print_tree   # noqa: F401
+from .bam2db_host import bam2db   # noqa: F401
+from .freq_host import cell_counts, freq, print_tree   # noqa: F401

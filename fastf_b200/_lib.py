@@ -24,7 +24,7 @@ class Bam2dbResult(C.Structure):
                 ("n_rows", C.c_uint64), ("row_keys", c_u64p),
                 ("bits_cell", C.c_uint32), ("bits_gene", C.c_uint32), ("bits_umi", C.c_uint32), ("umi_max_bytes", C.c_uint32),
                 ("n_blocks", C.c_uint64), ("compressed_bytes", C.c_uint64), ("inflated_bytes", C.c_uint64),
-                ("status", C.c_uint32), ("n_launches", C.c_uint32),
+                ("status", C.c_uint32), ("n_launches", C.c_uint32), ("n_chunks", C.c_uint32),
                 ("ms_inflate", C.c_float), ("ms_parse", C.c_float), ("ms_gather", C.c_float), ("ms_mt", C.c_float),
                 ("ms_sample", C.c_float), ("ms_sort", C.c_float), ("ms_count", C.c_float), ("ms_device_total", C.c_float)]
 
@@ -50,6 +50,7 @@ _SIGS = {
     "fastf_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "fastf_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "fastf_synchronize": (C.c_int, [C.c_void_p]),
+    "fastf_ctx_trim": (None, [C.c_void_p]),
     "fastf_launch_count": (C.c_uint32, [C.c_void_p]),
     "fastf_compute_stream": (C.c_void_p, [C.c_void_p]),
     "fastf_keep_threshold": (C.c_uint64, [C.c_float]),

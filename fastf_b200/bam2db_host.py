@@ -130,47 +130,95 @@ def decode_rows(row_keys, bits_gene, bits_umi, umi_max_bytes):
     return cell, gene, nbytes, content
 
 
+class Bam2dbJob:
+    """One streaming bam2db job on one GPU: begin -> feed*/feed_device* -> (counts -> sample(base)) -> finish."""
+
+    def __init__(self, ctx, inputs, rate_depth, seed, want_rows=True, inflate_lanes=0, chunk_inflated_bytes=0, umi_max_bytes=0):
+        self.ctx, self.lib = ctx, ctx.lib
+        ckeys, coff = _pack_table(inputs.cells)
+        gkeys, goff = _pack_table([f[0] for f in inputs.features])
+        self._keep = (ckeys, coff, gkeys, goff)
+        p = _lib.Bam2dbParams()
+        p.cell_keys = ckeys
+        p.cell_off = coff.ctypes.data_as(_lib.c_u32p)
+        p.n_cells = len(inputs.cells)
+        p.gene_keys = gkeys
+        p.gene_off = goff.ctypes.data_as(_lib.c_u32p)
+        p.n_genes = len(inputs.features)
+        p.seed = seed
+        p.d0 = inputs.d0
+        p.keep_threshold = self.lib.fastf_keep_threshold(C.c_float(rate_depth))
+        p.umi_max_bytes = umi_max_bytes
+        p.want_rows = 1 if want_rows else 0
+        p.inflate_lanes = inflate_lanes
+        p.chunk_inflated_bytes = chunk_inflated_bytes
+        self.want_rows = want_rows
+        self.job = C.c_void_p()
+        ctx.check(self.lib.fastf_bam2db_begin(ctx.h, C.byref(p), C.byref(self.job)), "bam2db_begin")
+
+    def feed(self, host_ptr, nbytes):
+        self.ctx.check(self.lib.fastf_bam2db_feed(self.job, C.c_void_p(host_ptr), nbytes), "bam2db_feed")
+
+    def feed_device(self, dev_ptr, nbytes, in_off, in_len, isize):
+        self.ctx.check(self.lib.fastf_bam2db_feed_device(self.job, C.c_void_p(dev_ptr), nbytes, in_off.ctypes.data_as(_lib.c_u64p), in_len.ctypes.data_as(_lib.c_u32p),
+                                                         isize.ctypes.data_as(_lib.c_u32p), len(in_off)), "bam2db_feed_device")
+
+    def counts(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self.ctx.check(self.lib.fastf_bam2db_counts(self.job, C.byref(a), C.byref(b)), "bam2db_counts")
+        return a.value, b.value
+
+    def sample(self, ordinal_base=0):
+        self.ctx.check(self.lib.fastf_bam2db_sample(self.job, ordinal_base), "bam2db_sample")
+
+    def kept_device(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self.ctx.check(self.lib.fastf_bam2db_kept_device(self.job, C.byref(p), C.byref(n)), "bam2db_kept_device")
+        return p.value, n.value
+
+    def key_layout(self):
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self.lib.fastf_bam2db_key_layout(self.job, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def finish(self, copy=True):
+        res = _lib.Bam2dbResult()
+        self.ctx.check(self.lib.fastf_bam2db_finish(self.job, C.byref(res)), "bam2db_finish")
+        out = None
+        if copy:
+            z32 = np.zeros(0, np.uint32)
+            out = {
+                "m_gene": np.ctypeslib.as_array(res.m_gene, (res.nnz,)).copy() if res.nnz else z32,
+                "m_cell": np.ctypeslib.as_array(res.m_cell, (res.nnz,)).copy() if res.nnz else z32,
+                "m_count": np.ctypeslib.as_array(res.m_count, (res.nnz,)).copy() if res.nnz else z32,
+                "row_keys": np.ctypeslib.as_array(res.row_keys, (res.n_rows,)).copy() if (self.want_rows and res.n_rows) else np.zeros(0, np.uint64),
+            }
+        stats = {f: getattr(res, f) for f, _ in _lib.Bam2dbResult._fields_ if not f.startswith("m_") and f != "row_keys"}
+        self.lib.fastf_bam2db_result_free(C.byref(res))
+        return stats, out
+
+    def close(self):
+        if self.job:
+            self.lib.fastf_bam2db_job_free(self.job)
+            self.job = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
 def run_device(ctx, bam_bytes, inputs, rate_depth, seed, want_rows=True, inflate_lanes=0, chunk_inflated_bytes=0, feed_piece=0, umi_max_bytes=0):
-    """The C-ABI call sequence for one BAM image in host memory.  Returns (Bam2dbResult, dict of numpy copies)."""
-    lib = ctx.lib
-    ckeys, coff = _pack_table(inputs.cells)
-    gkeys, goff = _pack_table([f[0] for f in inputs.features])
-    p = _lib.Bam2dbParams()
-    p.cell_keys = ckeys
-    p.cell_off = coff.ctypes.data_as(_lib.c_u32p)
-    p.n_cells = len(inputs.cells)
-    p.gene_keys = gkeys
-    p.gene_off = goff.ctypes.data_as(_lib.c_u32p)
-    p.n_genes = len(inputs.features)
-    p.seed = seed
-    p.d0 = inputs.d0
-    p.keep_threshold = lib.fastf_keep_threshold(C.c_float(rate_depth))
-    p.umi_max_bytes = umi_max_bytes
-    p.want_rows = 1 if want_rows else 0
-    p.inflate_lanes = inflate_lanes
-    p.chunk_inflated_bytes = chunk_inflated_bytes
-    job = C.c_void_p()
-    ctx.check(lib.fastf_bam2db_begin(ctx.h, C.byref(p), C.byref(job)), "bam2db_begin")
-    res = _lib.Bam2dbResult()
-    try:
+    """The C-ABI call sequence for one BAM image in host memory.  Returns (stats dict, dict of numpy result arrays)."""
+    with Bam2dbJob(ctx, inputs, rate_depth, seed, want_rows, inflate_lanes, chunk_inflated_bytes, umi_max_bytes) as job:
         buf = np.frombuffer(bam_bytes, dtype=np.uint8)
         n = buf.size
         step = feed_piece if feed_piece else max(n, 1)
         for lo in range(0, n, step):
             hi = min(n, lo + step)
-            ctx.check(lib.fastf_bam2db_feed(job, C.c_void_p(buf.ctypes.data + lo), hi - lo), "bam2db_feed")
-        ctx.check(lib.fastf_bam2db_finish(job, C.byref(res)), "bam2db_finish")
-        out = {
-            "m_gene": np.ctypeslib.as_array(res.m_gene, (res.nnz,)).copy() if res.nnz else np.zeros(0, np.uint32),
-            "m_cell": np.ctypeslib.as_array(res.m_cell, (res.nnz,)).copy() if res.nnz else np.zeros(0, np.uint32),
-            "m_count": np.ctypeslib.as_array(res.m_count, (res.nnz,)).copy() if res.nnz else np.zeros(0, np.uint32),
-            "row_keys": np.ctypeslib.as_array(res.row_keys, (res.n_rows,)).copy() if (want_rows and res.n_rows) else np.zeros(0, np.uint64),
-        }
-        stats = {f: getattr(res, f) for f, _ in _lib.Bam2dbResult._fields_ if not f.startswith("m_") and f != "row_keys"}
-        lib.fastf_bam2db_result_free(C.byref(res))
-        return stats, out
-    finally:
-        lib.fastf_bam2db_job_free(job)
+            job.feed(buf.ctypes.data + lo, hi - lo)
+        return job.finish()
 
 
 def matrix_header(bam_file, rate_cell, rate_depth, total, sampled, valid):

@@ -27,11 +27,15 @@
 
 #define FASTF_ABI_VERSION 1
 
+struct PoolEntry { void *p; size_t cap; };
 struct fastf_ctx {
     int device;
     cudaStream_t compute, copy, mt;
     char err[1024];
     u32 launches;   // kernels launched through this context (bench: gpu_launches)
+    // size-bucketed caches of device / pinned allocations: a job's buffers are recycled by the next job on the same
+    // context, so steady-state calls do not pay cudaMalloc / cudaMallocHost (both synchronise the device)
+    std::vector<PoolEntry> *dev_pool, *pin_pool;
 };
 
 static int ctx_fail(fastf_ctx *ctx, const char *fmt, ...)
@@ -70,55 +74,89 @@ static const char *status_string(u32 st, char *buf, size_t n)
     return buf;
 }
 
-// ---- growable device / pinned buffers -------------------------------------------------------------
+// ---- growable device / pinned buffers, recycled through the context's pools ------------------------
+static void *pool_take(std::vector<PoolEntry> &pool, size_t bytes)
+{
+    int best = -1;
+    for (size_t i = 0; i < pool.size(); i++)
+        if (pool[i].cap >= bytes && (best < 0 || pool[i].cap < pool[(size_t)best].cap)) best = (int)i;
+    if (best < 0 || pool[(size_t)best].cap > 2 * bytes + (1u << 20)) return nullptr;   // do not burn a huge buffer on a small request
+    void *p = pool[(size_t)best].p;
+    pool.erase(pool.begin() + best);
+    return p;
+}
+static size_t pool_cap_of(const std::vector<PoolEntry> &pool, size_t bytes)
+{
+    size_t best = 0;
+    for (auto &e : pool)
+        if (e.cap >= bytes && (!best || e.cap < best)) best = e.cap;
+    return best;
+}
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
     template <class T> T *as() const { return (T *)p; }
 };
+static void dev_release(fastf_ctx *ctx, DevBuf &b)
+{
+    if (b.p) ctx->dev_pool->push_back(PoolEntry{b.p, b.cap});
+    b.p = nullptr;
+    b.cap = 0;
+}
 static int dev_reserve(fastf_ctx *ctx, DevBuf &b, size_t bytes, size_t keep_bytes = 0, cudaStream_t s = 0)
 {
     if (bytes <= b.cap) return 0;
     size_t ncap = std::max(bytes, b.cap + b.cap / 2);
     ncap = (ncap + 255) & ~(size_t)255;
+    size_t pc = pool_cap_of(*ctx->dev_pool, ncap);
     void *np = nullptr;
-    CK(cudaMalloc(&np, ncap));
-    if (keep_bytes && b.p) {
-        CK(cudaMemcpyAsync(np, b.p, keep_bytes, cudaMemcpyDeviceToDevice, s));
-        CK(cudaStreamSynchronize(s));
+    if (pc && pc <= 2 * ncap + (1u << 20)) { np = pool_take(*ctx->dev_pool, ncap); ncap = pc; }
+    if (!np) CK(cudaMalloc(&np, ncap));
+    if (b.p) {
+        if (keep_bytes) CK(cudaMemcpyAsync(np, b.p, keep_bytes, cudaMemcpyDeviceToDevice, s));
+        // the old buffer goes back to the pool: nothing in flight on any of our streams may still touch it
+        CK(cudaStreamSynchronize(ctx->compute));
+        CK(cudaStreamSynchronize(ctx->copy));
+        CK(cudaStreamSynchronize(ctx->mt));
+        dev_release(ctx, b);
     }
-    if (b.p) CK(cudaFree(b.p));
     b.p = np;
     b.cap = ncap;
     return 0;
-}
-static void dev_release(DevBuf &b)
-{
-    if (b.p) cudaFree(b.p);
-    b.p = nullptr;
-    b.cap = 0;
 }
 struct PinBuf {
     void *p = nullptr;
     size_t cap = 0;
     template <class T> T *as() const { return (T *)p; }
 };
+static void pin_release(fastf_ctx *ctx, PinBuf &b)
+{
+    if (b.p) ctx->pin_pool->push_back(PoolEntry{b.p, b.cap});
+    b.p = nullptr;
+    b.cap = 0;
+}
 static int pin_reserve(fastf_ctx *ctx, PinBuf &b, size_t bytes)
 {
     if (bytes <= b.cap) return 0;
     size_t ncap = std::max(bytes, b.cap * 2);
-    if (b.p) CK(cudaFreeHost(b.p));
-    b.p = nullptr;
-    b.cap = 0;
-    CK(cudaMallocHost(&b.p, ncap));
-    b.cap = ncap;
+    ncap = (ncap + 63) & ~(size_t)63;
+    if (b.p) {
+        CK(cudaStreamSynchronize(ctx->compute));
+        CK(cudaStreamSynchronize(ctx->copy));
+        CK(cudaStreamSynchronize(ctx->mt));
+        pin_release(ctx, b);
+    }
+    size_t pc = pool_cap_of(*ctx->pin_pool, ncap);
+    if (pc && pc <= 2 * ncap + (1u << 20)) { b.p = pool_take(*ctx->pin_pool, ncap); b.cap = pc; }
+    if (!b.p) { CK(cudaMallocHost(&b.p, ncap)); b.cap = ncap; }
     return 0;
 }
-static void pin_release(PinBuf &b)
+static void pools_trim(fastf_ctx *ctx)
 {
-    if (b.p) cudaFreeHost(b.p);
-    b.p = nullptr;
-    b.cap = 0;
+    for (auto &e : *ctx->dev_pool) cudaFree(e.p);
+    for (auto &e : *ctx->pin_pool) cudaFreeHost(e.p);
+    ctx->dev_pool->clear();
+    ctx->pin_pool->clear();
 }
 
 struct Timer {   // CUDA-event stopwatch on one stream; accumulates into *acc at collect()
@@ -157,6 +195,8 @@ extern "C" int fastf_ctx_create(int device, fastf_ctx **out)
         free(ctx);
         return 1;
     }
+    ctx->dev_pool = new std::vector<PoolEntry>();
+    ctx->pin_pool = new std::vector<PoolEntry>();
     *out = ctx;
     return 0;
 }
@@ -164,6 +204,10 @@ extern "C" void fastf_ctx_destroy(fastf_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    pools_trim(ctx);
+    delete ctx->dev_pool;
+    delete ctx->pin_pool;
     cudaStreamDestroy(ctx->compute);
     cudaStreamDestroy(ctx->copy);
     cudaStreamDestroy(ctx->mt);
@@ -180,6 +224,7 @@ extern "C" int fastf_memcpy_h2d(fastf_ctx *ctx, void *d, const void *s, size_t n
 extern "C" int fastf_memcpy_d2h(fastf_ctx *ctx, void *d, const void *s, size_t n) { CK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, ctx->compute)); CK(cudaStreamSynchronize(ctx->compute)); return 0; }
 extern "C" int fastf_synchronize(fastf_ctx *ctx) { CK(cudaStreamSynchronize(ctx->copy)); CK(cudaStreamSynchronize(ctx->mt)); CK(cudaStreamSynchronize(ctx->compute)); return 0; }
 extern "C" void fastf_free(void *p) { free(p); }
+extern "C" void fastf_ctx_trim(fastf_ctx *ctx) { if (ctx) { cudaSetDevice(ctx->device); cudaDeviceSynchronize(); pools_trim(ctx); } }
 
 // ---------------------------------------------------------------------------------------------------
 // host helpers that define the sampling contract
@@ -372,7 +417,7 @@ static int sort_keys(fastf_ctx *ctx, SortScratch &S, u64 *keys, u64 *alt, u32 *v
     *sorted_in_alt = (src == alt);
     return 0;
 }
-static void sort_scratch_release(SortScratch &S) { dev_release(S.hist); dev_release(S.totals); dev_release(S.dbase); }
+static void sort_scratch_release(fastf_ctx *ctx, SortScratch &S) { dev_release(ctx, S.hist); dev_release(ctx, S.totals); dev_release(ctx, S.dbase); }
 
 // OR / AND of all keys -> which bit positions vary (device reduction, 16 bytes back)
 __global__ void __launch_bounds__(256) fastf_key_bits_kernel(const u64 *__restrict__ keys, u64 n, u64 *__restrict__ or_and)
@@ -388,11 +433,11 @@ struct RleScratch {
     DevBuf tile_counts, tile_totals, grp_key, grp_first, grp_dstart, grp_val, count, out_gene, out_cell;
     PinBuf totals_host;
 };
-static void rle_scratch_release(RleScratch &R)
+static void rle_scratch_release(fastf_ctx *ctx, RleScratch &R)
 {
-    dev_release(R.tile_counts); dev_release(R.tile_totals); dev_release(R.grp_key); dev_release(R.grp_first); dev_release(R.grp_dstart); dev_release(R.grp_val);
-    dev_release(R.count); dev_release(R.out_gene); dev_release(R.out_cell);
-    pin_release(R.totals_host);
+    dev_release(ctx, R.tile_counts); dev_release(ctx, R.tile_totals); dev_release(ctx, R.grp_key); dev_release(ctx, R.grp_first); dev_release(ctx, R.grp_dstart); dev_release(ctx, R.grp_val);
+    dev_release(ctx, R.count); dev_release(ctx, R.out_gene); dev_release(ctx, R.out_cell);
+    pin_release(ctx, R.totals_host);
 }
 // After this: R.grp_key/grp_first/grp_dstart(/grp_val)/count hold ngroups entries on device; with split_bits_gene > 0
 // R.out_gene / R.out_cell hold the split group key.
@@ -515,7 +560,7 @@ static int index_upload(fastf_ctx *ctx, BlockIndexDev &I, cudaStream_t s)
     CK(cudaMemcpyAsync(I.buf.p, I.host.p, index_bytes_up(I.cap_blocks), cudaMemcpyHostToDevice, s));
     return 0;
 }
-static void index_release(BlockIndexDev &I) { dev_release(I.buf); pin_release(I.host); I.cap_blocks = 0; }
+static void index_release(fastf_ctx *ctx, BlockIndexDev &I) { dev_release(ctx, I.buf); pin_release(ctx, I.host); I.cap_blocks = 0; }
 
 // ---------------------------------------------------------------------------------------------------
 // bam2db job
@@ -564,7 +609,7 @@ struct fastf_bam2db_job {
     RleScratch rleS;
     // stats
     u64 n_blocks = 0, comp_bytes = 0, infl_bytes = 0;
-    u32 launches0 = 0;
+    u32 launches0 = 0, n_chunks = 0;
     Timer t_infl[2], t_parse[2], t_gather[2], t_mt[2], t_sample, t_sort, t_count;
     u32 mt_launches = 0;
     cudaEvent_t ev_first = nullptr, ev_last = nullptr;
@@ -584,7 +629,7 @@ extern "C" void fastf_bam2db_job_free(fastf_bam2db_job *job)
     cudaStreamSynchronize(ctx->mt);
     for (int i = 0; i < 2; i++) {
         ChunkSlot &S = job->slot[i];
-        index_release(S.idx); dev_release(S.comp); dev_release(S.stage); pin_release(S.snap);
+        index_release(ctx, S.idx); dev_release(ctx, S.comp); dev_release(ctx, S.stage); pin_release(ctx, S.snap);
         if (S.ev_copy) cudaEventDestroy(S.ev_copy);
         if (S.ev_done) cudaEventDestroy(S.ev_done);
         job->t_infl[i].destroy(); job->t_parse[i].destroy(); job->t_gather[i].destroy();
@@ -593,12 +638,12 @@ extern "C" void fastf_bam2db_job_free(fastf_bam2db_job *job)
     if (job->ev_mt) cudaEventDestroy(job->ev_mt);
     if (job->ev_first) cudaEventDestroy(job->ev_first);
     if (job->ev_last) cudaEventDestroy(job->ev_last);
-    dev_release(job->cells.slots); dev_release(job->cells.pool); dev_release(job->genes.slots); dev_release(job->genes.pool);
-    dev_release(job->infl); dev_release(job->counters); dev_release(job->hdr_off); dev_release(job->cand); dev_release(job->mt_state); dev_release(job->keepbits);
-    dev_release(job->tile_valid); dev_release(job->tile_tot); dev_release(job->sample_counters); dev_release(job->kept); dev_release(job->orand);
-    pin_release(job->small_host);
-    sort_scratch_release(job->sortS);
-    rle_scratch_release(job->rleS);
+    dev_release(ctx, job->cells.slots); dev_release(ctx, job->cells.pool); dev_release(ctx, job->genes.slots); dev_release(ctx, job->genes.pool);
+    dev_release(ctx, job->infl); dev_release(ctx, job->counters); dev_release(ctx, job->hdr_off); dev_release(ctx, job->cand); dev_release(ctx, job->mt_state); dev_release(ctx, job->keepbits);
+    dev_release(ctx, job->tile_valid); dev_release(ctx, job->tile_tot); dev_release(ctx, job->sample_counters); dev_release(ctx, job->kept); dev_release(ctx, job->orand);
+    pin_release(ctx, job->small_host);
+    sort_scratch_release(ctx, job->sortS);
+    rle_scratch_release(ctx, job->rleS);
     delete job;
 }
 
@@ -767,6 +812,7 @@ static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb
     S.nblocks = nb;
     S.pending = true;
     job->n_blocks += nb;
+    job->n_chunks++;
     job->infl_bytes += out_total;
     job->next_slot ^= 1u;
     // now that this chunk is queued, gather the previous one (its counters are long done)
@@ -1041,6 +1087,7 @@ extern "C" int fastf_bam2db_finish(fastf_bam2db_job *job, fastf_bam2db_result *r
         CK(cudaEventElapsedTime(&res->ms_device_total, job->ev_first, job->ev_last));
     }
     res->n_launches = ctx->launches - job->launches0;
+    res->n_chunks = job->n_chunks;
     return 0;
 }
 
@@ -1073,9 +1120,9 @@ extern "C" int fastf_sort_u64_device(fastf_ctx *ctx, uint64_t *dev_keys, uint32_
         if (!rc && dev_vals) rc = cudaMemcpyAsync(dev_vals, valt.p, n * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->compute) != cudaSuccess;
     }
     if (cudaStreamSynchronize(ctx->compute) != cudaSuccess && !rc) rc = ctx_fail(ctx, "sort_u64_device: stream error");
-    sort_scratch_release(S);
-    dev_release(alt);
-    dev_release(valt);
+    sort_scratch_release(ctx, S);
+    dev_release(ctx, alt);
+    dev_release(ctx, valt);
     return rc;
 }
 
@@ -1088,7 +1135,7 @@ extern "C" int fastf_dedup_count_device(fastf_ctx *ctx, const uint64_t *dev_sort
     int rc = rle_groups(ctx, R, dev_sorted_keys, nullptr, n, bits_umi, bits_umi - 1, bits_gene, &ng, nullptr, ctx->compute);
     if (!rc) rc = coo_to_host(ctx, R, ng, m_gene, m_cell, m_count, ctx->compute);
     *nnz = ng;
-    rle_scratch_release(R);
+    rle_scratch_release(ctx, R);
     return rc;
 }
 
@@ -1159,10 +1206,10 @@ extern "C" int fastf_unique_partition_device(fastf_ctx *ctx, uint64_t *dev_keys,
     };
     rc = body();
     cudaStreamSynchronize(s);
-    sort_scratch_release(S);
-    rle_scratch_release(R);
-    dev_release(alt); dev_release(orand); dev_release(bounds);
-    pin_release(host);
+    sort_scratch_release(ctx, S);
+    rle_scratch_release(ctx, R);
+    dev_release(ctx, alt); dev_release(ctx, orand); dev_release(ctx, bounds);
+    pin_release(ctx, host);
     return rc;
 }
 
@@ -1175,7 +1222,7 @@ struct InflatedFile {
     u64 n_blocks = 0, infl_bytes = 0;
     u32 status = 0;
 };
-static void inflated_release(InflatedFile &F) { dev_release(F.comp); dev_release(F.infl); index_release(F.idx); }
+static void inflated_release(fastf_ctx *ctx, InflatedFile &F) { dev_release(ctx, F.comp); dev_release(ctx, F.infl); index_release(ctx, F.idx); }
 
 // Inflate a whole BGZF image (host bytes, or device bytes + host index) into F.infl in one launch.
 static int inflate_whole(fastf_ctx *ctx, InflatedFile &F, const void *host_bytes, size_t n, const u8 *dev_bytes, const std::vector<FastfBgzfBlock> *pre, int lanes, float *ms, cudaStream_t s)
@@ -1241,7 +1288,7 @@ extern "C" int fastf_inflate_host(fastf_ctx *ctx, const void *bgzf_bytes, size_t
         if (!rc && F.infl_bytes) rc = fastf_memcpy_d2h(ctx, *out, F.infl.p, F.infl_bytes);
         *out_n = F.infl_bytes;
     }
-    inflated_release(F);
+    inflated_release(ctx, F);
     return rc;
 }
 
@@ -1261,8 +1308,8 @@ static int mt_host_common(fastf_ctx *ctx, uint32_t seed, uint64_t n, uint64_t th
         if (cudaGetLastError() != cudaSuccess) rc = ctx_fail(ctx, "mt19937 launch failed");
     }
     if (!rc) rc = out_words ? fastf_memcpy_d2h(ctx, out_words, out.p, (size_t)n * sizeof(u32)) : fastf_memcpy_d2h(ctx, out_bits, out.p, (size_t)((n + 31) / 32) * sizeof(u32));
-    dev_release(state);
-    dev_release(out);
+    dev_release(ctx, state);
+    dev_release(ctx, out);
     return rc;
 }
 extern "C" int fastf_mt19937_host(fastf_ctx *ctx, uint32_t seed, uint64_t n, uint32_t *out_words) { return mt_host_common(ctx, seed, n, 0, out_words, nullptr); }
@@ -1280,8 +1327,8 @@ extern "C" int fastf_sort_u64_host(fastf_ctx *ctx, uint64_t *keys, uint32_t *val
     if (!rc) rc = fastf_sort_u64_device(ctx, dk.as<u64>(), vals ? dv.as<u32>() : nullptr, n, key_bits);
     if (!rc) rc = fastf_memcpy_d2h(ctx, keys, dk.p, n * sizeof(u64));
     if (!rc && vals) rc = fastf_memcpy_d2h(ctx, vals, dv.p, n * sizeof(u32));
-    dev_release(dk);
-    dev_release(dv);
+    dev_release(ctx, dk);
+    dev_release(ctx, dv);
     return rc;
 }
 
@@ -1297,11 +1344,11 @@ static int freq_on_text(fastf_ctx *ctx, const u8 *text, u64 n, u32 key_len, fast
     RleScratch R;
     Timer t_keys, t_sort, t_rle;
     auto cleanup = [&]() {
-        dev_release(tiles); dev_release(tot); dev_release(keys); dev_release(exc_cnt); dev_release(exc_ord); dev_release(exc_bytes); dev_release(ckeys); dev_release(cidx);
-        dev_release(kalt); dev_release(valt); dev_release(orand);
-        pin_release(host);
-        sort_scratch_release(S);
-        rle_scratch_release(R);
+        dev_release(ctx, tiles); dev_release(ctx, tot); dev_release(ctx, keys); dev_release(ctx, exc_cnt); dev_release(ctx, exc_ord); dev_release(ctx, exc_bytes); dev_release(ctx, ckeys); dev_release(ctx, cidx);
+        dev_release(ctx, kalt); dev_release(ctx, valt); dev_release(ctx, orand);
+        pin_release(ctx, host);
+        sort_scratch_release(ctx, S);
+        rle_scratch_release(ctx, R);
         t_keys.destroy(); t_sort.destroy(); t_rle.destroy();
     };
     auto body = [&]() -> int {
@@ -1463,8 +1510,8 @@ static int freq_common(fastf_ctx *ctx, const void *host_bytes, size_t n, const u
     cudaEventElapsedTime(&res->ms_device_total, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    inflated_release(F);
-    dev_release(plain);
+    inflated_release(ctx, F);
+    dev_release(ctx, plain);
     res->n_launches = ctx->launches - l0;
     if (rc) fastf_freq_result_free(res);
     return rc;

@@ -39,6 +39,8 @@ void fastf_device_free(fastf_ctx *ctx, void *p);
 int fastf_memcpy_h2d(fastf_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int fastf_memcpy_d2h(fastf_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 int fastf_synchronize(fastf_ctx *ctx);
+/* device and pinned buffers of finished jobs are cached in the context; this returns them to the driver */
+void fastf_ctx_trim(fastf_ctx *ctx);
 /* kernels launched through this context so far (bench.py: gpu_launches) */
 uint32_t fastf_launch_count(const fastf_ctx *ctx);
 /* the cudaStream_t all hot-path kernels are launched on (for external CUDA-event timing) */
@@ -88,6 +90,7 @@ typedef struct {
     uint64_t n_blocks, compressed_bytes, inflated_bytes;
     uint32_t status;            /* OR of FASTF_ST_* bits seen (0 = clean) */
     uint32_t n_launches;        /* kernels launched for this job */
+    uint32_t n_chunks;          /* inflate (= parse) launches: one per streamed chunk */
     /* device time, CUDA events on the launching stream, milliseconds */
     float ms_inflate, ms_parse, ms_gather, ms_mt, ms_sample, ms_sort, ms_count, ms_device_total;
 } fastf_bam2db_result;

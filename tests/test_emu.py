@@ -1,0 +1,46 @@
+"""CPU tests of the KERNEL LOGIC: the same .cu/.cuh sources compiled with g++ under tests/emu/cuda_emu.h (a cooperative SIMT
+emulator: fibers per CUDA thread, warp collectives and __syncthreads as rendezvous, deadlock detection).  This is test
+infrastructure; the product never loads the emulator build.  The real parity tests are the -m gpu ones."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    from fastf_b200 import build
+    return build.build_emu()
+
+
+def _run(emu_lib, names, shuffle=None):
+    env = dict(os.environ, FASTF_GPU_LIB=emu_lib)
+    if shuffle:
+        env["FASTF_EMU_SHUFFLE"] = str(shuffle)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "run_emu_case.py")] + names, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
+
+
+def test_emu_inflate_adversarial_streams():
+    """stored / fixed / dynamic / RLE / huffman-only / empty / 64 KiB / multi-stored blocks + corrupt streams, byte-for-byte vs zlib"""
+    exe = os.path.join(ROOT, "tests", "emu", "_build", "emu_inflate")
+    src = os.path.join(ROOT, "tests", "emu", "emu_inflate.cpp")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-DFASTF_EMU", "-I" + os.path.join(ROOT, "tests", "emu"), "-o", exe, src, "-lz"], check=True)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "FAIL" not in r.stdout, r.stdout[-2000:]
+
+
+def test_emu_bam2db_edge_cases(emu_lib):
+    _run(emu_lib, ["edge-c0.5-r0.5-s926"])
+
+
+def test_emu_bam2db_edge_cases_shuffled_schedule(emu_lib):
+    _run(emu_lib, ["edge-c1.0-r1.0-s926"], shuffle=7)
+
+
+def test_emu_freq_ragged(emu_lib):
+    _run(emu_lib, ["freq-ragged-l16-u12", "freq-ragged_nonl-l16-u0", "freq-ragged_trunc-l5-u3"])

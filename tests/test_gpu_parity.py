@@ -1,0 +1,275 @@
+"""GPU parity tests (run on the B200 with `-m gpu`): the CUDA path, called through the C-ABI, against the CPU oracle on the
+same seeded inputs, against the golden fixtures recorded from the unmodified reference, and -- at large sizes -- through
+size-independent properties.  Bit-exact everywhere (integer / byte work)."""
+import ctypes as C
+import gzip
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _cases(kind):
+    p = os.path.join(GOLD, "manifest.json")
+    return [c for c in json.load(open(p))["cases"] if c["kind"] == kind] if os.path.exists(p) else []
+
+
+# ------------------------------------------------------------------------------------------------ single kernels
+def test_mt19937_stream_matches_reference_generator(gpu_ctx, oracle):
+    from fastf_b200 import _lib
+    n = 3_000_001
+    for seed in (926, 5489, 0, 0xFFFFFFFF):
+        out = np.zeros(n, dtype=np.uint32)
+        gpu_ctx.check(gpu_ctx.lib.fastf_mt19937_host(gpu_ctx.h, seed, n, out.ctypes.data_as(_lib.c_u32p)), "mt")
+        assert np.array_equal(out, oracle.mt_stream(seed, n))
+    out = np.zeros(10000, dtype=np.uint32)
+    gpu_ctx.check(gpu_ctx.lib.fastf_mt19937_host(gpu_ctx.h, 5489, 10000, out.ctypes.data_as(_lib.c_u32p)), "mt")
+    assert int(out[-1]) == 4123659995   # public mt19937ar known answer
+
+
+@pytest.mark.parametrize("rate", [0.0, 0.1, 0.3, 0.5, 0.9, 1.0])
+def test_keep_bits_match_reference_rule(gpu_ctx, oracle, rate):
+    from fastf_b200 import _lib
+    n = 1_000_003
+    T = gpu_ctx.lib.fastf_keep_threshold(C.c_float(rate))
+    bits = np.zeros((n + 31) // 32, dtype=np.uint32)
+    gpu_ctx.check(gpu_ctx.lib.fastf_mt19937_keepbits_host(gpu_ctx.h, 926, n, T, bits.ctypes.data_as(_lib.c_u32p)), "keepbits")
+    got = np.unpackbits(bits.view(np.uint8), bitorder="little")[:n].astype(bool)
+    u = oracle.mt_stream(926, n)
+    want = (u.astype(np.float64) * (1.0 / 4294967295.0)) < np.float64(np.float32(rate))   # genrand_real1() >= rate -> drop
+    assert np.array_equal(got, want)
+
+
+def _inflate(gpu_ctx, img, lanes):
+    buf = np.frombuffer(img, dtype=np.uint8)
+    out, n, ms = C.c_void_p(), C.c_size_t(), C.c_float()
+    rc = gpu_ctx.lib.fastf_inflate_host(gpu_ctx.h, C.c_void_p(buf.ctypes.data), buf.size, lanes, C.byref(out), C.byref(n), C.byref(ms))
+    if rc:
+        return None
+    data = C.string_at(out, n.value)
+    gpu_ctx.lib.fastf_free(out)
+    return data
+
+
+@pytest.mark.parametrize("lanes", [32, 16, 8])
+def test_inflate_adversarial_blocks(gpu_ctx, lanes):
+    import bamgen
+    rng = np.random.default_rng(3)
+    payloads = [b"", b"a", b"abc" * 20000, bytes(rng.integers(0, 256, 65280, dtype=np.uint8)), bytes(rng.integers(0, 4, 65536, dtype=np.uint8)),
+                b"\0" * 65536, bytes(rng.integers(65, 70, 40000, dtype=np.uint8)), (b"ACGT" * 7 + b"N") * 2000, bytes(range(256)) * 255]
+    modes = [(6, zlib.Z_DEFAULT_STRATEGY), (0, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED), (9, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE), (1, zlib.Z_DEFAULT_STRATEGY)]
+    for shift in range(len(modes)):
+        use = []
+        for i, p in enumerate(payloads):
+            lvl, strat = modes[(i + shift) % len(modes)]
+            if lvl == 0 and len(p) > 65000:
+                lvl = 1   # a stored 64 KiB payload does not fit one BGZF block
+            if len(p) > 65000 and strat in (zlib.Z_HUFFMAN_ONLY, zlib.Z_FIXED) and p[:1] != b"\0":
+                strat = zlib.Z_DEFAULT_STRATEGY
+            use.append((lvl, strat))
+        img = b"".join(bamgen.bgzf_block(p, *m) for p, m in zip(payloads, use)) + bamgen.EOF_BLOCK
+        assert _inflate(gpu_ctx, img, lanes) == b"".join(payloads)
+
+
+def test_inflate_flags_corrupt_streams(gpu_ctx):
+    import bamgen
+    good = bamgen.bgzf_block(b"hello world, hello world, hello world" * 100)
+    for pos in (20, 25, 40):
+        bad = bytearray(good)
+        bad[pos] ^= 0xFF
+        img = bytes(bad) + bamgen.EOF_BLOCK
+        out = _inflate(gpu_ctx, img, 32)
+        want = None
+        try:
+            want = zlib.decompress(bytes(bad[18:-8]), -15)
+        except zlib.error:
+            pass
+        if want is None or len(want) != 3700:
+            assert out is None, "corrupt stream at byte %d must be reported" % pos
+            assert b"malformed" in gpu_ctx.lib.fastf_last_error(gpu_ctx.h)
+
+
+def test_inflate_synthetic_bam_vs_zlib(gpu_ctx, synth, oracle):
+    p = synth.params(n_reads=100000, n_cells=500, n_genes=800, seed=21)
+    bam, st = synth.bam(p)
+    want = oracle.inflate(bam)
+    for lanes in (32, 16, 8):
+        assert _inflate(gpu_ctx, bam, lanes) == want
+
+
+@pytest.mark.parametrize("n,bits", [(1, 64), (1000, 20), (2049, 64), (1 << 20, 54), (3_000_017, 58)])
+def test_radix_sort_is_a_stable_sort(gpu_ctx, n, bits):
+    from fastf_b200 import _lib
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 2**63, n, dtype=np.uint64) >> np.uint64(64 - bits) if bits < 64 else rng.integers(0, 2**64, n, dtype=np.uint64)
+    keys[: n // 3] = keys[n // 2: n // 2 + n // 3]   # plenty of duplicates
+    vals = np.arange(n, dtype=np.uint32)
+    k2, v2 = keys.copy(), vals.copy()
+    gpu_ctx.check(gpu_ctx.lib.fastf_sort_u64_host(gpu_ctx.h, k2.ctypes.data_as(_lib.c_u64p), v2.ctypes.data_as(_lib.c_u32p), n, bits), "sort")
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k2, keys[order]) and np.array_equal(v2, order.astype(np.uint32))
+    k3 = keys.copy()
+    gpu_ctx.check(gpu_ctx.lib.fastf_sort_u64_host(gpu_ctx.h, k3.ctypes.data_as(_lib.c_u64p), None, n, bits), "sort")
+    assert np.array_equal(k3, k2)
+
+
+# ------------------------------------------------------------------------------------------------ bam2db
+def _oracle_rows_as_keys(o, stats):
+    bg, bu, mb = stats["bits_gene"], stats["bits_umi"], stats["umi_max_bytes"]
+    nb = o["row_umi_nbytes"].astype(np.int64)
+    content = (o["row_umi"].astype(np.uint64) >> np.uint64(64 - 8 * mb))
+    code = np.where(nb >= 0, (np.uint64(1) << np.uint64(bu - 1)) | (content << np.uint64(3)) | np.maximum(nb, 0).astype(np.uint64), np.uint64(0))
+    return (o["row_cell"].astype(np.uint64) << np.uint64(bg + bu)) | (o["row_gene"].astype(np.uint64) << np.uint64(bu)) | code
+
+
+def _check_against_oracle(gpu_ctx, oracle, paths, rc, rd, seed, **kw):
+    from fastf_b200 import bam2db_host as B
+    want = oracle.bam2db(paths["bam"], paths["barcodes"], paths["features"], rc, rd, seed)
+    inputs = B.Bam2dbInputs(gpu_ctx.lib, paths["barcodes"], paths["features"], rc, seed)
+    assert inputs.d0 == want["d0"] and len(inputs.cells) == want["n_cell_rows"] and len(inputs.features) == want["n_features"]
+    stats, out = B.run_device(gpu_ctx, np.fromfile(paths["bam"], dtype=np.uint8), inputs, rd, seed, want_rows=True, **kw)
+    for k in ("total", "cb_valid", "sampled", "valid", "nnz"):
+        assert stats[k] == want[k], (k, stats[k], want[k])
+    assert np.array_equal(out["m_gene"], want["m_gene"])
+    assert np.array_equal(out["m_cell"], want["m_cell"])
+    assert np.array_equal(out["m_count"], want["m_count"])
+    assert np.array_equal(out["row_keys"], _oracle_rows_as_keys(want, stats))   # the sqlite `umi` table, in read order
+    return stats, out
+
+
+@pytest.mark.parametrize("rc,rd,seed", [(0.5, 0.5, 926), (1.0, 0.3, 926), (1.0, 1.0, 1), (0.2, 0.9, 77), (0.9, 0.1, 4242), (0.5, 0.0, 5)])
+def test_bam2db_matches_oracle(gpu_ctx, oracle, synth, tmp_path, rc, rd, seed):
+    paths, _ = synth.write_bam_set(str(tmp_path), n_reads=300000, n_cells=1000, n_genes=2000, seed=seed, p_umi_n=0.005, n_molecules=100000)
+    _check_against_oracle(gpu_ctx, oracle, paths, rc, rd, seed)
+
+
+def test_bam2db_config1_shape(gpu_ctx, oracle, synth, tmp_path):
+    """BASELINE.json configs[0]: 1M reads, 1k cells, 2k genes, -c 0.5 -r 0.5 -s 926"""
+    paths, _ = synth.write_bam_set(str(tmp_path), n_reads=1000000, n_cells=1000, n_genes=2000, seed=11, p_umi_n=0.001)
+    stats, _ = _check_against_oracle(gpu_ctx, oracle, paths, 0.5, 0.5, 926)
+    assert stats["total"] == 1000000
+
+
+@pytest.mark.parametrize("lanes,chunk,piece", [(32, 1 << 20, 0), (16, 3 << 20, 1000003), (8, 0, 65536), (32, 1 << 20, 777)])
+def test_bam2db_streaming_is_invariant(gpu_ctx, oracle, synth, tmp_path, lanes, chunk, piece):
+    """any chunking of the inflated stream and any split of the compressed bytes (also inside BGZF blocks) gives the same result"""
+    paths, _ = synth.write_bam_set(str(tmp_path), n_reads=60000, n_cells=300, n_genes=500, seed=9, p_umi_n=0.01, n_molecules=20000)
+    _check_against_oracle(gpu_ctx, oracle, paths, 0.7, 0.6, 31, inflate_lanes=lanes, chunk_inflated_bytes=chunk, feed_piece=piece)
+
+
+@pytest.mark.parametrize("case", _cases("bam2db"), ids=lambda c: c["name"])
+def test_bam2db_golden_files(gpu_ctx, case, tmp_path):
+    """the whole operator (files in, files out) against outputs recorded from the unmodified reference; includes the edge-case BAM"""
+    import sqlite3
+    import fastf_b200
+    d = os.path.join(GOLD, case["dir"])
+    out = str(tmp_path)
+    cwd = os.getcwd()
+    os.chdir(d)
+    try:
+        assert fastf_b200.bam2db("in.bam", os.path.join(out, "x.db"), out, "barcodes.tsv.gz", "features.tsv.gz", case["rate_cell"], case["rate_depth"], case["seed"], ctx=gpu_ctx) == 0
+    finally:
+        os.chdir(cwd)
+    for f in ("matrix.mtx.gz", "barcodes.tsv.gz", "features.tsv.gz"):
+        assert gzip.open(os.path.join(out, f), "rb").read() == gzip.open(os.path.join(d, case["expect"], f), "rb").read(), f
+    db = sqlite3.connect(os.path.join(out, "x.db"))
+    n_umi, n_null = db.execute("select count(*), sum(encoded_umi is null) from umi").fetchone()
+    assert n_umi == case["counters"][2]
+    # the device COO equals what the reference's SQL computes from the umi table the device produced
+    sql = db.execute("SELECT feature_index, cell_index, COUNT(DISTINCT encoded_umi) FROM umi GROUP BY cell_index, feature_index").fetchall()
+    assert sql == db.execute("select * from mtx").fetchall()
+
+
+def test_bam2db_rejects_truncated_and_foreign_input(gpu_ctx, synth, tmp_path):
+    from fastf_b200 import bam2db_host as B, _lib
+    import bamgen
+    paths, _ = synth.write_bam_set(str(tmp_path), n_reads=5000, n_cells=50, n_genes=50, seed=2)
+    inputs = B.Bam2dbInputs(gpu_ctx.lib, paths["barcodes"], paths["features"], 1.0, 926)
+    bam = np.fromfile(paths["bam"], dtype=np.uint8)
+    with pytest.raises(_lib.FastfError, match="ends inside a BGZF block"):
+        B.run_device(gpu_ctx, bam[:-100].copy(), inputs, 1.0, 926)
+    with pytest.raises(_lib.FastfError, match="not a BGZF"):
+        B.run_device(gpu_ctx, np.frombuffer(gzip.compress(b"hello" * 100), dtype=np.uint8), inputs, 1.0, 926)
+    # a record split across two BGZF blocks (foreign writer): reported, never silently mis-parsed
+    raw = zlib.decompress(bytes(bam[18:]), -15) if False else None
+    whole = gzip.decompress(bytes(bam))
+    img = bamgen.bgzf_file([whole[i:i + 10007] for i in range(0, len(whole), 10007)])
+    with pytest.raises(_lib.FastfError, match="straddles"):
+        B.run_device(gpu_ctx, np.frombuffer(img, dtype=np.uint8), inputs, 1.0, 926)
+
+
+def test_bam2db_large_properties(gpu_ctx, synth, tmp_path):
+    """size-independent properties on a run too large for the oracle to be comfortable: counters are consistent, the COO is
+    strictly ascending in (cell, gene), sum(count) = number of distinct non-NULL keys, -r 1.0 keeps every draw but u = 2^32-1,
+    feeding the record blocks twice doubles the read counters and leaves distinct counts unchanged (idempotence of dedup)."""
+    from fastf_b200 import bam2db_host as B
+    from fastf_b200 import _lib
+    paths, st = synth.write_bam_set(str(tmp_path), n_reads=4_000_000, n_cells=5000, n_genes=20000, seed=77, p_umi_n=0.002)
+    inputs = B.Bam2dbInputs(gpu_ctx.lib, paths["barcodes"], paths["features"], 1.0, 926)
+    bam = np.fromfile(paths["bam"], dtype=np.uint8)
+    stats, out = B.run_device(gpu_ctx, bam, inputs, 1.0, 926, want_rows=True)
+    assert stats["total"] == 4_000_000 and stats["sampled"] == stats["cb_valid"] and stats["valid"] <= stats["sampled"]
+    ck = out["m_cell"].astype(np.uint64) << np.uint64(32) | out["m_gene"].astype(np.uint64)
+    assert np.all(ck[1:] > ck[:-1])
+    rows = out["row_keys"]
+    nn = (rows >> np.uint64(stats["bits_umi"] - 1)) & np.uint64(1)
+    assert int(out["m_count"].sum()) == np.unique(rows[nn == 1]).size
+    assert stats["nnz"] == np.unique(rows >> np.uint64(stats["bits_umi"])).size
+    # feed the record blocks twice
+    cap = int(st.n_blocks) + 8
+    io, il, isz = np.zeros(cap, np.uint64), np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+    used = C.c_size_t()
+    nb = gpu_ctx.lib.fastf_bgzf_index_host(C.c_void_p(bam.ctypes.data), bam.size, io.ctypes.data_as(_lib.c_u64p), il.ctypes.data_as(_lib.c_u32p), isz.ctypes.data_as(_lib.c_u32p), cap, C.byref(used))
+    first_rec, eof = int(io[1]) - 18, int(io[nb - 1]) - 18
+    with B.Bam2dbJob(gpu_ctx, inputs, 1.0, 926, want_rows=False) as job:
+        job.feed(bam.ctypes.data, eof)
+        job.feed(bam.ctypes.data + first_rec, eof - first_rec)
+        job.feed(bam.ctypes.data + eof, bam.size - eof)
+        s2, o2 = job.finish()
+    assert s2["total"] == 2 * stats["total"] and s2["cb_valid"] == 2 * stats["cb_valid"]
+    assert s2["nnz"] == stats["nnz"] and np.array_equal(o2["m_count"], out["m_count"]) and np.array_equal(o2["m_gene"], out["m_gene"])
+
+
+# ------------------------------------------------------------------------------------------------ freq
+@pytest.mark.parametrize("case", _cases("freq"), ids=lambda c: c["name"])
+def test_freq_golden_files(gpu_ctx, case, tmp_path):
+    import fastf_b200
+    d = os.path.join(GOLD, case["dir"])
+    assert fastf_b200.freq(os.path.join(d, case["input"]), str(tmp_path), case["l"], case["u"], ctx=gpu_ctx) == 0
+    assert open(tmp_path / "whitelist.txt", "rb").read() == gzip.open(os.path.join(d, case["expect"]), "rb").read()
+
+
+@pytest.mark.parametrize("n,cells,l,u", [(400000, 2000, 16, 12), (400000, 20000, 16, 0), (250000, 300, 16, 10), (100000, 50, 4, 0)])
+def test_freq_matches_oracle(gpu_ctx, oracle, synth, tmp_path, n, cells, l, u):
+    import fastf_b200
+    fq, _ = synth.write_fastq(str(tmp_path), n_reads=n, n_cells=cells, seed=n + l, p_umi_n=0.01)
+    assert fastf_b200.freq(fq, str(tmp_path), l, u, ctx=gpu_ctx) == 0
+    oracle.freq(fq, l, u, str(tmp_path / "want.txt"))
+    assert open(tmp_path / "whitelist.txt", "rb").read() == open(tmp_path / "want.txt", "rb").read()
+
+
+def test_freq_plain_text_input_and_gzip_refusal(gpu_ctx, oracle, tmp_path):
+    import fastf_b200
+    raw = gzip.open(os.path.join(GOLD, "freq", "ragged.fastq.gz"), "rb").read()
+    (tmp_path / "plain.fastq").write_bytes(raw)
+    assert fastf_b200.freq(str(tmp_path / "plain.fastq"), str(tmp_path), 16, 12, ctx=gpu_ctx) == 0
+    assert open(tmp_path / "whitelist.txt", "rb").read() == gzip.open(os.path.join(GOLD, "freq", "expect_ragged_l16_u12.txt.gz"), "rb").read()
+    (tmp_path / "single.fastq.gz").write_bytes(gzip.compress(raw))
+    assert fastf_b200.freq(str(tmp_path / "single.fastq.gz"), str(tmp_path), 16, 12, ctx=gpu_ctx) == 1   # loud refusal, not a CPU fallback
+
+
+def test_freq_large_properties(gpu_ctx, synth, tmp_path):
+    """counts sum to the number of reads; keys strictly ascending; first-occurrence ordinals are a valid insertion order"""
+    from fastf_b200 import freq_host as F
+    fq, _ = synth.write_fastq(str(tmp_path), n_reads=6_000_000, n_cells=20000, seed=1, p_umi_n=0.001)
+    st = {}
+    h = F.cell_counts(fq, 16, 12, ctx=gpu_ctx, stats_out=st)
+    assert h.n_reads == 6_000_000 and int(np.sum(h.count)) == 6_000_000
+    assert all(h.keys[i] < h.keys[i + 1] for i in range(0, len(h.keys) - 1, 997))
+    assert len(set(h.first.tolist())) == len(h.keys) and int(h.first.min()) == 0
