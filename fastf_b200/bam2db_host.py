@@ -280,10 +280,10 @@ def bam2db(bam_file, db_file, path_out, barcodes_file, features_file, rate_cell,
         if inputs.duplicate_features:
             print("Warning: Duplicate feature names were found in %s!" % features_file)
         db.execute("BEGIN TRANSACTION")
-        db.executemany("INSERT INTO cell VALUES (?1);", ((c.decode("latin-1"),) for c in inputs.cells))
+        db.executemany("INSERT INTO cell VALUES (?);", ((c.decode("latin-1"),) for c in inputs.cells))
         db.execute("END TRANSACTION")
         db.execute("BEGIN TRANSACTION")
-        db.executemany("INSERT INTO feature VALUES (?1, ?2, ?3);", ((f[1].decode("latin-1"), f[2].decode("latin-1"), f[3].decode("latin-1")) for f in inputs.features))
+        db.executemany("INSERT INTO feature VALUES (?, ?, ?);", ((f[1].decode("latin-1"), f[2].decode("latin-1"), f[3].decode("latin-1")) for f in inputs.features))
         db.execute("END TRANSACTION")
         print("Start to convert bam file to sqlite3 database...")
         sys.stdout.flush()
@@ -296,7 +296,7 @@ def bam2db(bam_file, db_file, path_out, barcodes_file, features_file, rate_cell,
             for c, g, nb, ct in zip(cell.tolist(), gene.tolist(), nbytes.tolist(), content.tolist()):
                 yield (c, g, None if nb < 0 else ct.to_bytes(mb, "big")[:nb])
         db.execute("BEGIN TRANSACTION")
-        db.executemany("INSERT INTO umi VALUES (?1, ?2, ?3);", rows())
+        db.executemany("INSERT INTO umi VALUES (?, ?, ?);", rows())
         db.execute("END TRANSACTION")
         print("In %s, total fastQ reads: %d" % (bam_file, stats["total"]))
         print("In %s, sampled fastQ reads: %d" % (bam_file, stats["sampled"]))
@@ -304,7 +304,7 @@ def bam2db(bam_file, db_file, path_out, barcodes_file, features_file, rate_cell,
         # table mtx from the device COO, with the schema text sqlite gives `CREATE TABLE mtx AS SELECT ...` (src/bam2db_ds.c:480-483)
         db.execute("CREATE TABLE mtx(\n  feature_index INT,\n  cell_index INT,\n  expression_level\n)")
         db.execute("BEGIN TRANSACTION")
-        db.executemany("INSERT INTO mtx VALUES (?1, ?2, ?3);", zip(out["m_gene"].tolist(), out["m_cell"].tolist(), out["m_count"].tolist()))
+        db.executemany("INSERT INTO mtx VALUES (?, ?, ?);", zip(out["m_gene"].tolist(), out["m_cell"].tolist(), out["m_count"].tolist()))
         db.execute("END TRANSACTION")
         try:
             fb = gzip.open(os.path.join(path_out, "barcodes.tsv.gz"), "wb")
@@ -331,7 +331,7 @@ def bam2db(bam_file, db_file, path_out, barcodes_file, features_file, rate_cell,
             c2, g2, nb2, ct2 = decode_rows(uniq, stats["bits_gene"], stats["bits_umi"], stats["umi_max_bytes"])
             db.execute("CREATE TABLE numi(\n  feature_index INT,\n  cell_index INT,\n  encoded_umi TEXT,\n  n_copy\n)")
             db.execute("BEGIN TRANSACTION")
-            db.executemany("INSERT INTO numi VALUES (?1, ?2, ?3, ?4);",
+            db.executemany("INSERT INTO numi VALUES (?, ?, ?, ?);",
                            ((g, c, None if nb < 0 else ct.to_bytes(mb, "big")[:nb], n) for c, g, nb, ct, n in zip(c2.tolist(), g2.tolist(), nb2.tolist(), ct2.tolist(), counts.tolist())))
             db.execute("END TRANSACTION")
             with gzip.open(os.path.join(path_out, "umi.tsv.gz"), "wb") as fu:

@@ -33,14 +33,29 @@ __device__ __forceinline__ void fastf_prefetch_l1(const void *p) { asm volatile(
 inline void fastf_prefetch_l1(const void *) {}
 #endif
 
-// warp-cooperative lookup of s[0..len) in a string table; every lane gets the value (0 = absent)
-__device__ __forceinline__ u32 fastf_table_lookup(const FastfStrTableView &T, u32 my_pw1, u32 my_pw2, const u8 *__restrict__ s, u32 len, u32 lane)
+// Byte accessors over the inflated stream: the shared-memory window of the current warp (normal case) or
+// global memory (records larger than the window).  off is an offset into the chunk's inflated buffer.
+struct FastfWinAcc {
+    const u8 *W;
+    u64 wbase;
+    __device__ __forceinline__ u32 byte(u64 off) const { return W[off - wbase]; }
+};
+struct FastfGlobAcc {
+    const u8 *infl;
+    __device__ __forceinline__ u32 byte(u64 off) const { return infl[off]; }
+};
+template <class Acc> __device__ __forceinline__ u32 fastf_acc_u16(const Acc &A, u64 off) { return A.byte(off) | (A.byte(off + 1) << 8); }
+template <class Acc> __device__ __forceinline__ u32 fastf_acc_u32(const Acc &A, u64 off) { return A.byte(off) | (A.byte(off + 1) << 8) | (A.byte(off + 2) << 16) | (A.byte(off + 3) << 24); }
+
+// warp-cooperative lookup of the len bytes at offset s in a string table; every lane gets the value (0 = absent)
+template <class Acc>
+__device__ __forceinline__ u32 fastf_table_lookup(const FastfStrTableView &T, u32 my_pw1, u32 my_pw2, const Acc &A, u64 s, u32 len, u32 lane)
 {
     u32 h1 = 0, h2 = 0;
     u32 c = 0;
     do {
         u32 i = c + lane;
-        u32 byte = (i < len) ? (u32)s[i] + 1u : 0u;
+        u32 byte = (i < len) ? A.byte(s + i) + 1u : 0u;
         u32 s1 = __reduce_add_sync(FASTF_FULL_MASK, byte * my_pw1);
         u32 s2 = __reduce_add_sync(FASTF_FULL_MASK, byte * my_pw2);
         h1 = h1 * FASTF_H1_Q + s1;
@@ -55,7 +70,7 @@ __device__ __forceinline__ u32 fastf_table_lookup(const FastfStrTableView &T, u3
             bool same = true;
             for (u32 c2 = 0; c2 < len; c2 += 32) {
                 u32 i = c2 + lane;
-                bool ok = (i >= len) || (s[i] == T.pool[e.off + i]);
+                bool ok = (i >= len) || (A.byte(s + i) == T.pool[e.off + i]);
                 same = same && __all_sync(FASTF_FULL_MASK, ok);
             }
             if (same) return e.value;
@@ -64,9 +79,10 @@ __device__ __forceinline__ u32 fastf_table_lookup(const FastfStrTableView &T, u3
     }
 }
 
-struct FastfAuxHit { u32 off; u32 len; u32 type; };   // off = offset of the value inside the inflated buffer
+struct FastfAuxHit { u64 off; u32 len; u32 type; };   // off = offset of the value inside the inflated buffer
 
 #define FASTF_PARSE_WARPS 4
+#define FASTF_PARSE_WIN 2048   // bytes of the block staged in shared memory per warp
 
 // BAM header walk (what sam_hdr_read does at reference src/bam2db_ds.c:340): "BAM\1", l_text, text, n_ref,
 // (l_name, name, l_ref) x n_ref.  One thread; writes the inflated offset of the first alignment record.
@@ -87,14 +103,127 @@ __global__ void fastf_bam_header_kernel(const u8 *__restrict__ infl, u64 n, u64 
     *first_record_off = p;
 }
 
+// One alignment record [rec, rend) (after its block_size word): the reference's per-read decision up to the draw.
+// Returns 0 = not CB-valid (no candidate), 1 = candidate with *key set (FASTF_INVALID_KEY when it would not be inserted).
+template <class Acc>
+__device__ __forceinline__ u32 fastf_parse_record(const Acc &A, u64 rec, u64 rend, u32 bs, const FastfStrTableView &cells, const FastfStrTableView &genes, const FastfKeyLayout &L,
+                                                  u32 c_pw1, u32 c_pw2, u32 g_pw1, u32 g_pw2, u32 lane, u32 *status, u64 *key_out)
+{
+    const u32 l_read_name = A.byte(rec + 8);
+    const u32 n_cigar = fastf_acc_u16(A, rec + 12);
+    const i32 l_seq = (i32)fastf_acc_u32(A, rec + 16);
+    const i64 aoff = 32 + (i64)l_read_name + 4 * (i64)n_cigar + (((i64)l_seq + 1) >> 1) + (i64)l_seq;
+    if (l_seq < 0 || aoff > (i64)bs) { *status |= FASTF_ST_REC_CORRUPT; return 2; }
+
+    // ---- aux walk: find the first CB, xf, GX, UB ----
+    FastfAuxHit cb = {0, 0, 0}, xf = {0, 0, 0}, gx = {0, 0, 0}, ub = {0, 0, 0};
+    u32 found = 0;
+    u64 q = rec + (u64)aoff;
+    while (rend - q >= 3 && found != 15u) {
+        const u32 t0 = A.byte(q), t1 = A.byte(q + 1), ty = A.byte(q + 2);
+        const u64 v = q + 3;
+        u64 next;
+        u32 vlen = 0;
+        if (ty == 'Z' || ty == 'H') {
+            bool term = false;
+            u64 s = v;
+            while (s < rend) {
+                u64 i = s + lane;
+                bool z = (i < rend) && (A.byte(i) == 0);
+                u32 m = __ballot_sync(FASTF_FULL_MASK, z);
+                if (m) { s += (u32)__ffs((int)m) - 1u; term = true; break; }
+                s += 32;
+            }
+            if (!term) break;   // htslib: a malformed field hides this and every later tag; not a failure
+            vlen = (u32)(s - v);
+            next = s + 1;
+        } else {
+            u64 sz;
+            switch (ty) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'd': sz = 8; break;
+            case 'B': {
+                if (rend - v < 5) { sz = ~0ull; break; }
+                u32 sub = A.byte(v);
+                u64 cnt = fastf_acc_u32(A, v + 1);
+                u64 es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
+                sz = es ? 5 + es * cnt : ~0ull;
+                break;
+            }
+            default: sz = ~0ull;
+            }
+            if (sz == ~0ull || sz > rend - v) break;
+            next = v + sz;
+        }
+        if (t0 == 'C' && t1 == 'B' && !(found & 1u)) { cb.off = v; cb.len = vlen; cb.type = ty; found |= 1u; }
+        else if (t0 == 'x' && t1 == 'f' && !(found & 2u)) { xf.off = v; xf.type = ty; found |= 2u; }
+        else if (t0 == 'G' && t1 == 'X' && !(found & 4u)) { gx.off = v; gx.len = vlen; gx.type = ty; found |= 4u; }
+        else if (t0 == 'U' && t1 == 'B' && !(found & 8u)) { ub.off = v; ub.len = vlen; ub.type = ty; found |= 8u; }
+        q = next;
+    }
+
+    // ---- CB gate: present, string-typed, in the sampled-cell table ----
+    if (!(found & 1u) || !(cb.type == 'Z' || cb.type == 'H')) return 0;
+    const u32 cidx = fastf_table_lookup(cells, c_pw1, c_pw2, A, cb.off, cb.len, lane);
+    if (cidx == 0) return 0;
+
+    // ---- this record consumes a draw; decide whether it would be inserted if kept ----
+    u64 key = FASTF_INVALID_KEY;
+    i64 xfv = 0;
+    if (found & 2u) {
+        const u64 x = xf.off;
+        switch (xf.type) {
+        case 'c': xfv = (i64)(int8_t)A.byte(x); break;
+        case 'C': xfv = A.byte(x); break;
+        case 's': xfv = (i64)(int16_t)fastf_acc_u16(A, x); break;
+        case 'S': xfv = fastf_acc_u16(A, x); break;
+        case 'i': xfv = (i64)(i32)fastf_acc_u32(A, x); break;
+        case 'I': xfv = fastf_acc_u32(A, x); break;
+        default: xfv = 0;
+        }
+    }
+    const int xfi = (int)xfv;   // the reference stores bam_aux2i() in an int
+    if ((xfi == 25 || xfi == 17) && (found & 4u) && (gx.type == 'Z' || gx.type == 'H') && (found & 8u) && (ub.type == 'Z' || ub.type == 'H')) {
+        const u32 gidx = fastf_table_lookup(genes, g_pw1, g_pw2, A, gx.off, gx.len, lane);
+        if (gidx != 0) {
+            if (ub.len > 4u * L.umi_max_bytes) {
+                *status |= FASTF_ST_UMI_TOO_LONG;
+            } else {
+                u32 code = 0, badbase = 0;
+                if (lane < ub.len) {
+                    u32 ch = A.byte(ub.off + lane);
+                    code = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
+                    badbase = code > 3u;
+                }
+                u32 hi = __reduce_or_sync(FASTF_FULL_MASK, (lane < 16u && !badbase) ? (code << (30u - 2u * lane)) : 0u);
+                u32 anybad = __any_sync(FASTF_FULL_MASK, badbase);
+                u64 ucode = 0;   // SQL NULL
+                if (!anybad) {
+                    u64 content = (u64)(hi >> (32u - 8u * L.umi_max_bytes));
+                    u64 nbytes = (ub.len + 3u) >> 2;
+                    ucode = (1ull << (L.bits_umi - 1u)) | (content << 3) | nbytes;
+                }
+                key = ((u64)cidx << (L.bits_gene + L.bits_umi)) | ((u64)gidx << L.bits_umi) | ucode;
+            }
+        }
+    }
+    *key_out = key;
+    return 1;
+}
+
+// infl_total = readable bytes of the inflated buffer (>= end of the last block, multiple of 16)
 __global__ void __launch_bounds__(FASTF_PARSE_WARPS * 32)
-fastf_bam_parse_kernel(const u8 *__restrict__ infl, const u64 *__restrict__ blk_off, const u32 *__restrict__ blk_isize, u32 nblocks, const u64 *__restrict__ first_record_off_ptr,
+fastf_bam_parse_kernel(const u8 *__restrict__ infl, u64 infl_total, const u64 *__restrict__ blk_off, const u32 *__restrict__ blk_isize, u32 nblocks, const u64 *__restrict__ first_record_off_ptr,
                        FastfStrTableView cells, FastfStrTableView genes, FastfKeyLayout L,
                        const u64 *__restrict__ stage_off, u64 *__restrict__ stage, u32 *__restrict__ blk_nrec, u32 *__restrict__ blk_ncbv, u32 *__restrict__ blk_status)
 {
+    __shared__ __align__(16) u8 s_win[FASTF_PARSE_WARPS][FASTF_PARSE_WIN];
     const u32 lane = threadIdx.x & 31u;
     const u32 b = blockIdx.x * FASTF_PARSE_WARPS + (threadIdx.x >> 5);
     if (b >= nblocks) return;
+    u8 *W = s_win[threadIdx.x >> 5];
     const u32 c_pw1 = cells.pw1[lane], c_pw2 = cells.pw2[lane];
     const u32 g_pw1 = genes.pw1[lane], g_pw2 = genes.pw2[lane];
     const u64 bstart = blk_off[b], bend = bstart + blk_isize[b];
@@ -102,120 +231,43 @@ fastf_bam_parse_kernel(const u8 *__restrict__ infl, const u64 *__restrict__ blk_
     u64 p = bstart > first_record_off ? bstart : first_record_off;
     u64 *out = stage + stage_off[b];
     u32 nrec = 0, ncbv = 0, status = 0;
+    u64 wbase = 0, wend = 0;   // the window holds infl[wbase, wend)
 
     while (p < bend) {
         if (bend - p < 4) { status |= FASTF_ST_REC_STRADDLE; break; }
-        const u32 bs = fastf_ld_u32(infl + p);
+        // make sure the record's length word and fixed fields are in the window
+        bool reloaded = false;
+        if (p < wbase || p + 36 > wend) {
+            wbase = p & ~15ull;
+            wend = wbase + FASTF_PARSE_WIN < infl_total ? wbase + FASTF_PARSE_WIN : infl_total;
+            __syncwarp();
+            for (u32 o = lane * 16u; wbase + o < wend; o += 512u) *reinterpret_cast<uint4 *>(W + o) = *reinterpret_cast<const uint4 *>(infl + wbase + o);
+            __syncwarp();
+            reloaded = true;
+        }
+        FastfWinAcc WA = {W, wbase};
+        const u32 bs = (p + 4 <= wend) ? fastf_acc_u32(WA, p) : fastf_ld_u32(infl + p);
         if ((i32)bs < 32) { status |= FASTF_ST_REC_CORRUPT; break; }
         if (p + 4 + (u64)bs > bend) { status |= FASTF_ST_REC_STRADDLE; break; }
         const u64 rec = p + 4, rend = rec + bs;
+        u64 key = 0;
+        u32 r;
+        if (rend <= wend) {
+            r = fastf_parse_record(WA, rec, rend, bs, cells, genes, L, c_pw1, c_pw2, g_pw1, g_pw2, lane, &status, &key);
+        } else if (!reloaded && (u64)bs + 4 + 16 <= FASTF_PARSE_WIN) {
+            wend = 0;      // slide the window to this record and take it again
+            continue;
+        } else {
+            FastfGlobAcc GA = {infl};   // a record larger than the window: walk it in global memory
+            r = fastf_parse_record(GA, rec, rend, bs, cells, genes, L, c_pw1, c_pw2, g_pw1, g_pw2, lane, &status, &key);
+        }
+        if (r == 2) break;
         p = rend;
-        // pull the next record's lines towards L1 while this one is parsed
-        { u64 a = rend + (u64)lane * 128u; if (lane < 4 && a < bend) fastf_prefetch_l1(infl + a); }
         nrec++;
-        const u32 l_read_name = infl[rec + 8];
-        const u32 n_cigar = fastf_ld_u16(infl + rec + 12);
-        const i32 l_seq = (i32)fastf_ld_u32(infl + rec + 16);
-        const i64 aoff = 32 + (i64)l_read_name + 4 * (i64)n_cigar + (((i64)l_seq + 1) >> 1) + (i64)l_seq;
-        if (l_seq < 0 || aoff > (i64)bs) { status |= FASTF_ST_REC_CORRUPT; break; }
-
-        // ---- aux walk: find the first CB, xf, GX, UB ----
-        FastfAuxHit cb = {0, 0, 0}, xf = {0, 0, 0}, gx = {0, 0, 0}, ub = {0, 0, 0};
-        u32 found = 0;
-        u64 q = rec + (u64)aoff;
-        while (rend - q >= 3 && found != 15u) {
-            const u32 t0 = infl[q], t1 = infl[q + 1], ty = infl[q + 2];
-            const u64 v = q + 3;
-            u64 next;
-            u32 vlen = 0;
-            if (ty == 'Z' || ty == 'H') {
-                bool term = false;
-                u64 s = v;
-                while (s < rend) {
-                    u64 i = s + lane;
-                    bool z = (i < rend) && (infl[i] == 0);
-                    u32 m = __ballot_sync(FASTF_FULL_MASK, z);
-                    if (m) { s += (u32)__ffs((int)m) - 1u; term = true; break; }
-                    s += 32;
-                }
-                if (!term) break;   // htslib: a malformed field hides this and every later tag; not a failure
-                vlen = (u32)(s - v);
-                next = s + 1;
-            } else {
-                u64 sz;
-                switch (ty) {
-                case 'A': case 'c': case 'C': sz = 1; break;
-                case 's': case 'S': sz = 2; break;
-                case 'i': case 'I': case 'f': sz = 4; break;
-                case 'd': sz = 8; break;
-                case 'B': {
-                    if (rend - v < 5) { sz = ~0ull; break; }
-                    u32 sub = infl[v];
-                    u64 cnt = fastf_ld_u32(infl + v + 1);
-                    u64 es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
-                    sz = es ? 5 + es * cnt : ~0ull;
-                    break;
-                }
-                default: sz = ~0ull;
-                }
-                if (sz == ~0ull || sz > rend - v) break;
-                next = v + sz;
-            }
-            if (t0 == 'C' && t1 == 'B' && !(found & 1u)) { cb.off = (u32)(v - bstart); cb.len = vlen; cb.type = ty; found |= 1u; }
-            else if (t0 == 'x' && t1 == 'f' && !(found & 2u)) { xf.off = (u32)(v - bstart); xf.type = ty; found |= 2u; }
-            else if (t0 == 'G' && t1 == 'X' && !(found & 4u)) { gx.off = (u32)(v - bstart); gx.len = vlen; gx.type = ty; found |= 4u; }
-            else if (t0 == 'U' && t1 == 'B' && !(found & 8u)) { ub.off = (u32)(v - bstart); ub.len = vlen; ub.type = ty; found |= 8u; }
-            q = next;
+        if (r == 1) {
+            if (lane == 0) out[ncbv] = key;
+            ncbv++;
         }
-
-        // ---- CB gate: present, string-typed, in the sampled-cell table ----
-        if (!(found & 1u) || !(cb.type == 'Z' || cb.type == 'H')) continue;
-        const u32 cidx = fastf_table_lookup(cells, c_pw1, c_pw2, infl + bstart + cb.off, cb.len, lane);
-        if (cidx == 0) continue;
-
-        // ---- this record consumes a draw; decide whether it would be inserted if kept ----
-        u64 key = FASTF_INVALID_KEY;
-        i64 xfv = 0;
-        if (found & 2u) {
-            const u8 *x = infl + bstart + xf.off;
-            switch (xf.type) {
-            case 'c': xfv = (i64)(int8_t)x[0]; break;
-            case 'C': xfv = x[0]; break;
-            case 's': xfv = (i64)(int16_t)fastf_ld_u16(x); break;
-            case 'S': xfv = fastf_ld_u16(x); break;
-            case 'i': xfv = (i64)(i32)fastf_ld_u32(x); break;
-            case 'I': xfv = fastf_ld_u32(x); break;
-            default: xfv = 0;
-            }
-        }
-        const int xfi = (int)xfv;   // the reference stores bam_aux2i() in an int
-        if ((xfi == 25 || xfi == 17) && (found & 4u) && (gx.type == 'Z' || gx.type == 'H') && (found & 8u) && (ub.type == 'Z' || ub.type == 'H')) {
-            const u32 gidx = fastf_table_lookup(genes, g_pw1, g_pw2, infl + bstart + gx.off, gx.len, lane);
-            if (gidx != 0) {
-                if (ub.len > 4u * L.umi_max_bytes) {
-                    status |= FASTF_ST_UMI_TOO_LONG;
-                } else {
-                    const u8 *u = infl + bstart + ub.off;
-                    u32 code = 0, badbase = 0;
-                    if (lane < ub.len) {
-                        u32 ch = u[lane];
-                        code = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
-                        badbase = code > 3u;
-                    }
-                    u32 hi = __reduce_or_sync(FASTF_FULL_MASK, (lane < 16u && !badbase) ? (code << (30u - 2u * lane)) : 0u);
-                    u32 anybad = __any_sync(FASTF_FULL_MASK, badbase);
-                    u64 ucode = 0;   // SQL NULL
-                    if (!anybad) {
-                        u64 content = (u64)(hi >> (32u - 8u * L.umi_max_bytes));
-                        u64 nbytes = (ub.len + 3u) >> 2;
-                        ucode = (1ull << (L.bits_umi - 1u)) | (content << 3) | nbytes;
-                    }
-                    key = ((u64)cidx << (L.bits_gene + L.bits_umi)) | ((u64)gidx << L.bits_umi) | ucode;
-                }
-            }
-        }
-        if (lane == 0) out[ncbv] = key;
-        ncbv++;
     }
     if (lane == 0) { blk_nrec[b] = nrec; blk_ncbv[b] = ncbv; blk_status[b] = status; }
 }

@@ -21,9 +21,19 @@
 #define FASTF_INFL_LBITS 10
 #define FASTF_INFL_DBITS 8
 
+// Decode-table entry (u32), everything a symbol needs folded into one shared-memory read:
+//   bits 0-3   code length in bits (0 = not in the primary table: canonical walk)
+//   bits 4-7   number of extra bits that follow the code
+//   bits 8-9   kind: 0 literal / plain symbol, 1 length or distance base, 2 end of block, 3 invalid symbol
+//   bits 16-31 literal byte, code-length symbol, or the length / distance base value
+#define FASTF_E_LIT 0u
+#define FASTF_E_BASE (1u << 8)
+#define FASTF_E_EOB (2u << 8)
+#define FASTF_E_BAD (3u << 8)
+
 struct FastfInflTables {
-    u16 lit_lut[1 << FASTF_INFL_LBITS];
-    u16 dist_lut[1 << FASTF_INFL_DBITS];
+    u32 lit_lut[1 << FASTF_INFL_LBITS];
+    u32 dist_lut[1 << FASTF_INFL_DBITS];
     u16 lit_sorted[288];
     u16 dist_sorted[32];
     u16 lit_cnt[16];
@@ -46,6 +56,22 @@ __constant__ u8 FASTF_LEN_EXTRA[32] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2,
 __constant__ u16 FASTF_DIST_BASE[32] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577, 0, 0};
 __constant__ u8 FASTF_DIST_EXTRA[32] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 0, 0};
 __constant__ u8 FASTF_CL_ORDER[20] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15, 0};
+
+enum { FASTF_ALPHA_PLAIN = 0, FASTF_ALPHA_LITLEN = 1, FASTF_ALPHA_DIST = 2 };
+
+// table entry of symbol `sym` (without the code length) for one of the three alphabets
+__device__ __forceinline__ u32 fastf_make_entry(const FastfInflConst &K, u32 alpha, u32 sym)
+{
+    if (alpha == FASTF_ALPHA_PLAIN) return FASTF_E_LIT | (sym << 16);
+    if (alpha == FASTF_ALPHA_LITLEN) {
+        if (sym < 256) return FASTF_E_LIT | (sym << 16);
+        if (sym == 256) return FASTF_E_EOB;
+        if (sym > 285) return FASTF_E_BAD;
+        return FASTF_E_BASE | ((u32)K.len_extra[sym - 257] << 4) | ((u32)K.len_base[sym - 257] << 16);
+    }
+    if (sym >= 30) return FASTF_E_BAD;
+    return FASTF_E_BASE | ((u32)K.dist_extra[sym] << 4) | ((u32)K.dist_base[sym] << 16);
+}
 
 // ---- lane-cooperative bit reader: identical (buf, nbits, widx) in every lane of the group ----
 template <int G> struct FastfBitReader {
@@ -95,7 +121,7 @@ template <int G> struct FastfBitReader {
 // Build one canonical Huffman decoding table from code lengths lens[0..n).
 // Returns 0 ok, non-zero for an over-subscribed or (non-trivially) incomplete code.
 template <int G>
-__device__ __forceinline__ u32 fastf_build_table(FastfInflTables &T, const u8 *lens, u32 n, u16 *cnt, u16 *sorted, u16 *lut, u32 tbits, u32 gmask, u32 glane)
+__device__ __forceinline__ u32 fastf_build_table(FastfInflTables &T, const FastfInflConst &K, u32 alpha, const u8 *lens, u32 n, u16 *cnt, u16 *sorted, u32 *lut, u32 tbits, u32 gmask, u32 glane)
 {
     for (u32 i = glane; i < (1u << tbits); i += G) lut[i] = 0;
     u32 bad = 0;
@@ -137,7 +163,7 @@ __device__ __forceinline__ u32 fastf_build_table(FastfInflTables &T, const u8 *l
         if (l <= tbits) {
             u32 code = (u32)T.first[l] + (i - (u32)T.start[l]);
             u32 rev = __brev(code) >> (32 - l);
-            u16 e = (u16)((sym << 4) | l);
+            u32 e = fastf_make_entry(K, alpha, sym) | l;
             for (u32 j = rev; j < (1u << tbits); j += (1u << l)) lut[j] = e;
         }
     }
@@ -145,35 +171,93 @@ __device__ __forceinline__ u32 fastf_build_table(FastfInflTables &T, const u8 *l
     return 0;
 }
 
-// Decode one symbol.  Needs >= 15 valid bits in br.buf.  Returns 0xffff when no code matches.
+// Decode one symbol without consuming it: returns its table entry (code length in bits 0-3).  Needs >= 15 valid
+// bits in br.buf.  An undecodable code returns FASTF_E_BAD with length 0.
 template <int G>
-__device__ __forceinline__ u32 fastf_decode_sym(FastfBitReader<G> &br, const u16 *lut, u32 tbits, const u16 *cnt, const u16 *sorted)
+__device__ __forceinline__ u32 fastf_decode_entry(const FastfBitReader<G> &br, const FastfInflConst &K, u32 alpha, const u32 *lut, u32 tbits, const u16 *cnt, const u16 *sorted)
 {
     u32 e = lut[(u32)br.buf & ((1u << tbits) - 1u)];
-    u32 l = e & 15u;
-    if (l) { br.drop(l); return e >> 4; }
-    // canonical walk for codes longer than the LUT (or absent codes)
+    if (e & 15u) return e;
+    // canonical walk for codes longer than the primary table (or absent codes)
     u32 code = 0, first = 0, index = 0;
     u32 bits = (u32)br.buf;
     for (u32 len = 1; len < 16; len++) {
         code |= bits & 1u;
         bits >>= 1;
         u32 c = cnt[len];
-        if (code < first + c) { br.drop(len); return sorted[index + (code - first)]; }
+        if (code < first + c) return fastf_make_entry(K, alpha, sorted[index + (code - first)]) | len;
         index += c;
         first = (first + c) << 1;
         code <<= 1;
     }
-    return 0xffffu;
+    return FASTF_E_BAD;
 }
+
+// Output side of one group: literal runs and match pieces are written as coalesced <= G-byte stores; match pieces
+// are kept in registers for FASTF_PENDING matches so that the L2 round trip of their source loads overlaps the
+// decoding of the following symbols.
+#define FASTF_PEND_SLOTS 3
+template <int G> struct FastfOutQueue {
+    u8 *out;
+    u32 glane;
+    u32 run_start, run_n, run_byte;          // literal run: lane i holds literal i
+    u32 ppos[FASTF_PEND_SLOTS], pn[FASTF_PEND_SLOTS], pbyte[FASTF_PEND_SLOTS];   // [0] = oldest
+
+    __device__ __forceinline__ void init(u8 *o, u32 gl)
+    {
+        out = o; glane = gl; run_start = 0; run_n = 0; run_byte = 0;
+#pragma unroll
+        for (int k = 0; k < FASTF_PEND_SLOTS; k++) { ppos[k] = 0; pn[k] = 0; pbyte[k] = 0; }
+    }
+    __device__ __forceinline__ void literal(u32 pos, u32 byte)
+    {
+        if (run_n == 0) run_start = pos;
+        if (glane == run_n) run_byte = byte;
+        run_n++;
+        if (run_n == (u32)G) flush_run();
+    }
+    __device__ __forceinline__ void flush_run()
+    {
+        if (glane < run_n) out[run_start + glane] = (u8)run_byte;
+        run_n = 0;
+    }
+    __device__ __forceinline__ void store_slot(int k)
+    {
+        if (glane < pn[k]) out[ppos[k] + glane] = (u8)pbyte[k];
+        pn[k] = 0;
+    }
+    __device__ __forceinline__ void flush_pending()
+    {
+#pragma unroll
+        for (int k = 0; k < FASTF_PEND_SLOTS; k++) store_slot(k);
+    }
+    // lowest output position that is still only in registers (or ~0u)
+    __device__ __forceinline__ u32 pending_lo() const
+    {
+        u32 lo = 0xffffffffu;
+#pragma unroll
+        for (int k = FASTF_PEND_SLOTS - 1; k >= 0; k--)
+            if (pn[k]) lo = ppos[k];
+        return lo;
+    }
+    __device__ __forceinline__ void push(u32 pos, u32 n, u32 byte)
+    {
+        store_slot(0);
+#pragma unroll
+        for (int k = 0; k + 1 < FASTF_PEND_SLOTS; k++) { ppos[k] = ppos[k + 1]; pn[k] = pn[k + 1]; pbyte[k] = pbyte[k + 1]; }
+        ppos[FASTF_PEND_SLOTS - 1] = pos; pn[FASTF_PEND_SLOTS - 1] = n; pbyte[FASTF_PEND_SLOTS - 1] = byte;
+    }
+};
 
 // Inflate one raw deflate stream of in_len bytes at comp+in_off into out[0..isize).  Returns status bits.
 template <int G>
-__device__ u32 fastf_inflate_stream(const u8 *__restrict__ comp, u64 comp_total, u64 in_off, u32 in_len, u8 *__restrict__ out, u32 isize,
+__device__ u32 fastf_inflate_stream(const u8 *__restrict__ comp, u64 comp_total, u64 in_off, u32 in_len, u8 *out, u32 isize,
                                     FastfInflTables &T, const FastfInflConst &K, u32 gmask, u32 glane)
 {
     FastfBitReader<G> br;
     br.init(comp, comp_total, in_off, gmask, glane);
+    FastfOutQueue<G> Q;
+    Q.init(out, glane);
     u32 pos = 0, err = 0;
     bool last = false;
     while (!last && !err) {
@@ -193,6 +277,8 @@ __device__ u32 fastf_inflate_stream(const u8 *__restrict__ comp, u64 comp_total,
             u64 consumed_bits = (u64)br.widx * 32u - br.nbits - br.skip_bits;   // multiple of 8 here
             u64 src_off = in_off + (consumed_bits >> 3);
             if ((consumed_bits >> 3) + len > (u64)in_len) { err |= FASTF_ST_BAD_STORED; break; }
+            Q.flush_run();
+            Q.flush_pending();
             for (u32 i = glane; i < len; i += G) out[pos + i] = comp[src_off + i];
             pos += len;
             // restart the reader after the raw bytes, keeping in_off as the origin for the overrun check
@@ -223,18 +309,20 @@ __device__ u32 fastf_inflate_stream(const u8 *__restrict__ comp, u64 comp_total,
                 if (glane == 0) T.lens[K.cl_order[i]] = (u8)v;
             }
             __syncwarp(gmask);
-            // code-length code: 7-bit LUT in the distance table's storage
-            if (fastf_build_table<G>(T, T.lens, 19, T.dist_cnt, T.dist_sorted, T.dist_lut, 7, gmask, glane)) { err |= FASTF_ST_BAD_CODELENS; break; }
+            // code-length code: 7-bit table in the distance table's storage
+            if (fastf_build_table<G>(T, K, FASTF_ALPHA_PLAIN, T.lens, 19, T.dist_cnt, T.dist_sorted, T.dist_lut, 7, gmask, glane)) { err |= FASTF_ST_BAD_CODELENS; break; }
             u32 n = hlit + hdist, i = 0, prev = 0;
             while (i < n) {
                 br.refill();
-                u32 sym = fastf_decode_sym<G>(br, T.dist_lut, 7, T.dist_cnt, T.dist_sorted);
+                u32 e = fastf_decode_entry<G>(br, K, FASTF_ALPHA_PLAIN, T.dist_lut, 7, T.dist_cnt, T.dist_sorted);
+                if ((e & 15u) == 0) { err |= FASTF_ST_BAD_CODELENS; break; }
+                br.drop(e & 15u);
+                u32 sym = e >> 16;
                 u32 rep, val;
                 if (sym < 16) { rep = 1; val = sym; prev = sym; }
                 else if (sym == 16) { if (i == 0) { err |= FASTF_ST_BAD_CODELENS; break; } rep = 3 + br.take(2); val = prev; }
                 else if (sym == 17) { rep = 3 + br.take(3); val = 0; prev = 0; }
-                else if (sym == 18) { rep = 11 + br.take(7); val = 0; prev = 0; }
-                else { err |= FASTF_ST_BAD_CODELENS; break; }
+                else { rep = 11 + br.take(7); val = 0; prev = 0; }
                 if (i + rep > n) { err |= FASTF_ST_BAD_CODELENS; break; }
                 for (u32 k = glane; k < rep; k += G) T.lens[i + k] = (u8)val;
                 i += rep;
@@ -243,39 +331,51 @@ __device__ u32 fastf_inflate_stream(const u8 *__restrict__ comp, u64 comp_total,
             __syncwarp(gmask);
             if (T.lens[256] == 0) { err |= FASTF_ST_BAD_CODELENS; break; }
         }
-        if (fastf_build_table<G>(T, T.lens, hlit, T.lit_cnt, T.lit_sorted, T.lit_lut, FASTF_INFL_LBITS, gmask, glane)) { err |= FASTF_ST_BAD_CODELENS; break; }
-        if (fastf_build_table<G>(T, T.lens + hlit, hdist, T.dist_cnt, T.dist_sorted, T.dist_lut, FASTF_INFL_DBITS, gmask, glane)) { err |= FASTF_ST_BAD_CODELENS; break; }
+        if (fastf_build_table<G>(T, K, FASTF_ALPHA_LITLEN, T.lens, hlit, T.lit_cnt, T.lit_sorted, T.lit_lut, FASTF_INFL_LBITS, gmask, glane)) { err |= FASTF_ST_BAD_CODELENS; break; }
+        if (fastf_build_table<G>(T, K, FASTF_ALPHA_DIST, T.lens + hlit, hdist, T.dist_cnt, T.dist_sorted, T.dist_lut, FASTF_INFL_DBITS, gmask, glane)) { err |= FASTF_ST_BAD_CODELENS; break; }
 
         // ---- symbol loop ----
         for (;;) {
             br.refill();
-            u32 sym = fastf_decode_sym<G>(br, T.lit_lut, FASTF_INFL_LBITS, T.lit_cnt, T.lit_sorted);
-            if (sym < 256) {
+            u32 e = fastf_decode_entry<G>(br, K, FASTF_ALPHA_LITLEN, T.lit_lut, FASTF_INFL_LBITS, T.lit_cnt, T.lit_sorted);
+            const u32 kind = e & (3u << 8);
+            if (kind == FASTF_E_LIT) {
                 if (pos >= isize) { err |= FASTF_ST_OUT_OVERFLOW; break; }
-                if (glane == 0) out[pos] = (u8)sym;
+                br.drop(e & 15u);
+                Q.literal(pos, e >> 16);
                 pos++;
                 continue;
             }
-            if (sym == 256) break;
-            if (sym > 285) { err |= FASTF_ST_BAD_SYMBOL; break; }
-            sym -= 257;
-            u32 len = (u32)K.len_base[sym] + br.take(K.len_extra[sym]);
+            if (kind == FASTF_E_EOB) { br.drop(e & 15u); break; }
+            if (kind == FASTF_E_BAD) { err |= FASTF_ST_BAD_SYMBOL; break; }
+            br.drop(e & 15u);
+            const u32 len = (e >> 16) + br.take((e >> 4) & 15u);
             br.refill();
-            u32 dsym = fastf_decode_sym<G>(br, T.dist_lut, FASTF_INFL_DBITS, T.dist_cnt, T.dist_sorted);
-            if (dsym >= 30) { err |= FASTF_ST_BAD_SYMBOL; break; }
-            u32 dist = (u32)K.dist_base[dsym] + br.take(K.dist_extra[dsym]);
+            const u32 d = fastf_decode_entry<G>(br, K, FASTF_ALPHA_DIST, T.dist_lut, FASTF_INFL_DBITS, T.dist_cnt, T.dist_sorted);
+            if ((d & (3u << 8)) != FASTF_E_BASE) { err |= FASTF_ST_BAD_SYMBOL; break; }
+            br.drop(d & 15u);
+            const u32 dist = (d >> 16) + br.take((d >> 4) & 15u);
             if (dist > pos) { err |= FASTF_ST_BAD_DISTANCE; break; }
             if (pos + len > isize) { err |= FASTF_ST_OUT_OVERFLOW; break; }
+            // the copy: sources are [pos-dist, pos-dist+min(len,dist)).  Literals go out now; match pieces still held in
+            // registers must be written first only when the source reaches into them.
+            Q.flush_run();
+            const u32 s0 = pos - dist;
+            const u32 s1 = s0 + (len < dist ? len : dist);
+            if (s1 > Q.pending_lo()) Q.flush_pending();
             __syncwarp(gmask);   // earlier stores by other lanes of the group are ordered before these loads
-            const u8 *src = out + pos - dist;
-            if (dist >= len) {
-                for (u32 i = glane; i < len; i += G) out[pos + i] = src[i];
-            } else {
-                for (u32 i = glane; i < len; i += G) out[pos + i] = src[i % dist];
+            const u8 *src = out + s0;
+            for (u32 k = 0; k < len; k += G) {
+                const u32 j = k + glane;
+                u32 b = 0;
+                if (j < len) b = src[dist >= len ? j : j % dist];
+                Q.push(pos + k, (len - k) < (u32)G ? (len - k) : (u32)G, b);
             }
             pos += len;
         }
     }
+    Q.flush_run();
+    Q.flush_pending();
     if (!err) {
         if (pos != isize) err |= FASTF_ST_SIZE_MISMATCH;
         if (br.bytes_consumed() > (u64)in_len) err |= FASTF_ST_IN_OVERRUN;
@@ -288,8 +388,8 @@ __device__ u32 fastf_inflate_stream(const u8 *__restrict__ comp, u64 comp_total,
 // the block's offset in the contiguous inflated buffer.  comp must be 4-byte aligned; comp_total is
 // the number of readable bytes (>= last payload end, padded to a multiple of 4).
 template <int G>
-__global__ void __launch_bounds__(32) fastf_bgzf_inflate_kernel(const u8 *__restrict__ comp, u64 comp_total, const u64 *__restrict__ in_off, const u32 *__restrict__ in_len,
-                                                               const u64 *__restrict__ out_off, const u32 *__restrict__ isize, u32 nblocks, u8 *__restrict__ out, u32 *__restrict__ status)
+__global__ void __launch_bounds__(32, G == 32 ? 32 : 16) fastf_bgzf_inflate_kernel(const u8 *__restrict__ comp, u64 comp_total, const u64 *__restrict__ in_off, const u32 *__restrict__ in_len,
+                                                               const u64 *__restrict__ out_off, const u32 *__restrict__ isize, u32 nblocks, u8 *out, u32 *__restrict__ status)
 {
     __shared__ FastfInflTables tabs[32 / G];
     __shared__ FastfInflConst K;

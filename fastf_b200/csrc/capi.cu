@@ -798,7 +798,7 @@ static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb
         CK(cudaMemsetAsync(job->hdr_off.p, 0, sizeof(u64), ctx->compute));
     }
     if (nb) {
-        FASTF_LAUNCH(fastf_bam_parse_kernel, (nb + FASTF_PARSE_WARPS - 1) / FASTF_PARSE_WARPS, FASTF_PARSE_WARPS * 32, 0, ctx->compute, (const u8 *)job->infl.as<u8>(),
+        FASTF_LAUNCH(fastf_bam_parse_kernel, (nb + FASTF_PARSE_WARPS - 1) / FASTF_PARSE_WARPS, FASTF_PARSE_WARPS * 32, 0, ctx->compute, (const u8 *)job->infl.as<u8>(), (u64)((out_total + 15) & ~15ull),
                      (const u64 *)S.idx.out_off, (const u32 *)S.idx.isize, nb, (const u64 *)job->hdr_off.as<u64>(), job->cells.view, job->genes.view, job->L, (const u64 *)S.idx.stage_off,
                      S.stage.as<u64>(), S.idx.nrec, S.idx.ncbv, S.idx.st_parse);
         CKL("bam_parse");

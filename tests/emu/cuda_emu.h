@@ -65,6 +65,7 @@ inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) 
 #define __constant__ static const
 #define __restrict__
 #define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
 
 inline dim3 threadIdx, blockIdx, blockDim, gridDim;
 using std::max;
