@@ -60,16 +60,23 @@ def build_synth(force=False):
     return SYNTH_LIB
 
 
-def build_cli(force=False):
+def build_cli(force=False, emu=False):
+    """The C host (`fastF bam2db|freq`).  emu=True links the SIMT-emulator build of the kernels instead (tests only)."""
     host = os.path.join(PKG, "host")
     srcs = _sources(host, (".c",))
     if not srcs:
         return None
     deps = srcs + _sources(host, (".h",)) + [os.path.join(ROOT, "include", "fastf_gpu.h")]
-    if force or not _newer(CLI_BIN, deps):
-        _run(["gcc", "-O2", "-std=gnu11", "-Wall", "-Wno-unused-result", "-I" + os.path.join(ROOT, "include"), "-o", CLI_BIN] + srcs +
-             ["-L" + BUILD, "-lfastf_gpu", "-Wl,-rpath,$ORIGIN", "-lz", "-l:libsqlite3.so.0", "-lm", "-ldl"])
-    return CLI_BIN
+    if emu:
+        libdir, libname, out = os.path.join(ROOT, "tests", "emu", "_build"), "fastf_emu", os.path.join(ROOT, "tests", "emu", "_build", "fastF_emu")
+        deps.append(build_emu())
+    else:
+        libdir, libname, out = BUILD, "fastf_gpu", CLI_BIN
+        deps.append(LIB)
+    if force or not _newer(out, deps):
+        _run(["gcc", "-O2", "-std=gnu11", "-Wall", "-Wno-unused-result", "-I" + os.path.join(ROOT, "include"), "-o", out] + srcs +
+             ["-L" + libdir, "-l" + libname, "-Wl,-rpath,$ORIGIN", "-lz", "-l:libsqlite3.so.0", "-lm", "-ldl"])
+    return out
 
 
 def build_oracle():

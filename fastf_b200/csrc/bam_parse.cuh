@@ -213,7 +213,147 @@ __device__ __forceinline__ u32 fastf_parse_record(const Acc &A, u64 rec, u64 ren
     return 1;
 }
 
-// infl_total = readable bytes of the inflated buffer (>= end of the last block, multiple of 16)
+// ---- thread-per-record variants (no warp collectives): lane i of the warp walks record i of the staged batch ----
+template <class Acc>
+__device__ __forceinline__ u32 fastf_table_lookup_lane(const FastfStrTableView &T, const Acc &A, u64 s, u32 len)
+{
+    u32 h1 = 0, h2 = 0;
+    u32 c = 0;
+    do {
+        u32 s1 = 0, s2 = 0;
+        const u32 m = len - c < 32u ? len - c : 32u;
+        for (u32 j = 0; j < m; j++) {
+            const u32 byte = A.byte(s + c + j) + 1u;
+            s1 += byte * T.pw1[j];
+            s2 += byte * T.pw2[j];
+        }
+        h1 = h1 * FASTF_H1_Q + s1;
+        h2 = h2 * FASTF_H2_Q + s2;
+        c += 32;
+    } while (c < len);
+    u32 slot = fastf_hash_finalize(h1) & T.mask;
+    for (;;) {
+        const uint4 raw = *reinterpret_cast<const uint4 *>(&T.slots[slot]);   // {tag, off, len, value}
+        if (raw.w == 0) return 0;
+        if (raw.x == h2 && raw.z == len) {
+            // pool strings start on 4-byte boundaries (FastfStrTableHost::insert): compare word-wise
+            const u32 *pw = reinterpret_cast<const u32 *>(T.pool + raw.y);
+            bool same = true;
+            for (u32 i = 0; i < len && same; i += 4) {
+                const u32 w = pw[i >> 2];
+                const u32 m = len - i < 4u ? len - i : 4u;
+                for (u32 b = 0; b < m; b++) same = same && (((w >> (8u * b)) & 255u) == A.byte(s + i + b));
+            }
+            if (same) return raw.w;
+        }
+        slot = (slot + 1) & T.mask;
+    }
+}
+
+// scalar twin of fastf_parse_record (same decisions, one thread)
+template <class Acc>
+__device__ __forceinline__ u32 fastf_parse_record_lane(const Acc &A, u64 rec, u64 rend, u32 bs, const FastfStrTableView &cells, const FastfStrTableView &genes, const FastfKeyLayout &L,
+                                                       u32 *status, u64 *key_out)
+{
+    const u32 l_read_name = A.byte(rec + 8);
+    const u32 n_cigar = fastf_acc_u16(A, rec + 12);
+    const i32 l_seq = (i32)fastf_acc_u32(A, rec + 16);
+    const i64 aoff = 32 + (i64)l_read_name + 4 * (i64)n_cigar + (((i64)l_seq + 1) >> 1) + (i64)l_seq;
+    if (l_seq < 0 || aoff > (i64)bs) { *status |= FASTF_ST_REC_CORRUPT; return 2; }
+    FastfAuxHit cb = {0, 0, 0}, xf = {0, 0, 0}, gx = {0, 0, 0}, ub = {0, 0, 0};
+    u32 found = 0;
+    u64 q = rec + (u64)aoff;
+    while (rend - q >= 3 && found != 15u) {
+        const u32 t0 = A.byte(q), t1 = A.byte(q + 1), ty = A.byte(q + 2);
+        const u64 v = q + 3;
+        u64 next;
+        u32 vlen = 0;
+        if (ty == 'Z' || ty == 'H') {
+            u64 s = v;
+            while (s < rend && A.byte(s) != 0) s++;
+            if (s >= rend) break;   // unterminated: this and every later tag is invisible (htslib)
+            vlen = (u32)(s - v);
+            next = s + 1;
+        } else {
+            u64 sz;
+            switch (ty) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'd': sz = 8; break;
+            case 'B': {
+                if (rend - v < 5) { sz = ~0ull; break; }
+                u32 sub = A.byte(v);
+                u64 cnt = fastf_acc_u32(A, v + 1);
+                u64 es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
+                sz = es ? 5 + es * cnt : ~0ull;
+                break;
+            }
+            default: sz = ~0ull;
+            }
+            if (sz == ~0ull || sz > rend - v) break;
+            next = v + sz;
+        }
+        if (t0 == 'C' && t1 == 'B' && !(found & 1u)) { cb.off = v; cb.len = vlen; cb.type = ty; found |= 1u; }
+        else if (t0 == 'x' && t1 == 'f' && !(found & 2u)) { xf.off = v; xf.type = ty; found |= 2u; }
+        else if (t0 == 'G' && t1 == 'X' && !(found & 4u)) { gx.off = v; gx.len = vlen; gx.type = ty; found |= 4u; }
+        else if (t0 == 'U' && t1 == 'B' && !(found & 8u)) { ub.off = v; ub.len = vlen; ub.type = ty; found |= 8u; }
+        q = next;
+    }
+    if (!(found & 1u) || !(cb.type == 'Z' || cb.type == 'H')) return 0;
+    const u32 cidx = fastf_table_lookup_lane(cells, A, cb.off, cb.len);
+    if (cidx == 0) return 0;
+    u64 key = FASTF_INVALID_KEY;
+    i64 xfv = 0;
+    if (found & 2u) {
+        const u64 x = xf.off;
+        switch (xf.type) {
+        case 'c': xfv = (i64)(int8_t)A.byte(x); break;
+        case 'C': xfv = A.byte(x); break;
+        case 's': xfv = (i64)(int16_t)fastf_acc_u16(A, x); break;
+        case 'S': xfv = fastf_acc_u16(A, x); break;
+        case 'i': xfv = (i64)(i32)fastf_acc_u32(A, x); break;
+        case 'I': xfv = fastf_acc_u32(A, x); break;
+        default: xfv = 0;
+        }
+    }
+    const int xfi = (int)xfv;   // the reference stores bam_aux2i() in an int
+    if ((xfi == 25 || xfi == 17) && (found & 4u) && (gx.type == 'Z' || gx.type == 'H') && (found & 8u) && (ub.type == 'Z' || ub.type == 'H')) {
+        const u32 gidx = fastf_table_lookup_lane(genes, A, gx.off, gx.len);
+        if (gidx != 0) {
+            if (ub.len > 4u * L.umi_max_bytes) {
+                *status |= FASTF_ST_UMI_TOO_LONG;
+            } else {
+                u32 hi = 0, anybad = 0;
+                for (u32 i = 0; i < ub.len; i++) {
+                    const u32 ch = A.byte(ub.off + i);
+                    const u32 code = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
+                    anybad |= code > 3u;
+                    hi |= (code & 3u) << (30u - 2u * i);
+                }
+                u64 ucode = 0;   // SQL NULL
+                if (!anybad) {
+                    u64 content = (u64)(hi >> (32u - 8u * L.umi_max_bytes));
+                    u64 nbytes = (ub.len + 3u) >> 2;
+                    ucode = (1ull << (L.bits_umi - 1u)) | (content << 3) | nbytes;
+                }
+                key = ((u64)cidx << (L.bits_gene + L.bits_umi)) | ((u64)gidx << L.bits_umi) | ucode;
+            }
+        }
+    }
+    *key_out = key;
+    return 1;
+}
+
+#undef FASTF_PARSE_WIN
+#define FASTF_PARSE_WIN 12224   // bytes of the block staged per warp and batch (4 warps x 12224 B stay under the 48 KB static limit)
+
+// One warp per BGZF block.  Per batch: (1) the warp copies the next FASTF_PARSE_WIN bytes of the block into shared
+// memory with coalesced 16-byte loads, (2) walks the block_size chain in the window (<= 32 records, lane k keeps
+// record k), (3) every lane parses ITS OWN record out of shared memory (aux walk, table lookups, UMI packing --
+// 32 records in flight per warp instead of 32 lanes repeating one record's scalar work), (4) the CB-valid records'
+// keys are compacted in record order with a ballot.  Records larger than the window take the warp-cooperative
+// global-memory path.  infl_total = readable bytes of the inflated buffer (>= end of the last block, multiple of 16).
 __global__ void __launch_bounds__(FASTF_PARSE_WARPS * 32)
 fastf_bam_parse_kernel(const u8 *__restrict__ infl, u64 infl_total, const u64 *__restrict__ blk_off, const u32 *__restrict__ blk_isize, u32 nblocks, const u64 *__restrict__ first_record_off_ptr,
                        FastfStrTableView cells, FastfStrTableView genes, FastfKeyLayout L,
@@ -224,50 +364,70 @@ fastf_bam_parse_kernel(const u8 *__restrict__ infl, u64 infl_total, const u64 *_
     const u32 b = blockIdx.x * FASTF_PARSE_WARPS + (threadIdx.x >> 5);
     if (b >= nblocks) return;
     u8 *W = s_win[threadIdx.x >> 5];
-    const u32 c_pw1 = cells.pw1[lane], c_pw2 = cells.pw2[lane];
-    const u32 g_pw1 = genes.pw1[lane], g_pw2 = genes.pw2[lane];
     const u64 bstart = blk_off[b], bend = bstart + blk_isize[b];
     const u64 first_record_off = *first_record_off_ptr;   // end of the BAM header (chunk 0) or 0
     u64 p = bstart > first_record_off ? bstart : first_record_off;
     u64 *out = stage + stage_off[b];
     u32 nrec = 0, ncbv = 0, status = 0;
-    u64 wbase = 0, wend = 0;   // the window holds infl[wbase, wend)
 
     while (p < bend) {
         if (bend - p < 4) { status |= FASTF_ST_REC_STRADDLE; break; }
-        // make sure the record's length word and fixed fields are in the window
-        bool reloaded = false;
-        if (p < wbase || p + 36 > wend) {
-            wbase = p & ~15ull;
-            wend = wbase + FASTF_PARSE_WIN < infl_total ? wbase + FASTF_PARSE_WIN : infl_total;
+        // (1) stage the window
+        const u64 wbase = p & ~15ull;
+        u64 wend = wbase + FASTF_PARSE_WIN < infl_total ? wbase + FASTF_PARSE_WIN : infl_total;
+        {
+            const u64 need = ((bend + 15ull) & ~15ull) < wend ? ((bend + 15ull) & ~15ull) : wend;   // nothing beyond the block is needed
             __syncwarp();
-            for (u32 o = lane * 16u; wbase + o < wend; o += 512u) *reinterpret_cast<uint4 *>(W + o) = *reinterpret_cast<const uint4 *>(infl + wbase + o);
+            for (u32 o = lane * 16u; wbase + o < need; o += 512u) *reinterpret_cast<uint4 *>(W + o) = *reinterpret_cast<const uint4 *>(infl + wbase + o);
             __syncwarp();
-            reloaded = true;
+            wend = need;
         }
-        FastfWinAcc WA = {W, wbase};
-        const u32 bs = (p + 4 <= wend) ? fastf_acc_u32(WA, p) : fastf_ld_u32(infl + p);
-        if ((i32)bs < 32) { status |= FASTF_ST_REC_CORRUPT; break; }
-        if (p + 4 + (u64)bs > bend) { status |= FASTF_ST_REC_STRADDLE; break; }
-        const u64 rec = p + 4, rend = rec + bs;
-        u64 key = 0;
-        u32 r;
-        if (rend <= wend) {
-            r = fastf_parse_record(WA, rec, rend, bs, cells, genes, L, c_pw1, c_pw2, g_pw1, g_pw2, lane, &status, &key);
-        } else if (!reloaded && (u64)bs + 4 + 16 <= FASTF_PARSE_WIN) {
-            wend = 0;      // slide the window to this record and take it again
+        const FastfWinAcc WA = {W, wbase};
+        // (2) chain walk: up to 32 records that lie completely inside the window
+        u64 myrec = 0;
+        u32 mybs = 0, nb = 0, stop = 0;
+        u64 q = p;
+        while (nb < 32u && q < bend) {
+            if (bend - q < 4) { stop = FASTF_ST_REC_STRADDLE; break; }
+            if (q + 4 > wend) break;
+            const u32 bs = fastf_acc_u32(WA, q);
+            if ((i32)bs < 32) { stop = FASTF_ST_REC_CORRUPT; break; }
+            if (q + 4 + (u64)bs > bend) { stop = FASTF_ST_REC_STRADDLE; break; }
+            if (q + 4 + (u64)bs > wend) break;
+            if (lane == nb) { myrec = q + 4; mybs = bs; }
+            nb++;
+            q += 4 + (u64)bs;
+        }
+        if (nb == 0 && !stop) {
+            // the record at p is larger than the window: warp-cooperative walk in global memory
+            const u32 bs = fastf_ld_u32(infl + p);
+            if ((i32)bs < 32) { status |= FASTF_ST_REC_CORRUPT; break; }
+            if (p + 4 + (u64)bs > bend) { status |= FASTF_ST_REC_STRADDLE; break; }
+            const FastfGlobAcc GA = {infl};
+            u64 key = 0;
+            const u32 r = fastf_parse_record(GA, p + 4, p + 4 + bs, bs, cells, genes, L, cells.pw1[lane], cells.pw2[lane], genes.pw1[lane], genes.pw2[lane], lane, &status, &key);
+            if (r == 2) break;
+            p += 4 + (u64)bs;
+            nrec++;
+            if (r == 1) { if (lane == 0) out[ncbv] = key; ncbv++; }
             continue;
-        } else {
-            FastfGlobAcc GA = {infl};   // a record larger than the window: walk it in global memory
-            r = fastf_parse_record(GA, rec, rend, bs, cells, genes, L, c_pw1, c_pw2, g_pw1, g_pw2, lane, &status, &key);
         }
-        if (r == 2) break;
-        p = rend;
-        nrec++;
-        if (r == 1) {
-            if (lane == 0) out[ncbv] = key;
-            ncbv++;
-        }
+        // (3) one record per lane
+        u64 key = 0;
+        u32 r = 0, st = 0;
+        if (lane < nb) r = fastf_parse_record_lane(WA, myrec, myrec + mybs, mybs, cells, genes, L, &st, &key);
+        // (4) ordered compaction; a corrupt record ends the block at that record
+        const u32 badm = __ballot_sync(FASTF_FULL_MASK, r == 2);
+        u32 good = nb;
+        if (badm) good = (u32)__ffs((int)badm) - 1u;
+        const u32 cm = __ballot_sync(FASTF_FULL_MASK, r == 1 && lane < good);
+        if (r == 1 && lane < good) out[ncbv + (u32)__popc(cm & fastf_lanemask_lt())] = key;
+        ncbv += (u32)__popc(cm);
+        nrec += good;
+        status |= __reduce_or_sync(FASTF_FULL_MASK, lane <= good ? st : 0u);
+        if (badm) break;
+        p = q;
+        if (stop) { status |= stop; break; }
     }
     if (lane == 0) { blk_nrec[b] = nrec; blk_ncbv[b] = ncbv; blk_status[b] = status; }
 }

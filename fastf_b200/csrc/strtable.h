@@ -103,6 +103,7 @@ struct FastfStrTableHost {
             if (slots[i].tag == h2 && slots[i].len == len && memcmp(pool.data() + slots[i].off, s, len) == 0) return false;
             i = (i + 1) & mask;
         }
+        while (pool.size() & 3u) pool.push_back(0);   // strings start on 4-byte boundaries: the device compares word-wise
         slots[i].tag = h2; slots[i].off = (uint32_t)pool.size(); slots[i].len = (uint32_t)len; slots[i].value = value;
         pool.insert(pool.end(), (const uint8_t *)s, (const uint8_t *)s + len);
         count++;

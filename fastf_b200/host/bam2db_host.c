@@ -1,0 +1,290 @@
+/* bam2db(): drop-in for reference src/bam2db_ds.c:106-573.  Same arguments, return value, stdout/stderr lines and output files;
+ * the BAM loop (reference :360-438) and the GROUP BY (:480-483) are replaced by the device job of include/fastf_gpu.h. */
+#include "fastf_host.h"
+#include "../../include/fastf_gpu.h"
+#include "sqlite3_decl.h"
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+int _umi_copies_flag = 0;
+int fastf_device = 0;
+
+typedef struct { char *buf; uint32_t *off; uint32_t n, cap; size_t len, bcap; } strlist;
+static void sl_push(strlist *l, const char *s, size_t n)
+{
+    if (l->n + 2 > l->cap) { l->cap = l->cap ? l->cap * 2 : 1024; l->off = (uint32_t *)realloc(l->off, sizeof(uint32_t) * l->cap); }
+    if (l->len + n + 1 > l->bcap) { l->bcap = (l->bcap ? l->bcap * 2 : 65536) + n; l->buf = (char *)realloc(l->buf, l->bcap); }
+    if (l->n == 0) l->off[0] = 0;
+    memcpy(l->buf + l->len, s, n);
+    l->len += n;
+    l->off[++l->n] = (uint32_t)l->len;
+}
+static void sl_free(strlist *l) { free(l->buf); free(l->off); memset(l, 0, sizeof *l); }
+/* open-addressing string set for the duplicate checks of the two list files (reference hash_table_insert refuses duplicates) */
+typedef struct { uint32_t *slot; uint32_t mask; const strlist *l; } strset;
+static uint32_t djb2(const char *s, size_t n) { uint32_t h = 5381; for (size_t i = 0; i < n; i++) h = h * 33u + (unsigned char)s[i]; return h; }
+static void ss_init(strset *s, const strlist *l, size_t expect) { uint32_t c = 64; while (c < expect * 2 + 8) c <<= 1; s->slot = (uint32_t *)calloc(c, 4); s->mask = c - 1; s->l = l; }
+static int ss_has(const strset *s, const char *k, size_t n)
+{
+    for (uint32_t i = djb2(k, n) & s->mask; s->slot[i]; i = (i + 1) & s->mask) {
+        uint32_t id = s->slot[i] - 1;
+        if (s->l->off[id + 1] - s->l->off[id] == n && !memcmp(s->l->buf + s->l->off[id], k, n)) return 1;
+    }
+    return 0;
+}
+static void ss_add(strset *s, const char *k, size_t n, uint32_t id) { uint32_t i = djb2(k, n) & s->mask; while (s->slot[i]) i = (i + 1) & s->mask; s->slot[i] = id + 1; }
+
+static int exec_sql(sqlite3 *db, const char *sql)
+{
+    char *err = NULL;
+    if (sqlite3_exec(db, sql, NULL, 0, &err) != SQLITE_OK) { fprintf(stderr, "SQL error: %s\n", err ? err : "?"); sqlite3_free(err); return 1; }
+    return 0;
+}
+
+int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, char *features_file, float rate_cell, float rate_depth, unsigned int seed)
+{
+    int rc = 1;
+    sqlite3 *db = NULL;
+    sqlite3_stmt *stmt = NULL;
+    fastf_ctx *ctx = NULL;
+    fastf_bam2db_job *job = NULL;
+    fastf_bam2db_result res;
+    memset(&res, 0, sizeof res);
+    strlist cells = {0}, fkeys = {0}, fid = {0}, fname = {0}, ftype = {0};
+    strset cset = {0}, fset = {0};
+    uint64_t *samp = NULL;
+    void *pin[2] = {NULL, NULL};
+    FILE *bam = NULL;
+    gzFile gb = NULL, gf = NULL, file_barcode = NULL, file_feature = NULL, file_matrix = NULL, file_umi = NULL;
+    char line[1024], path[2048];
+
+    if (sqlite3_open(db_file, &db)) { fprintf(stderr, "Can't open database: %s\n", sqlite3_errmsg(db)); goto done; }
+    fprintf(stderr, "Opened database successfully\n");
+    bam = fopen(bam_file, "rb");
+    if (!bam) { fprintf(stderr, "Can't open BAM file %s\n", bam_file); goto done; }
+    fprintf(stderr, "Opened BAM file %s successfully\n", bam_file);
+    gb = gzopen(barcodes_file, "r");
+    if (!gb) { fprintf(stderr, "Can't open cell barcode file %s\n", barcodes_file); goto done; }
+    fprintf(stderr, "Opened cell barcode file %s successfully\n", barcodes_file);
+    gf = gzopen(features_file, "r");
+    if (!gf) { fprintf(stderr, "Can't open feature name file %s\n", features_file); goto done; }
+    fprintf(stderr, "Opened feature name file %s successfully\n", features_file);
+    if (exec_sql(db, "CREATE TABLE cell (cell_barcode TEXT);") || exec_sql(db, "CREATE TABLE feature (feature_id TEXT, feature_name TEXT, feature_type);") ||
+        exec_sql(db, "CREATE TABLE umi (cell_index INTEGER, feature_index INTEGER, encoded_umi TEXT);")) goto done;
+
+    /* ---- barcodes: count, sample, second pass (reference :229-289) ---- */
+    size_t n_cells = 0;
+    while (gzgets(gb, line, 1024) != NULL) n_cells++;
+    printf("Total number of cells: %zu\n", n_cells);
+    samp = (uint64_t *)malloc(sizeof(uint64_t) * (n_cells ? n_cells : 1));
+    uint64_t d0 = 0;
+    uint64_t ns = fastf_sample_cells(n_cells, rate_cell, seed, samp, &d0);
+    if (ns == UINT64_MAX) { printf("Sample size must be smaller than population size when sampling without replacement."); goto done; }
+    printf("Actual number of sampled cell barcodes: %zu\n", (size_t)ns);
+    gzrewind(gb);
+    ss_init(&cset, &cells, ns);
+    exec_sql(db, "BEGIN TRANSACTION");
+    sqlite3_prepare_v2(db, "INSERT INTO cell VALUES (?1);", -1, &stmt, NULL);
+    size_t cell_index = 1, nth = 0;
+    while (gzgets(gb, line, 1024) != NULL && cell_index <= ns) {
+        nth++;
+        if (nth - 1 != samp[cell_index - 1]) continue;
+        line[strcspn(line, "\n\r\t")] = '\0';
+        size_t n = strlen(line);
+        if (!ss_has(&cset, line, n)) {
+            sl_push(&cells, line, n);
+            ss_add(&cset, line, n, cells.n - 1);
+            sqlite3_bind_text(stmt, 1, line, (int)n, SQLITE_TRANSIENT);
+            if (sqlite3_step(stmt) != SQLITE_DONE) { fprintf(stderr, "SQL error: %s\n", sqlite3_errmsg(db)); goto done; }
+            sqlite3_reset(stmt);
+            cell_index++;
+        } else {
+            printf("Warning: Duplicate cell barcodes were found in %s!\n", barcodes_file);
+        }
+    }
+    exec_sql(db, "END TRANSACTION");
+    sqlite3_finalize(stmt);
+    stmt = NULL;
+
+    /* ---- features (reference :296-337): strtok on tabs, key = buffer up to its first NUL ---- */
+    {
+        size_t nlines = 0;
+        while (gzgets(gf, line, 1024) != NULL) nlines++;
+        gzrewind(gf);
+        ss_init(&fset, &fkeys, nlines);
+    }
+    exec_sql(db, "BEGIN TRANSACTION");
+    sqlite3_prepare_v2(db, "INSERT INTO feature VALUES (?1, ?2, ?3);", -1, &stmt, NULL);
+    while (gzgets(gf, line, 1024) != NULL) {
+        char *id = strtok(line, "\t"), *name = strtok(NULL, "\t"), *type = strtok(NULL, "\t");
+        if (!id || !name || !type) { fprintf(stderr, "\x1b[31mError:\x1b[0m feature line with fewer than three tab-separated fields in %s\n", features_file); goto done; }
+        type[strcspn(type, "\n\r\t")] = '\0';
+        size_t kn = strlen(line);
+        if (!ss_has(&fset, line, kn)) {
+            sl_push(&fkeys, line, kn);
+            ss_add(&fset, line, kn, fkeys.n - 1);
+            sl_push(&fid, id, strlen(id)); sl_push(&fname, name, strlen(name)); sl_push(&ftype, type, strlen(type));
+            sqlite3_bind_text(stmt, 1, id, (int)strlen(id), SQLITE_TRANSIENT);
+            sqlite3_bind_text(stmt, 2, name, (int)strlen(name), SQLITE_TRANSIENT);
+            sqlite3_bind_text(stmt, 3, type, (int)strlen(type), SQLITE_TRANSIENT);
+            if (sqlite3_step(stmt) != SQLITE_DONE) { fprintf(stderr, "SQL error: %s\n", sqlite3_errmsg(db)); goto done; }
+            sqlite3_reset(stmt);
+        } else {
+            printf("Warning: Duplicate feature names were found in %s!\n", features_file);
+        }
+    }
+    exec_sql(db, "END TRANSACTION");
+    sqlite3_finalize(stmt);
+    stmt = NULL;
+
+    /* ---- the hot path: device job fed with the raw BGZF bytes ---- */
+    printf("Start to convert bam file to sqlite3 database...\n");
+    fflush(stdout);
+    if (fastf_ctx_create(fastf_device, &ctx)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(NULL)); goto done; }
+    {
+        fastf_bam2db_params p;
+        memset(&p, 0, sizeof p);
+        uint32_t zero_off[1] = {0};
+        p.cell_keys = cells.buf ? cells.buf : ""; p.cell_off = cells.off ? cells.off : zero_off; p.n_cells = cells.n;
+        p.gene_keys = fkeys.buf ? fkeys.buf : ""; p.gene_off = fkeys.off ? fkeys.off : zero_off; p.n_genes = fkeys.n;
+        p.seed = seed; p.d0 = d0; p.keep_threshold = fastf_keep_threshold(rate_depth);
+        p.umi_max_bytes = 4;    /* UMIs up to 16 bases */
+        p.want_rows = 1;
+        if (fastf_bam2db_begin(ctx, &p, &job)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
+        const size_t PIECE = (size_t)256 << 20;
+        if (fastf_host_alloc(ctx, PIECE, &pin[0]) || fastf_host_alloc(ctx, PIECE, &pin[1])) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
+        size_t got;
+        int which = 0;
+        while ((got = fread(pin[which], 1, PIECE, bam)) > 0) {
+            if (fastf_bam2db_feed(job, pin[which], got)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
+            which ^= 1;
+        }
+        if (fastf_bam2db_finish(job, &res)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
+    }
+
+    /* ---- table umi in read order (reference :351-435) ---- */
+    exec_sql(db, "BEGIN TRANSACTION");
+    sqlite3_prepare_v2(db, "INSERT INTO umi VALUES (?1, ?2, ?3);", -1, &stmt, NULL);
+    {
+        const uint32_t bu = res.bits_umi, bg = res.bits_gene, mb = res.umi_max_bytes;
+        for (uint64_t i = 0; i < res.n_rows; i++) {
+            uint64_t k = res.row_keys[i];
+            uint64_t code = k & ((1ull << bu) - 1);
+            int gene = (int)((k >> bu) & ((1ull << bg) - 1)), cell = (int)(k >> (bu + bg));
+            sqlite3_bind_int(stmt, 1, cell);
+            sqlite3_bind_int(stmt, 2, gene);
+            if ((code >> (bu - 1)) & 1) {
+                uint8_t blob[8];
+                uint64_t content = (code >> 3) & ((1ull << (8 * mb)) - 1);
+                int nb = (int)(code & 7);
+                for (uint32_t b = 0; b < mb; b++) blob[b] = (uint8_t)(content >> (8 * (mb - 1 - b)));
+                sqlite3_bind_blob(stmt, 3, blob, nb, SQLITE_TRANSIENT);
+            } else {
+                sqlite3_bind_null(stmt, 3);
+            }
+            if (sqlite3_step(stmt) != SQLITE_DONE) { fprintf(stderr, "SQL error: %s\n", sqlite3_errmsg(db)); goto done; }
+            sqlite3_reset(stmt);
+        }
+    }
+    exec_sql(db, "END TRANSACTION");
+    sqlite3_finalize(stmt);
+    stmt = NULL;
+    printf("In %s, total fastQ reads: %zu\n", bam_file, (size_t)res.total);
+    printf("In %s, sampled fastQ reads: %zu\n", bam_file, (size_t)res.sampled);
+    printf("In %s, sampled and valid fastQ reads: %zu\n", bam_file, (size_t)res.valid);
+
+    /* ---- 10x output (reference :447-567) ---- */
+    snprintf(path, sizeof path, "%s/barcodes.tsv.gz", path_out);
+    if (!(file_barcode = gzopen(path, "wb"))) { fprintf(stderr, "\x1b[31mError:\x1b[0m can not open file %s\n", path); goto done; }
+    snprintf(path, sizeof path, "%s/features.tsv.gz", path_out);
+    if (!(file_feature = gzopen(path, "wb"))) { fprintf(stderr, "\x1b[31mError:\x1b[0m can not open file %s\n", path); goto done; }
+    snprintf(path, sizeof path, "%s/matrix.mtx.gz", path_out);
+    if (!(file_matrix = gzopen(path, "wb"))) { fprintf(stderr, "\x1b[31mError:\x1b[0m can not open file %s\n", path); goto done; }
+    /* table mtx: the device COO, under the schema text sqlite gives `CREATE TABLE mtx AS SELECT ...` */
+    if (exec_sql(db, "CREATE TABLE mtx(\n  feature_index INT,\n  cell_index INT,\n  expression_level\n)")) goto done;
+    exec_sql(db, "BEGIN TRANSACTION");
+    sqlite3_prepare_v2(db, "INSERT INTO mtx VALUES (?1, ?2, ?3);", -1, &stmt, NULL);
+    for (uint64_t i = 0; i < res.nnz; i++) {
+        sqlite3_bind_int(stmt, 1, (int)res.m_gene[i]); sqlite3_bind_int(stmt, 2, (int)res.m_cell[i]); sqlite3_bind_int(stmt, 3, (int)res.m_count[i]);
+        if (sqlite3_step(stmt) != SQLITE_DONE) { fprintf(stderr, "SQL error: %s\n", sqlite3_errmsg(db)); goto done; }
+        sqlite3_reset(stmt);
+    }
+    exec_sql(db, "END TRANSACTION");
+    sqlite3_finalize(stmt);
+    stmt = NULL;
+    /* the reference's "%%%M" prints "%%M" with glibc (src/bam2db_ds.c:500) */
+    gzprintf(file_matrix,
+             "%%%%MatrixMarket matrix coordinate integer general\n%%metadata_json: \n%%{\n%%\t\"software_version\": \"fastF-1.0.0\",\n%%\t\"format_version\": 1,\n"
+             "%%\t\"parent_bam\": \"%s\",\n%%\t\"rate_cell\": %.3f,\n%%\t\"rate_depth\": %.3f,\n%%\t\"total_n_FastQ\": %zu,\n%%\t\"sampled_n_FastQ\": %zu,\n"
+             "%%\t\"sampled_valid_n_FastQ\": %zu\n%%}\n",
+             bam_file, rate_cell, rate_depth, (size_t)res.total, (size_t)res.sampled, (size_t)res.valid);
+    gzprintf(file_matrix, "%zu %zu %zu\n", (size_t)fkeys.n, (size_t)cells.n, (size_t)res.nnz);
+    for (uint64_t i = 0; i < res.nnz; i++) gzprintf(file_matrix, "%d %d %d\n", (int)res.m_gene[i], (int)res.m_cell[i], (int)res.m_count[i]);
+    printf("matrix.mtx.gz is generated.\n");
+    for (uint32_t i = 0; i < cells.n; i++) { gzwrite(file_barcode, cells.buf + cells.off[i], cells.off[i + 1] - cells.off[i]); gzputc(file_barcode, '\n'); }
+    printf("barcodes.tsv.gz is generated.\n");
+    for (uint32_t i = 0; i < fid.n; i++) {
+        gzwrite(file_feature, fid.buf + fid.off[i], fid.off[i + 1] - fid.off[i]); gzputc(file_feature, '\t');
+        gzwrite(file_feature, fname.buf + fname.off[i], fname.off[i + 1] - fname.off[i]); gzputc(file_feature, '\t');
+        gzwrite(file_feature, ftype.buf + ftype.off[i], ftype.off[i + 1] - ftype.off[i]); gzputc(file_feature, '\n');
+    }
+    printf("features.tsv.gz is generated.\n");
+    if (_umi_copies_flag) {
+        /* numi: copies per distinct (cell, gene, umi) in (cell, gene, umi) order, NULL first (reference :527-556); decode_DNA(blob, 10) at :629 */
+        snprintf(path, sizeof path, "%s/umi.tsv.gz", path_out);
+        if (!(file_umi = gzopen(path, "wb"))) { fprintf(stderr, "\x1b[31mError:\x1b[0m can not open file %s\n", path); goto done; }
+        uint64_t n = res.n_rows, *k = (uint64_t *)malloc(sizeof(uint64_t) * (n ? n : 1));
+        memcpy(k, res.row_keys, sizeof(uint64_t) * n);
+        if (fastf_sort_u64_host(ctx, k, NULL, n, res.bits_cell + res.bits_gene + res.bits_umi)) { free(k); fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
+        if (exec_sql(db, "CREATE TABLE numi(\n  feature_index INT,\n  cell_index INT,\n  encoded_umi TEXT,\n  n_copy\n)")) { free(k); goto done; }
+        exec_sql(db, "BEGIN TRANSACTION");
+        sqlite3_prepare_v2(db, "INSERT INTO numi VALUES (?1, ?2, ?3, ?4);", -1, &stmt, NULL);
+        const uint32_t bu = res.bits_umi, bg = res.bits_gene, mb = res.umi_max_bytes;
+        for (uint64_t i = 0; i < n;) {
+            uint64_t j = i;
+            while (j < n && k[j] == k[i]) j++;
+            uint64_t code = k[i] & ((1ull << bu) - 1);
+            int gene = (int)((k[i] >> bu) & ((1ull << bg) - 1)), cell = (int)(k[i] >> (bu + bg));
+            sqlite3_bind_int(stmt, 1, gene); sqlite3_bind_int(stmt, 2, cell);
+            char dec[16] = "NULL";
+            if ((code >> (bu - 1)) & 1) {
+                uint8_t blob[8];
+                uint64_t content = (code >> 3) & ((1ull << (8 * mb)) - 1);
+                for (uint32_t b = 0; b < mb; b++) blob[b] = (uint8_t)(content >> (8 * (mb - 1 - b)));
+                sqlite3_bind_blob(stmt, 3, blob, (int)(code & 7), SQLITE_TRANSIENT);
+                for (int b = 0; b < 10; b++) { int sh = (int)(8 * mb) - 2 * (b + 1); dec[b] = "ACGT"[sh >= 0 ? (content >> sh) & 3 : 0]; }
+                dec[10] = 0;
+            } else sqlite3_bind_null(stmt, 3);
+            sqlite3_bind_int(stmt, 4, (int)(j - i));
+            sqlite3_step(stmt);
+            sqlite3_reset(stmt);
+            gzprintf(file_umi, "%d\t%d\t%s\t%d\n", gene, cell, dec, (int)(j - i));
+            i = j;
+        }
+        exec_sql(db, "END TRANSACTION");
+        sqlite3_finalize(stmt);
+        stmt = NULL;
+        free(k);
+        printf("umi.tsv.gz is generated.\n");
+    }
+    rc = 0;
+done:
+    if (stmt) sqlite3_finalize(stmt);
+    if (file_barcode) gzclose(file_barcode);
+    if (file_feature) gzclose(file_feature);
+    if (file_matrix) gzclose(file_matrix);
+    if (file_umi) gzclose(file_umi);
+    if (gb) gzclose(gb);
+    if (gf) gzclose(gf);
+    if (bam) fclose(bam);
+    fastf_bam2db_result_free(&res);
+    if (job) fastf_bam2db_job_free(job);
+    if (ctx) { fastf_host_free(ctx, pin[0]); fastf_host_free(ctx, pin[1]); fastf_ctx_destroy(ctx); }
+    if (db) sqlite3_close(db);
+    free(samp);
+    free(cset.slot); free(fset.slot);
+    sl_free(&cells); sl_free(&fkeys); sl_free(&fid); sl_free(&fname); sl_free(&ftype);
+    return rc;
+}

@@ -19,15 +19,33 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 REF = os.path.join(ROOT, "oracle", "_ref", "fastF_ref")
 
 
-def run_ref_bam2db(d, expect, rc, rd, seed):
+def db_digest(path):
+    """schema text + sha256 of every table's rows (in rowid order) of a bam2db sqlite file"""
+    import hashlib
+    import sqlite3
+    c = sqlite3.connect(path)
+    out = {"schema": [list(r) for r in c.execute("select name, sql from sqlite_master order by name")]}
+    for (name,) in c.execute("select name from sqlite_master where type='table' order by name").fetchall():
+        h = hashlib.sha256()
+        n = 0
+        for row in c.execute("select * from %s order by rowid" % name):
+            h.update(repr(row).encode())
+            n += 1
+        out[name] = [n, h.hexdigest()]
+    c.close()
+    return out
+
+
+def run_ref_bam2db(d, expect, rc, rd, seed, umicopies=False):
     out = os.path.join(d, expect)
     shutil.rmtree(out, ignore_errors=True)
     os.makedirs(out)
     db = os.path.join(d, "tmp.db")
     if os.path.exists(db):
         os.remove(db)
-    r = subprocess.run([REF, "bam2db", "-b", "in.bam", "-f", "features.tsv.gz", "-a", "barcodes.tsv.gz", "-d", "tmp.db", "-c", str(rc), "-r", str(rd), "-o", expect, "-s", str(seed)],
+    r = subprocess.run([REF, "bam2db", "-b", "in.bam", "-f", "features.tsv.gz", "-a", "barcodes.tsv.gz", "-d", "tmp.db", "-c", str(rc), "-r", str(rd), "-o", expect, "-s", str(seed)] + (["-u"] if umicopies else []),
                        cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, check=True)
+    json.dump(db_digest(db), open(os.path.join(out, "db_digest.json"), "w"), indent=1)
     os.remove(db)
     c = {}
     for ln in r.stdout.splitlines():
@@ -52,8 +70,8 @@ def main():
     os.rename(paths["bam"], os.path.join(d, "in.bam"))
     for rc, rd, seed in ((0.5, 0.5, 926), (1.0, 0.3, 926), (1.0, 1.0, 1), (0.2, 0.9, 77)):
         exp = "expect_c%s_r%s_s%d" % (rc, rd, seed)
-        cnt = run_ref_bam2db(d, exp, rc, rd, seed)
-        cases.append({"name": "synth4k-c%s-r%s-s%d" % (rc, rd, seed), "kind": "bam2db", "dir": "synth4k", "expect": exp, "rate_cell": rc, "rate_depth": rd, "seed": seed, "counters": cnt})
+        cnt = run_ref_bam2db(d, exp, rc, rd, seed, umicopies=True)
+        cases.append({"name": "synth4k-c%s-r%s-s%d" % (rc, rd, seed), "kind": "bam2db", "dir": "synth4k", "expect": exp, "rate_cell": rc, "rate_depth": rd, "seed": seed, "counters": cnt, "umicopies": True})
     # 2. hand-crafted edge cases, every deflate block type, a multi-block header
     d = os.path.join(GOLD, "edge")
     shutil.rmtree(d, ignore_errors=True)

@@ -16,8 +16,11 @@ def emu_lib():
     return build.build_emu()
 
 
-def _run(emu_lib, names, shuffle=None):
+def _run(emu_lib, names, shuffle=None, cli=False):
     env = dict(os.environ, FASTF_GPU_LIB=emu_lib)
+    if cli:
+        from fastf_b200 import build
+        env["FASTF_EMU_CLI"] = build.build_cli(emu=True)
     if shuffle:
         env["FASTF_EMU_SHUFFLE"] = str(shuffle)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "run_emu_case.py")] + names, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
@@ -44,3 +47,12 @@ def test_emu_bam2db_edge_cases_shuffled_schedule(emu_lib):
 
 def test_emu_freq_ragged(emu_lib):
     _run(emu_lib, ["freq-ragged-l16-u12", "freq-ragged_nonl-l16-u0", "freq-ragged_trunc-l5-u3"])
+
+
+def test_emu_c_host_cli(emu_lib):
+    """the C host (fastf_b200/host: option parsing, list readers, sqlite + gz writers, -u) linked against the emulator build"""
+    _run(emu_lib, ["synth4k-c0.5-r0.5-s926", "freq-ragged-l16-u0"], cli=True)
+
+
+def test_emu_python_host_umicopies(emu_lib):
+    _run(emu_lib, ["synth4k-c0.2-r0.9-s77"])

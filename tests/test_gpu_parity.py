@@ -168,16 +168,21 @@ def test_bam2db_golden_files(gpu_ctx, case, tmp_path):
     """the whole operator (files in, files out) against outputs recorded from the unmodified reference; includes the edge-case BAM"""
     import sqlite3
     import fastf_b200
+    from fastf_b200 import bam2db_host
+    from dbdigest import db_digest
     d = os.path.join(GOLD, case["dir"])
     out = str(tmp_path)
     cwd = os.getcwd()
     os.chdir(d)
+    bam2db_host._umi_copies_flag = 1 if case.get("umicopies") else 0
     try:
         assert fastf_b200.bam2db("in.bam", os.path.join(out, "x.db"), out, "barcodes.tsv.gz", "features.tsv.gz", case["rate_cell"], case["rate_depth"], case["seed"], ctx=gpu_ctx) == 0
     finally:
         os.chdir(cwd)
-    for f in ("matrix.mtx.gz", "barcodes.tsv.gz", "features.tsv.gz"):
+        bam2db_host._umi_copies_flag = 0
+    for f in ["matrix.mtx.gz", "barcodes.tsv.gz", "features.tsv.gz"] + (["umi.tsv.gz"] if case.get("umicopies") else []):
         assert gzip.open(os.path.join(out, f), "rb").read() == gzip.open(os.path.join(d, case["expect"], f), "rb").read(), f
+    assert db_digest(os.path.join(out, "x.db")) == json.load(open(os.path.join(d, case["expect"], "db_digest.json")))   # every table, row for row
     db = sqlite3.connect(os.path.join(out, "x.db"))
     n_umi, n_null = db.execute("select count(*), sum(encoded_umi is null) from umi").fetchone()
     assert n_umi == case["counters"][2]
@@ -273,3 +278,38 @@ def test_freq_large_properties(gpu_ctx, synth, tmp_path):
     assert h.n_reads == 6_000_000 and int(np.sum(h.count)) == 6_000_000
     assert all(h.keys[i] < h.keys[i + 1] for i in range(0, len(h.keys) - 1, 997))
     assert len(set(h.first.tolist())) == len(h.keys) and int(h.first.min()) == 0
+
+
+# ------------------------------------------------------------------------------------------------ the C host
+@pytest.mark.parametrize("name", ["synth4k-c0.5-r0.5-s926", "edge-c0.8-r0.6-s3"])
+def test_c_cli_bam2db_golden(gpu_ctx, name, tmp_path):
+    """`fastF bam2db ...` (fastf_b200/host, C) against the outputs recorded from the reference CLI"""
+    import subprocess
+    from fastf_b200 import build
+    from dbdigest import db_digest
+    case = [c for c in _cases("bam2db") if c["name"] == name][0]
+    d = os.path.join(GOLD, case["dir"])
+    out = str(tmp_path)
+    cli = build.build_cli()
+    cmd = [cli, "bam2db", "-b", "in.bam", "-f", "features.tsv.gz", "-a", "barcodes.tsv.gz", "-d", os.path.join(out, "x.db"), "-c", str(case["rate_cell"]), "-r", str(case["rate_depth"]), "-o", out,
+           "-s", str(case["seed"])] + (["-u"] if case.get("umicopies") else [])
+    r = subprocess.run(cmd, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "In in.bam, total fastQ reads: %d" % case["counters"][0] in r.stdout and "Opened database successfully" in r.stderr
+    for f in ["matrix.mtx.gz", "barcodes.tsv.gz", "features.tsv.gz"] + (["umi.tsv.gz"] if case.get("umicopies") else []):
+        assert gzip.open(os.path.join(out, f), "rb").read() == gzip.open(os.path.join(d, case["expect"], f), "rb").read(), f
+    assert db_digest(os.path.join(out, "x.db")) == json.load(open(os.path.join(d, case["expect"], "db_digest.json")))
+    # the reference refuses an existing database (src/main.c:341-345)
+    r = subprocess.run(cmd, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "already exists" in r.stderr
+
+
+def test_c_cli_freq_golden(gpu_ctx, tmp_path):
+    import subprocess
+    from fastf_b200 import build
+    cli = build.build_cli()
+    for case in _cases("freq"):
+        d = os.path.join(GOLD, case["dir"])
+        r = subprocess.run([cli, "freq", "-R", os.path.join(d, case["input"]), "-o", str(tmp_path), "-l", str(case["l"]), "-u", str(case["u"])], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(tmp_path / "whitelist.txt", "rb").read() == gzip.open(os.path.join(d, case["expect"]), "rb").read(), case["name"]
