@@ -265,21 +265,15 @@ def main():
         chunk = args.chunk_mb << 20
 
         def one_job(device_resident, want_copy=False):
-            with B.Bam2dbJob(ctx, inputs, RATE_DEPTH, SEED, want_rows=False, inflate_lanes=args.lanes, chunk_inflated_bytes=chunk) as job:
+            with B.Bam2dbJob(ctx, inputs, RATE_DEPTH, SEED, want_rows=False, inflate_lanes=args.lanes, chunk_inflated_bytes=chunk, headerless=(rank != 0)) as job:
                 for t in range(tiles):
                     if device_resident:
-                        lo = 0 if t == 0 else rec_lo
+                        lo = 0 if (t == 0 and rank == 0) else rec_lo
                         job.feed_device(dptr.value, nbytes, in_off[lo:rec_hi], in_len[lo:rec_hi], isz[lo:rec_hi])
                     else:
-                        lo = 0 if t == 0 else hdr_end
+                        lo = 0 if (t == 0 and rank == 0) else hdr_end
                         job.feed(hptr.value + lo, eof_start - lo)
                 if world > 1:
-                    n_rec, n_cbv = job.counts()
-                    cnt = torch.tensor([n_rec, n_cbv], dtype=torch.int64, device="cuda")
-                    allc = [torch.zeros_like(cnt) for _ in range(world)]
-                    dist.all_gather(allc, cnt)
-                    base_ord = int(sum(int(c[1]) for c in allc[:rank]))
-                    job.sample(base_ord)
                     return multi_gpu_tail(job, dist, torch, ctx, rank, world, inputs)
                 return job.finish(copy=want_copy)
 
@@ -330,7 +324,7 @@ def main():
                 tt = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
                 e_ms = float(tt[0])
-            d2h = int(estats[-1]["nnz"]) * 12 + 64
+            d2h = int(estats[-1].get("nnz") or 0) * 12 + 64
             e2e = {"value": world * reads_per_step / (e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(tiles * comp_rec_bytes + hdr_end), "d2h_bytes_per_step": d2h,
                    "ms_per_step": e_ms, "steps": args.e2e_steps, "timing": "host wall clock around begin..finish (pinned host BGZF bytes in, COO out)"}
         if rank != 0:
@@ -343,13 +337,16 @@ def main():
         stages = {}
         for k, bytes_ in (("inflate", st["compressed_bytes"] + st["inflated_bytes"]), ("parse", st["inflated_bytes"] + 8 * st["total"]), ("mt", st["cb_valid"] / 8.0 + 0),
                           ("sample", st["cb_valid"] * 8 * 2 + st["valid"] * 8), ("sort", st["valid"] * 16 * 7), ("count", st["valid"] * 8 + st["nnz"] * 12)):
+            if world > 1 and k in ("sort", "count", "sample", "mt"):
+                continue   # rank 0's local clocks only cover the streaming stages in the sharded job
             ms = st["ms_" + k]
             stages[k] = {"ms": round(ms, 3), "alg_GBps": round(bytes_ / (ms * 1e-3) / 1e9, 1) if ms > 0 else None}
         line = {"metric": "bam2db reads/sec (device-timed)", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": workload, "tiling": f"{base['reads']}-read zlib-6 BGZF segment ({base['compressed'] / 1e6:.0f} MB compressed, {base['inflated'] / 1e6:.0f} MB inflated) streamed {tiles}x per step",
                            "l2": "inputs larger than L2 (compressed segment >> 126 MB); no explicit flush", "timing": "CUDA events on the library's launching stream around the K timed jobs, barrier + synchronize on both sides; max over ranks",
-                           "ms_per_step_wall": ms_step_wall, "ms_per_job_library_clock": ms_job_dev, "counters": {k: st[k] for k in ("total", "cb_valid", "sampled", "valid", "nnz", "n_blocks", "n_chunks")}},
+                           "ms_per_step_wall": ms_step_wall, "ms_per_job_library_clock": ms_job_dev, "counters": {k: st.get(k) for k in ("total", "cb_valid", "sampled", "valid", "nnz", "n_blocks", "n_chunks", "exchanged_keys")},
+                           "parallelism": ("single GPU" if world == 1 else f"{world} ranks: contiguous BGZF block shards, all-gather of counts, NCCL all-to-all of locally deduplicated keys by cell hash, gather of COO")},
                 "roofline": {"bound": "hbm", "kernel": "fastf_bgzf_inflate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes_launch, "ms_per_launch": infl_ms_launch},
                 "stages": stages, "gpu_launches": launches, "clocks": clocks, "e2e": e2e}
@@ -367,7 +364,13 @@ def main():
 
 
 def multi_gpu_tail(job, dist, torch, ctx, rank, world, inputs):
-    raise SystemExit("bench.py: multi-GPU tail not wired yet")
+    """counts all-gather -> sample at the global ordinal -> unique + partition by cell hash -> NCCL all-to-all -> local dedup/count -> gather"""
+    from fastf_b200 import sharded
+    res = sharded.sharded_tail(ctx, job, dist, torch, "cuda", rank, world, want_rows=False)
+    st = job.stats()           # this rank's stage clocks and byte counts
+    if res is not None:
+        st.update({k: v for k, v in res[0].items() if k in ("total", "cb_valid", "sampled", "valid", "nnz", "exchanged_keys")})
+    return st, (res[1] if res is not None else None)
 
 
 if __name__ == "__main__":

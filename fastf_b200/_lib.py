@@ -15,7 +15,7 @@ class Bam2dbParams(C.Structure):
                 ("gene_keys", C.c_char_p), ("gene_off", c_u32p), ("n_genes", C.c_uint32),
                 ("seed", C.c_uint32), ("d0", C.c_uint64), ("keep_threshold", C.c_uint64),
                 ("umi_max_bytes", C.c_uint32), ("want_rows", C.c_uint32), ("inflate_lanes", C.c_uint32),
-                ("chunk_inflated_bytes", C.c_uint64)]
+                ("chunk_inflated_bytes", C.c_uint64), ("headerless", C.c_uint32)]
 
 
 class Bam2dbResult(C.Structure):
@@ -63,8 +63,10 @@ _SIGS = {
     "fastf_bam2db_counts": (C.c_int, [C.c_void_p, c_u64p, c_u64p]),
     "fastf_bam2db_sample": (C.c_int, [C.c_void_p, C.c_uint64]),
     "fastf_bam2db_kept_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), c_u64p]),
+    "fastf_bam2db_sample_counts": (C.c_int, [C.c_void_p, c_u64p, c_u64p]),
     "fastf_bam2db_key_layout": (C.c_int, [C.c_void_p, c_u32p, c_u32p, c_u32p]),
     "fastf_bam2db_finish": (C.c_int, [C.c_void_p, C.POINTER(Bam2dbResult)]),
+    "fastf_bam2db_stats": (C.c_int, [C.c_void_p, C.POINTER(Bam2dbResult)]),
     "fastf_bam2db_job_free": (None, [C.c_void_p]),
     "fastf_bam2db_result_free": (None, [C.POINTER(Bam2dbResult)]),
     "fastf_sort_u64_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]),

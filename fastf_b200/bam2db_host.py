@@ -133,7 +133,7 @@ def decode_rows(row_keys, bits_gene, bits_umi, umi_max_bytes):
 class Bam2dbJob:
     """One streaming bam2db job on one GPU: begin -> feed*/feed_device* -> (counts -> sample(base)) -> finish."""
 
-    def __init__(self, ctx, inputs, rate_depth, seed, want_rows=True, inflate_lanes=0, chunk_inflated_bytes=0, umi_max_bytes=0):
+    def __init__(self, ctx, inputs, rate_depth, seed, want_rows=True, inflate_lanes=0, chunk_inflated_bytes=0, umi_max_bytes=0, headerless=False):
         self.ctx, self.lib = ctx, ctx.lib
         ckeys, coff = _pack_table(inputs.cells)
         gkeys, goff = _pack_table([f[0] for f in inputs.features])
@@ -152,6 +152,7 @@ class Bam2dbJob:
         p.want_rows = 1 if want_rows else 0
         p.inflate_lanes = inflate_lanes
         p.chunk_inflated_bytes = chunk_inflated_bytes
+        p.headerless = 1 if headerless else 0
         self.want_rows = want_rows
         self.job = C.c_void_p()
         ctx.check(self.lib.fastf_bam2db_begin(ctx.h, C.byref(p), C.byref(self.job)), "bam2db_begin")
@@ -170,6 +171,11 @@ class Bam2dbJob:
 
     def sample(self, ordinal_base=0):
         self.ctx.check(self.lib.fastf_bam2db_sample(self.job, ordinal_base), "bam2db_sample")
+
+    def sample_counts(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self.ctx.check(self.lib.fastf_bam2db_sample_counts(self.job, C.byref(a), C.byref(b)), "bam2db_sample_counts")
+        return a.value, b.value
 
     def kept_device(self):
         p, n = C.c_void_p(), C.c_uint64()
@@ -196,6 +202,11 @@ class Bam2dbJob:
         stats = {f: getattr(res, f) for f, _ in _lib.Bam2dbResult._fields_ if not f.startswith("m_") and f != "row_keys"}
         self.lib.fastf_bam2db_result_free(C.byref(res))
         return stats, out
+
+    def stats(self):
+        res = _lib.Bam2dbResult()
+        self.ctx.check(self.lib.fastf_bam2db_stats(self.job, C.byref(res)), "bam2db_stats")
+        return {f: getattr(res, f) for f, _ in _lib.Bam2dbResult._fields_ if not f.startswith("m_") and f != "row_keys"}
 
     def close(self):
         if self.job:
@@ -252,94 +263,112 @@ def decode_dna10(blob_content, umi_max_bytes):
     return "".join(out)
 
 
-def bam2db(bam_file, db_file, path_out, barcodes_file, features_file, rate_cell, rate_depth, seed=926, device=0, ctx=None):
-    own = ctx is None
+def open_database(db_file, bam_file, barcodes_file, features_file):
+    """the reference's opening sequence with its stderr lines (src/bam2db_ds.c:127-210); returns the sqlite connection or None"""
     try:
-        if own:
-            ctx = _lib.Context(device)
-        lib = ctx.lib
-        try:
-            db = sqlite3.connect(db_file, isolation_level=None)
-        except sqlite3.Error as e:
-            sys.stderr.write("Can't open database: %s\n" % e)
-            return 1
-        sys.stderr.write("Opened database successfully\n")
-        for path, what in ((bam_file, "BAM"), (barcodes_file, "cell barcode"), (features_file, "feature name")):
-            if not os.path.exists(path):
-                sys.stderr.write("Can't open %s file %s\n" % (what, path))
-                return 1
-            sys.stderr.write("Opened %s file %s successfully\n" % (what, path))
-        db.execute("CREATE TABLE cell (cell_barcode TEXT);")
-        db.execute("CREATE TABLE feature (feature_id TEXT, feature_name TEXT, feature_type);")
-        db.execute("CREATE TABLE umi (cell_index INTEGER, feature_index INTEGER, encoded_umi TEXT);")
-        inputs = Bam2dbInputs(lib, barcodes_file, features_file, rate_cell, seed)
-        print("Total number of cells: %d" % inputs.n_cells)
-        print("Actual number of sampled cell barcodes: %d" % inputs.n_cells_sampled)
-        if inputs.duplicate_barcodes:
-            print("Warning: Duplicate cell barcodes were found in %s!" % barcodes_file)
-        if inputs.duplicate_features:
-            print("Warning: Duplicate feature names were found in %s!" % features_file)
+        db = sqlite3.connect(db_file, isolation_level=None)
+    except sqlite3.Error as e:
+        sys.stderr.write("Can't open database: %s\n" % e)
+        return None
+    sys.stderr.write("Opened database successfully\n")
+    for path, what in ((bam_file, "BAM"), (barcodes_file, "cell barcode"), (features_file, "feature name")):
+        if not os.path.exists(path):
+            sys.stderr.write("Can't open %s file %s\n" % (what, path))
+            return None
+        sys.stderr.write("Opened %s file %s successfully\n" % (what, path))
+    db.execute("CREATE TABLE cell (cell_barcode TEXT);")
+    db.execute("CREATE TABLE feature (feature_id TEXT, feature_name TEXT, feature_type);")
+    db.execute("CREATE TABLE umi (cell_index INTEGER, feature_index INTEGER, encoded_umi TEXT);")
+    return db
+
+
+def load_lists(db, lib, barcodes_file, features_file, rate_cell, seed):
+    inputs = Bam2dbInputs(lib, barcodes_file, features_file, rate_cell, seed)
+    print("Total number of cells: %d" % inputs.n_cells)
+    print("Actual number of sampled cell barcodes: %d" % inputs.n_cells_sampled)
+    if inputs.duplicate_barcodes:
+        print("Warning: Duplicate cell barcodes were found in %s!" % barcodes_file)
+    if inputs.duplicate_features:
+        print("Warning: Duplicate feature names were found in %s!" % features_file)
+    if db is not None:
         db.execute("BEGIN TRANSACTION")
         db.executemany("INSERT INTO cell VALUES (?);", ((c.decode("latin-1"),) for c in inputs.cells))
         db.execute("END TRANSACTION")
         db.execute("BEGIN TRANSACTION")
         db.executemany("INSERT INTO feature VALUES (?, ?, ?);", ((f[1].decode("latin-1"), f[2].decode("latin-1"), f[3].decode("latin-1")) for f in inputs.features))
         db.execute("END TRANSACTION")
+    return inputs
+
+
+def write_outputs(db, bam_file, path_out, inputs, rate_cell, rate_depth, stats, out):
+    """sqlite tables umi / mtx (/ numi) and the 10x .gz files from the device result (reference src/bam2db_ds.c:351-567)"""
+    cell, gene, nbytes, content = decode_rows(out["row_keys"], stats["bits_gene"], stats["bits_umi"], stats["umi_max_bytes"])
+    mb = stats["umi_max_bytes"]
+
+    def rows():
+        for c, g, nb, ct in zip(cell.tolist(), gene.tolist(), nbytes.tolist(), content.tolist()):
+            yield (c, g, None if nb < 0 else ct.to_bytes(mb, "big")[:nb])
+    db.execute("BEGIN TRANSACTION")
+    db.executemany("INSERT INTO umi VALUES (?, ?, ?);", rows())
+    db.execute("END TRANSACTION")
+    print("In %s, total fastQ reads: %d" % (bam_file, stats["total"]))
+    print("In %s, sampled fastQ reads: %d" % (bam_file, stats["sampled"]))
+    print("In %s, sampled and valid fastQ reads: %d" % (bam_file, stats["valid"]))
+    # table mtx from the device COO, with the schema text sqlite gives `CREATE TABLE mtx AS SELECT ...` (src/bam2db_ds.c:480-483)
+    db.execute("CREATE TABLE mtx(\n  feature_index INT,\n  cell_index INT,\n  expression_level\n)")
+    db.execute("BEGIN TRANSACTION")
+    db.executemany("INSERT INTO mtx VALUES (?, ?, ?);", zip(out["m_gene"].tolist(), out["m_cell"].tolist(), out["m_count"].tolist()))
+    db.execute("END TRANSACTION")
+    try:
+        fb = gzip.open(os.path.join(path_out, "barcodes.tsv.gz"), "wb")
+        ff = gzip.open(os.path.join(path_out, "features.tsv.gz"), "wb")
+        fm = gzip.open(os.path.join(path_out, "matrix.mtx.gz"), "wb")
+    except OSError as e:
+        sys.stderr.write("\x1b[31mError:\x1b[0m can not open file %s\n" % e.filename)
+        return 1
+    fm.write(matrix_header(bam_file, rate_cell, rate_depth, stats["total"], stats["sampled"], stats["valid"]).encode("latin-1"))
+    fm.write(b"%d %d %d\n" % (len(inputs.features), len(inputs.cells), stats["nnz"]))
+    fm.write(_lines_u32([out["m_gene"], out["m_cell"], out["m_count"]], " "))
+    fm.close()
+    print("matrix.mtx.gz is generated.")
+    fb.write(b"".join(c + b"\n" for c in inputs.cells))
+    fb.close()
+    print("barcodes.tsv.gz is generated.")
+    ff.write(b"".join(f[1] + b"\t" + f[2] + b"\t" + f[3] + b"\n" for f in inputs.features))
+    ff.close()
+    print("features.tsv.gz is generated.")
+    if _umi_copies_flag:
+        # numi = copies per distinct (cell, gene, umi): GROUP BY cell_index, feature_index, encoded_umi (src/bam2db_ds.c:539-543)
+        uniq, counts = np.unique(out["row_keys"], return_counts=True)
+        c2, g2, nb2, ct2 = decode_rows(uniq, stats["bits_gene"], stats["bits_umi"], stats["umi_max_bytes"])
+        db.execute("CREATE TABLE numi(\n  feature_index INT,\n  cell_index INT,\n  encoded_umi TEXT,\n  n_copy\n)")
+        db.execute("BEGIN TRANSACTION")
+        db.executemany("INSERT INTO numi VALUES (?, ?, ?, ?);",
+                       ((g, c, None if nb < 0 else ct.to_bytes(mb, "big")[:nb], n) for c, g, nb, ct, n in zip(c2.tolist(), g2.tolist(), nb2.tolist(), ct2.tolist(), counts.tolist())))
+        db.execute("END TRANSACTION")
+        with gzip.open(os.path.join(path_out, "umi.tsv.gz"), "wb") as fu:
+            for c, g, nb, ct, n in zip(c2.tolist(), g2.tolist(), nb2.tolist(), ct2.tolist(), counts.tolist()):
+                fu.write(("%d\t%d\t%s\t%d\n" % (g, c, "NULL" if nb < 0 else decode_dna10(ct, mb), n)).encode())
+        print("umi.tsv.gz is generated.")
+    return 0
+
+
+def bam2db(bam_file, db_file, path_out, barcodes_file, features_file, rate_cell, rate_depth, seed=926, device=0, ctx=None):
+    own = ctx is None
+    try:
+        if own:
+            ctx = _lib.Context(device)
+        db = open_database(db_file, bam_file, barcodes_file, features_file)
+        if db is None:
+            return 1
+        inputs = load_lists(db, ctx.lib, barcodes_file, features_file, rate_cell, seed)
         print("Start to convert bam file to sqlite3 database...")
         sys.stdout.flush()
         bam_bytes = np.fromfile(bam_file, dtype=np.uint8)
-        stats, out = run_device(ctx, bam_bytes, inputs, rate_depth, seed, want_rows=True)
-        cell, gene, nbytes, content = decode_rows(out["row_keys"], stats["bits_gene"], stats["bits_umi"], stats["umi_max_bytes"])
-        mb = stats["umi_max_bytes"]
-
-        def rows():
-            for c, g, nb, ct in zip(cell.tolist(), gene.tolist(), nbytes.tolist(), content.tolist()):
-                yield (c, g, None if nb < 0 else ct.to_bytes(mb, "big")[:nb])
-        db.execute("BEGIN TRANSACTION")
-        db.executemany("INSERT INTO umi VALUES (?, ?, ?);", rows())
-        db.execute("END TRANSACTION")
-        print("In %s, total fastQ reads: %d" % (bam_file, stats["total"]))
-        print("In %s, sampled fastQ reads: %d" % (bam_file, stats["sampled"]))
-        print("In %s, sampled and valid fastQ reads: %d" % (bam_file, stats["valid"]))
-        # table mtx from the device COO, with the schema text sqlite gives `CREATE TABLE mtx AS SELECT ...` (src/bam2db_ds.c:480-483)
-        db.execute("CREATE TABLE mtx(\n  feature_index INT,\n  cell_index INT,\n  expression_level\n)")
-        db.execute("BEGIN TRANSACTION")
-        db.executemany("INSERT INTO mtx VALUES (?, ?, ?);", zip(out["m_gene"].tolist(), out["m_cell"].tolist(), out["m_count"].tolist()))
-        db.execute("END TRANSACTION")
-        try:
-            fb = gzip.open(os.path.join(path_out, "barcodes.tsv.gz"), "wb")
-            ff = gzip.open(os.path.join(path_out, "features.tsv.gz"), "wb")
-            fm = gzip.open(os.path.join(path_out, "matrix.mtx.gz"), "wb")
-        except OSError as e:
-            sys.stderr.write("\x1b[31mError:\x1b[0m can not open file %s\n" % e.filename)
-            return 1
-        fm.write(matrix_header(bam_file, rate_cell, rate_depth, stats["total"], stats["sampled"], stats["valid"]).encode("latin-1"))
-        fm.write(b"%d %d %d\n" % (len(inputs.features), len(inputs.cells), stats["nnz"]))
-        fm.write(_lines_u32([out["m_gene"], out["m_cell"], out["m_count"]], " "))
-        fm.close()
-        print("matrix.mtx.gz is generated.")
-        fb.write(b"".join(c + b"\n" for c in inputs.cells))
-        fb.close()
-        print("barcodes.tsv.gz is generated.")
-        ff.write(b"".join(f[1] + b"\t" + f[2] + b"\t" + f[3] + b"\n" for f in inputs.features))
-        ff.close()
-        print("features.tsv.gz is generated.")
-        if _umi_copies_flag:
-            # numi = copies per distinct (cell, gene, umi): GROUP BY cell_index, feature_index, encoded_umi (src/bam2db_ds.c:539-543)
-            keys = np.sort(out["row_keys"], kind="stable")
-            uniq, counts = np.unique(keys, return_counts=True)
-            c2, g2, nb2, ct2 = decode_rows(uniq, stats["bits_gene"], stats["bits_umi"], stats["umi_max_bytes"])
-            db.execute("CREATE TABLE numi(\n  feature_index INT,\n  cell_index INT,\n  encoded_umi TEXT,\n  n_copy\n)")
-            db.execute("BEGIN TRANSACTION")
-            db.executemany("INSERT INTO numi VALUES (?, ?, ?, ?);",
-                           ((g, c, None if nb < 0 else ct.to_bytes(mb, "big")[:nb], n) for c, g, nb, ct, n in zip(c2.tolist(), g2.tolist(), nb2.tolist(), ct2.tolist(), counts.tolist())))
-            db.execute("END TRANSACTION")
-            with gzip.open(os.path.join(path_out, "umi.tsv.gz"), "wb") as fu:
-                for c, g, nb, ct, n in zip(c2.tolist(), g2.tolist(), nb2.tolist(), ct2.tolist(), counts.tolist()):
-                    fu.write(("%d\t%d\t%s\t%d\n" % (g, c, "NULL" if nb < 0 else decode_dna10(ct, mb), n)).encode())
-            print("umi.tsv.gz is generated.")
+        stats, out = run_device(ctx, bam_bytes, inputs, rate_depth, seed, want_rows=True, umi_max_bytes=4)
+        rc = write_outputs(db, bam_file, path_out, inputs, rate_cell, rate_depth, stats, out)
         db.close()
-        return 0
+        return rc
     except (_lib.FastfError, ValueError, OSError, sqlite3.Error) as e:
         sys.stderr.write("bam2db: %s\n" % e)
         return 1

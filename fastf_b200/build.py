@@ -92,7 +92,7 @@ def build_emu():
     if _newer(out, deps):
         return out
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    _run(["g++", "-O1", "-g", "-std=c++17", "-DFASTF_EMU", "-I" + os.path.join(ROOT, "tests", "emu"), "-x", "c++", "-fPIC", "-shared", "-o", out,
+    _run(["g++", "-O2", "-std=c++17", "-DFASTF_EMU", "-I" + os.path.join(ROOT, "tests", "emu"), "-x", "c++", "-fPIC", "-shared", "-o", out,
           os.path.join(csrc, "capi.cu"), "-lz"])
     return out
 

@@ -685,6 +685,7 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
     rc = rc || cudaEventCreateWithFlags(&job->ev_mt, cudaEventDisableTiming) != cudaSuccess;
     rc = rc || cudaEventCreate(&job->ev_first) != cudaSuccess || cudaEventCreate(&job->ev_last) != cudaSuccess;
     if (!rc) rc = cudaMemsetAsync(job->counters.p, 0, 4 * sizeof(u64), ctx->compute) != cudaSuccess;
+    job->header_done = p->headerless != 0;
     if (rc) { if (!ctx->err[0]) ctx_fail(ctx, "bam2db_begin: resource setup failed"); fastf_bam2db_job_free(job); return 1; }
     *out = job;
     return 0;
@@ -1000,6 +1001,15 @@ extern "C" int fastf_bam2db_kept_device(fastf_bam2db_job *job, uint64_t **dev_ke
     return 0;
 }
 
+extern "C" int fastf_bam2db_sample_counts(fastf_bam2db_job *job, uint64_t *sampled, uint64_t *valid)
+{
+    fastf_ctx *ctx = job->ctx;
+    if (!job->sampled_done) return ctx_fail(ctx, "bam2db_sample_counts: call fastf_bam2db_sample first");
+    if (sampled) *sampled = job->n_sampled;
+    if (valid) *valid = job->n_valid;
+    return 0;
+}
+
 extern "C" int fastf_bam2db_key_layout(fastf_bam2db_job *job, uint32_t *bits_cell, uint32_t *bits_gene, uint32_t *bits_umi)
 {
     *bits_cell = job->L.bits_cell; *bits_gene = job->L.bits_gene; *bits_umi = job->L.bits_umi;
@@ -1033,6 +1043,42 @@ static int coo_to_host(fastf_ctx *ctx, RleScratch &R, u64 nnz, u32 **m_gene, u32
         CK(cudaStreamSynchronize(s));
     }
     return 0;
+}
+
+// counters, sizes and the per-stage CUDA-event clocks of a job (no result arrays)
+static int fill_stats(fastf_bam2db_job *job, fastf_bam2db_result *res)
+{
+    fastf_ctx *ctx = job->ctx;
+    const FastfKeyLayout &L = job->L;
+    res->total = job->n_records;
+    res->cb_valid = job->n_cand;
+    res->sampled = job->n_sampled;
+    res->valid = job->n_valid;
+    res->bits_cell = L.bits_cell; res->bits_gene = L.bits_gene; res->bits_umi = L.bits_umi; res->umi_max_bytes = L.umi_max_bytes;
+    res->n_blocks = job->n_blocks; res->compressed_bytes = job->comp_bytes; res->inflated_bytes = job->infl_bytes;
+    res->status = job->status;
+    for (int i = 0; i < 2; i++) { job->t_infl[i].collect(&job->ms_inflate); job->t_parse[i].collect(&job->ms_parse); job->t_gather[i].collect(&job->ms_gather); }
+    job->t_mt[0].collect(&job->ms_mt); job->t_mt[1].collect(&job->ms_mt); job->t_sample.collect(&job->ms_sample); job->t_sort.collect(&job->ms_sort); job->t_count.collect(&job->ms_count);
+    res->ms_inflate = job->ms_inflate; res->ms_parse = job->ms_parse; res->ms_gather = job->ms_gather; res->ms_mt = job->ms_mt;
+    res->ms_sample = job->ms_sample; res->ms_sort = job->ms_sort; res->ms_count = job->ms_count;
+    if (job->first_recorded) {
+        CK(cudaEventRecord(job->ev_last, ctx->compute));
+        CK(cudaEventSynchronize(job->ev_last));
+        CK(cudaEventElapsedTime(&res->ms_device_total, job->ev_first, job->ev_last));
+    }
+    res->n_launches = ctx->launches - job->launches0;
+    res->n_chunks = job->n_chunks;
+    return 0;
+}
+
+extern "C" int fastf_bam2db_stats(fastf_bam2db_job *job, fastf_bam2db_result *res)
+{
+    fastf_ctx *ctx = job->ctx;
+    CK(cudaSetDevice(ctx->device));
+    memset(res, 0, sizeof *res);
+    CK(cudaStreamSynchronize(ctx->compute));
+    CK(cudaStreamSynchronize(ctx->mt));
+    return fill_stats(job, res);
 }
 
 extern "C" int fastf_bam2db_finish(fastf_bam2db_job *job, fastf_bam2db_result *res)
@@ -1069,25 +1115,8 @@ extern "C" int fastf_bam2db_finish(fastf_bam2db_job *job, fastf_bam2db_result *r
     TRY(coo_to_host(ctx, job->rleS, nnz, &res->m_gene, &res->m_cell, &res->m_count, ctx->compute));
     CK(cudaStreamSynchronize(ctx->compute));
     CK(cudaStreamSynchronize(ctx->mt));
-    res->total = job->n_records;
-    res->cb_valid = job->n_cand;
-    res->sampled = job->n_sampled;
-    res->valid = job->n_valid;
+    TRY(fill_stats(job, res));
     res->nnz = nnz;
-    res->bits_cell = L.bits_cell; res->bits_gene = L.bits_gene; res->bits_umi = L.bits_umi; res->umi_max_bytes = L.umi_max_bytes;
-    res->n_blocks = job->n_blocks; res->compressed_bytes = job->comp_bytes; res->inflated_bytes = job->infl_bytes;
-    res->status = job->status;
-    for (int i = 0; i < 2; i++) { job->t_infl[i].collect(&job->ms_inflate); job->t_parse[i].collect(&job->ms_parse); job->t_gather[i].collect(&job->ms_gather); }
-    job->t_mt[0].collect(&job->ms_mt); job->t_mt[1].collect(&job->ms_mt); job->t_sample.collect(&job->ms_sample); job->t_sort.collect(&job->ms_sort); job->t_count.collect(&job->ms_count);
-    res->ms_inflate = job->ms_inflate; res->ms_parse = job->ms_parse; res->ms_gather = job->ms_gather; res->ms_mt = job->ms_mt;
-    res->ms_sample = job->ms_sample; res->ms_sort = job->ms_sort; res->ms_count = job->ms_count;
-    if (job->first_recorded) {
-        CK(cudaEventRecord(job->ev_last, ctx->compute));
-        CK(cudaEventSynchronize(job->ev_last));
-        CK(cudaEventElapsedTime(&res->ms_device_total, job->ev_first, job->ev_last));
-    }
-    res->n_launches = ctx->launches - job->launches0;
-    res->n_chunks = job->n_chunks;
     return 0;
 }
 

@@ -75,6 +75,7 @@ typedef struct {
     uint32_t want_rows;         /* also return the kept rows in read order (the sqlite `umi` table) */
     uint32_t inflate_lanes;     /* 0 = default; lanes per BGZF block in the inflate kernel: 32, 16 or 8 */
     uint64_t chunk_inflated_bytes; /* 0 = default streaming chunk size */
+    uint32_t headerless;        /* 1: the fed blocks start at an alignment record (a later shard of a BAM; the BAM header went to another job) */
 } fastf_bam2db_params;
 
 typedef struct {
@@ -108,9 +109,13 @@ int fastf_bam2db_counts(fastf_bam2db_job *job, uint64_t *n_records, uint64_t *n_
 /* depth sampling with the global ordinal of this job's first CB-valid read; leaves the kept keys (read order) on device */
 int fastf_bam2db_sample(fastf_bam2db_job *job, uint64_t ordinal_base);
 int fastf_bam2db_kept_device(fastf_bam2db_job *job, uint64_t **dev_keys, uint64_t *n);
+/* after fastf_bam2db_sample: this job's sampled_reads_counts and sampled_valid_reads_counts (reference src/bam2db_ds.c:392,435) */
+int fastf_bam2db_sample_counts(fastf_bam2db_job *job, uint64_t *sampled, uint64_t *valid);
 int fastf_bam2db_key_layout(fastf_bam2db_job *job, uint32_t *bits_cell, uint32_t *bits_gene, uint32_t *bits_umi);
 /* single-GPU tail: (sample if not done) + sort + dedup + count + copy back */
 int fastf_bam2db_finish(fastf_bam2db_job *job, fastf_bam2db_result *res);
+/* counters, sizes and per-stage device clocks so far, without finishing (multi-GPU driver); no arrays are allocated */
+int fastf_bam2db_stats(fastf_bam2db_job *job, fastf_bam2db_result *res);
 void fastf_bam2db_job_free(fastf_bam2db_job *job);
 void fastf_bam2db_result_free(fastf_bam2db_result *res);
 

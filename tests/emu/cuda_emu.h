@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY.  A small cooperative SIMT emulator so the CUDA kernels under
 // fastf_b200/csrc can be compiled with g++ (-DFASTF_EMU) and logic-tested in a container that has
-// no GPU.  One CTA runs at a time; each CUDA thread is a ucontext fiber; warp collectives and
+// no GPU.  One CTA runs at a time; each CUDA thread is a fiber (hand-rolled x86-64 stack switch: no syscalls); warp collectives and
 // __syncthreads are rendezvous points.  A round in which no fiber makes progress is reported as a
 // deadlock (catches divergent collectives).  FASTF_EMU_SHUFFLE=<seed> permutes the fiber visiting
 // order each round to shake out missing-barrier bugs.  Nothing here models performance.
@@ -12,7 +12,6 @@
 #include <cstring>
 #include <functional>
 #include <map>
-#include <ucontext.h>
 #include <vector>
 
 struct dim3 {
@@ -71,9 +70,20 @@ inline dim3 threadIdx, blockIdx, blockDim, gridDim;
 using std::max;
 using std::min;
 
+#if !defined(__x86_64__)
+#error "cuda_emu.h: the fiber switch below is x86-64 System V only"
+#endif
+// saves the callee-saved registers on the current stack, stores its stack pointer in *save_sp, continues on new_sp
+extern "C" void fastf_emu_switch(void **save_sp, void *new_sp);
+__asm__(".text\n.globl fastf_emu_switch\n.type fastf_emu_switch,@function\nfastf_emu_switch:\n"
+        "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+        "  movq %rsp, (%rdi)\n  movq %rsi, %rsp\n"
+        "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n  ret\n"
+        ".size fastf_emu_switch, .-fastf_emu_switch\n");
+
 namespace emu {
 struct Fiber {
-    ucontext_t ctx;
+    void *sp = nullptr;   // saved stack pointer while the fiber is switched out
     char *stack = nullptr;
     bool done = true;
 };
@@ -84,7 +94,7 @@ struct Rdv {
 };
 struct State {
     std::vector<Fiber> fibers;
-    ucontext_t sched;
+    void *sched_sp = nullptr;
     int cur = -1, live = 0, nthreads = 0;
     bool progress = false;
     uint32_t bar_arrived = 0, bar_gen = 0;
@@ -95,7 +105,7 @@ struct State {
 inline State g;
 static const size_t STACK_BYTES = 256 * 1024;
 
-inline void yield() { swapcontext(&g.fibers[g.cur].ctx, &g.sched); }
+inline void yield() { fastf_emu_switch(&g.fibers[g.cur].sp, g.sched_sp); }
 inline void fiber_entry()
 {
     g.body();
@@ -104,7 +114,8 @@ inline void fiber_entry()
     g.live--;
     g.progress = true;
     if (g.live > 0 && g.bar_arrived == (uint32_t)g.live && g.bar_arrived) { g.bar_arrived = 0; g.bar_gen++; }
-    swapcontext(&f.ctx, &g.sched);
+    fastf_emu_switch(&f.sp, g.sched_sp);
+    abort();   // a finished fiber is never resumed
 }
 inline void set_tid(int i)
 {
@@ -127,12 +138,14 @@ template <class F> void launch(dim3 grid, dim3 block, size_t, F &&body)
         for (int i = 0; i < T; i++) {
             Fiber &f = g.fibers[i];
             if (!f.stack) f.stack = (char *)malloc(STACK_BYTES);
-            getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = f.stack;
-            f.ctx.uc_stack.ss_size = STACK_BYTES;
-            f.ctx.uc_link = &g.sched;
+            // initial frame: six callee-saved register slots, then the entry address `ret` jumps to (rsp % 16 == 8 on entry)
+            void **top = (void **)(((uintptr_t)f.stack + STACK_BYTES) & ~(uintptr_t)15);
+            top -= 8;
+            for (int r = 0; r < 6; r++) top[r] = nullptr;
+            top[6] = (void *)fiber_entry;
+            top[7] = nullptr;
+            f.sp = (void *)top;
             f.done = false;
-            makecontext(&f.ctx, (void (*)())fiber_entry, 0);
             order[i] = i;
         }
         uint64_t rs = g.shuffle_seed * 0x9e3779b97f4a7c15ull + bx + 1;
@@ -144,7 +157,7 @@ template <class F> void launch(dim3 grid, dim3 block, size_t, F &&body)
                 if (g.fibers[i].done) continue;
                 g.cur = i;
                 set_tid(i);
-                swapcontext(&g.sched, &g.fibers[i].ctx);
+                fastf_emu_switch(&g.sched_sp, g.fibers[i].sp);
             }
             if (!g.progress && g.live > 0) {
                 fprintf(stderr, "cuda_emu: DEADLOCK in block %u (%d live threads blocked; divergent barrier/collective?)\n", bx, g.live);

@@ -46,13 +46,9 @@ def test_emu_bam2db_edge_cases_shuffled_schedule(emu_lib):
 
 
 def test_emu_freq_ragged(emu_lib):
-    _run(emu_lib, ["freq-ragged-l16-u12", "freq-ragged_nonl-l16-u0", "freq-ragged_trunc-l5-u3"])
+    _run(emu_lib, ["freq-ragged_nonl-l16-u12", "freq-ragged_trunc-l5-u3"])
 
 
 def test_emu_c_host_cli(emu_lib):
     """the C host (fastf_b200/host: option parsing, list readers, sqlite + gz writers, -u) linked against the emulator build"""
     _run(emu_lib, ["synth4k-c0.5-r0.5-s926", "freq-ragged-l16-u0"], cli=True)
-
-
-def test_emu_python_host_umicopies(emu_lib):
-    _run(emu_lib, ["synth4k-c0.2-r0.9-s77"])

@@ -313,3 +313,42 @@ def test_c_cli_freq_golden(gpu_ctx, tmp_path):
         r = subprocess.run([cli, "freq", "-R", os.path.join(d, case["input"]), "-o", str(tmp_path), "-l", str(case["l"]), "-u", str(case["u"])], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         assert r.returncode == 0, r.stderr
         assert open(tmp_path / "whitelist.txt", "rb").read() == gzip.open(os.path.join(d, case["expect"]), "rb").read(), case["name"]
+
+
+# ------------------------------------------------------------------------------------------------ several GPUs
+def test_bam2db_two_gpus_equal_reference_and_one_gpu(gpu_ctx, synth, oracle, tmp_path):
+    """2 ranks over NCCL (contiguous block shards, global draw ordinals, all-to-all by cell hash) reproduce the single-GPU result
+    and the oracle byte for byte.  Needs 2 GPUs (gpurun --gpus 2); skipped on a 1-GPU box, where tests/test_sharded_gloo.py
+    covers the same host logic on CPU."""
+    import subprocess
+    import sys
+    import torch
+    import fastf_b200
+    from dbdigest import db_digest
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    d = tmp_path / "in"
+    d.mkdir()
+    paths, _ = synth.write_bam_set(str(d), n_reads=400000, n_cells=800, n_genes=1500, seed=5, p_umi_n=0.004, n_molecules=150000)
+    os.rename(paths["bam"], str(d / "in.bam"))
+    one, two, ora = tmp_path / "one", tmp_path / "two", tmp_path / "ora"
+    for x in (one, two, ora):
+        x.mkdir()
+    cwd = os.getcwd()
+    os.chdir(str(d))
+    try:
+        assert fastf_b200.bam2db("in.bam", str(one / "x.db"), str(one), "barcodes.tsv.gz", "features.tsv.gz", 0.6, 0.4, 926, ctx=gpu_ctx) == 0
+        oracle.bam2db("in.bam", "barcodes.tsv.gz", "features.tsv.gz", 0.6, 0.4, 926, str(ora))
+    finally:
+        os.chdir(cwd)
+    env = dict(os.environ, FASTF_SHARDED_BACKEND="nccl")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29733",
+           os.path.join(ROOT, "tests", "sharded_worker.py"), str(d), str(two), "0.6", "0.4", "926"]
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    for f in ("matrix.mtx.gz", "barcodes.tsv.gz", "features.tsv.gz"):
+        a, b = gzip.open(str(one / f), "rb").read(), gzip.open(str(two / f), "rb").read()
+        assert a == b, f
+        assert a == open(str(ora / f[:-3]), "rb").read(), f
+    d1, d2 = db_digest(str(one / "x.db")), db_digest(str(two / "x.db"))
+    assert d1 == d2
