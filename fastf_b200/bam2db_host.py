@@ -365,7 +365,12 @@ def bam2db(bam_file, db_file, path_out, barcodes_file, features_file, rate_cell,
         print("Start to convert bam file to sqlite3 database...")
         sys.stdout.flush()
         bam_bytes = np.fromfile(bam_file, dtype=np.uint8)
-        stats, out = run_device(ctx, bam_bytes, inputs, rate_depth, seed, want_rows=True, umi_max_bytes=4)
+        try:
+            stats, out = run_device(ctx, bam_bytes, inputs, rate_depth, seed, want_rows=True, umi_max_bytes=3)   # 10x UMIs: 10 or 12 bases
+        except _lib.FastfError as e:
+            if "umi-too-long" not in str(e):
+                raise
+            stats, out = run_device(ctx, bam_bytes, inputs, rate_depth, seed, want_rows=True, umi_max_bytes=4)   # up to 16 bases
         rc = write_outputs(db, bam_file, path_out, inputs, rate_cell, rate_depth, stats, out)
         db.close()
         return rc

@@ -726,6 +726,8 @@ static int finalize_slot(fastf_bam2db_job *job, u32 si)
     job->status |= (u32)snap[2];
     if (job->status) {
         char buf[256];
+        if (job->status == FASTF_ST_UMI_TOO_LONG)
+            return ctx_fail(ctx, "bam2db: umi-too-long: a UB tag holds more than %u bases; begin the job with a larger umi_max_bytes", 4u * job->L.umi_max_bytes);
         return ctx_fail(ctx, "bam2db: malformed input in chunk ending at block %llu: %s", (unsigned long long)job->n_blocks, status_string(job->status, buf, sizeof buf));
     }
     if (n_cand > job->cand_cap) {
@@ -1199,7 +1201,8 @@ extern "C" int fastf_unique_partition_device(fastf_ctx *ctx, uint64_t *dev_keys,
     CK(cudaSetDevice(ctx->device));
     for (u32 p = 0; p < nparts; p++) part_counts[p] = 0;
     if (n == 0) return 0;
-    if (nparts == 0 || nparts > 255 || key_bits + 8 > 64) return ctx_fail(ctx, "unique_partition: bad nparts/key_bits");
+    if (nparts == 0 || nparts > 256 || key_bits + (nparts > 1 ? bits_for(nparts - 1) : 0) > 64)
+        return ctx_fail(ctx, "unique_partition: %u key bits leave no room for the destination tag of %u parts", key_bits, nparts);
     cudaStream_t s = ctx->compute;
     SortScratch S;
     RleScratch R;

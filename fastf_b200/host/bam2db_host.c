@@ -143,25 +143,30 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
     printf("Start to convert bam file to sqlite3 database...\n");
     fflush(stdout);
     if (fastf_ctx_create(fastf_device, &ctx)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(NULL)); goto done; }
-    {
+    for (uint32_t umi_bytes = 3; umi_bytes <= 4; umi_bytes++) {   /* 10x UMIs are 10 or 12 bases; retry once with room for 16 */
         fastf_bam2db_params p;
         memset(&p, 0, sizeof p);
         uint32_t zero_off[1] = {0};
         p.cell_keys = cells.buf ? cells.buf : ""; p.cell_off = cells.off ? cells.off : zero_off; p.n_cells = cells.n;
         p.gene_keys = fkeys.buf ? fkeys.buf : ""; p.gene_off = fkeys.off ? fkeys.off : zero_off; p.n_genes = fkeys.n;
         p.seed = seed; p.d0 = d0; p.keep_threshold = fastf_keep_threshold(rate_depth);
-        p.umi_max_bytes = 4;    /* UMIs up to 16 bases */
+        p.umi_max_bytes = umi_bytes;
         p.want_rows = 1;
         if (fastf_bam2db_begin(ctx, &p, &job)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
         const size_t PIECE = (size_t)256 << 20;
-        if (fastf_host_alloc(ctx, PIECE, &pin[0]) || fastf_host_alloc(ctx, PIECE, &pin[1])) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
+        if (!pin[0] && (fastf_host_alloc(ctx, PIECE, &pin[0]) || fastf_host_alloc(ctx, PIECE, &pin[1]))) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
         size_t got;
-        int which = 0;
-        while ((got = fread(pin[which], 1, PIECE, bam)) > 0) {
-            if (fastf_bam2db_feed(job, pin[which], got)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
+        int which = 0, failed = 0;
+        rewind(bam);
+        while (!failed && (got = fread(pin[which], 1, PIECE, bam)) > 0) {
+            failed = fastf_bam2db_feed(job, pin[which], got);
             which ^= 1;
         }
-        if (fastf_bam2db_finish(job, &res)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
+        if (!failed) failed = fastf_bam2db_finish(job, &res);
+        if (!failed) break;
+        if (umi_bytes == 3 && strstr(fastf_last_error(ctx), "umi-too-long")) { fastf_bam2db_job_free(job); job = NULL; continue; }
+        fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx));
+        goto done;
     }
 
     /* ---- table umi in read order (reference :351-435) ---- */

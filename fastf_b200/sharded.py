@@ -132,7 +132,7 @@ def bam2db_sharded(bam_file, db_file, path_out, barcodes_file, features_file, ra
         lo, hi = shard_ranges(len(io), world)[rank]
         start = int(io[lo]) - 18 if lo < len(io) else buf.size     # 18 = BGZF header with the 6-byte BC extra field
         end = int(io[hi]) - 18 if hi < len(io) else buf.size
-        with B.Bam2dbJob(ctx, inputs, rate_depth, seed, want_rows=True, umi_max_bytes=4, headerless=(rank != 0)) as job:
+        with B.Bam2dbJob(ctx, inputs, rate_depth, seed, want_rows=True, umi_max_bytes=3, headerless=(rank != 0)) as job:
             if end > start:
                 job.feed(buf.ctypes.data + start, end - start)
             res = sharded_tail(ctx, job, dist, torch, device, rank, world, want_rows=True)
