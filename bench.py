@@ -366,7 +366,7 @@ def main():
 def multi_gpu_tail(job, dist, torch, ctx, rank, world, inputs):
     """counts all-gather -> sample at the global ordinal -> unique + partition by cell hash -> NCCL all-to-all -> local dedup/count -> gather"""
     from fastf_b200 import sharded
-    res = sharded.sharded_tail(ctx, job, dist, torch, "cuda", rank, world, want_rows=False)
+    res = sharded.sharded_tail(ctx, job, dist, torch, "cuda", rank, world, len(inputs.cells), want_rows=False)
     st = job.stats()           # this rank's stage clocks and byte counts
     if res is not None:
         st.update({k: v for k, v in res[0].items() if k in ("total", "cb_valid", "sampled", "valid", "nnz", "exchanged_keys")})

@@ -1157,6 +1157,26 @@ extern "C" int fastf_sort_u64_device(fastf_ctx *ctx, uint64_t *dev_keys, uint32_
     return rc;
 }
 
+// same, results left on the device in caller-provided arrays of capacity >= n (multi-GPU driver: the pieces travel over NCCL)
+extern "C" int fastf_dedup_count_device_out(fastf_ctx *ctx, const uint64_t *dev_sorted_keys, uint64_t n, uint32_t bits_gene, uint32_t bits_umi, uint64_t *nnz, uint32_t *dev_gene, uint32_t *dev_cell,
+                                            uint32_t *dev_count)
+{
+    CK(cudaSetDevice(ctx->device));
+    RleScratch R;
+    u64 ng = 0;
+    int rc = rle_groups(ctx, R, dev_sorted_keys, nullptr, n, bits_umi, bits_umi - 1, bits_gene, &ng, nullptr, ctx->compute);
+    if (!rc && ng) {
+        rc = cudaMemcpyAsync(dev_gene, R.out_gene.p, ng * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->compute) != cudaSuccess ||
+             cudaMemcpyAsync(dev_cell, R.out_cell.p, ng * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->compute) != cudaSuccess ||
+             cudaMemcpyAsync(dev_count, R.count.p, ng * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->compute) != cudaSuccess;
+        if (rc) ctx_fail(ctx, "dedup_count_device_out: copy failed");
+    }
+    if (cudaStreamSynchronize(ctx->compute) != cudaSuccess && !rc) rc = ctx_fail(ctx, "dedup_count_device_out: stream error");
+    *nnz = ng;
+    rle_scratch_release(ctx, R);
+    return rc;
+}
+
 extern "C" int fastf_dedup_count_device(fastf_ctx *ctx, const uint64_t *dev_sorted_keys, uint64_t n, uint32_t bits_gene, uint32_t bits_umi, uint64_t *nnz, uint32_t **m_gene, uint32_t **m_cell,
                                         uint32_t **m_count)
 {
@@ -1170,15 +1190,19 @@ extern "C" int fastf_dedup_count_device(fastf_ctx *ctx, const uint64_t *dev_sort
     return rc;
 }
 
-// destination of a cell for the multi-GPU exchange: all keys of one (cell, gene) group must meet on one rank
-static inline __host__ __device__ u32 fastf_cell_dest(u32 cell, u32 nparts) { return fastf_hash_finalize(cell * 0x9e3779b1u + 0x7f4a7c15u) % nparts; }
+// Destination of a cell for the multi-GPU exchange: all keys of one (cell, gene) group must meet on one rank.  The "hash" is
+// order preserving -- an equal-width range partition of the 1-based cell index, which is itself the position of the barcode in a
+// file-ordered random sample, so depth is spread evenly -- and therefore the ranks' (cell, gene)-sorted COO pieces concatenate
+// in rank order without a merge.
+static inline __host__ __device__ u32 fastf_cell_dest(u32 cell, u32 n_cells, u32 nparts) { return (u32)(((u64)(cell - 1u) * nparts) / (n_cells ? n_cells : 1u)); }
 
-__global__ void __launch_bounds__(256) fastf_tag_dest_kernel(u64 *__restrict__ keys, u64 n, u32 cell_shift, u32 key_bits, u32 nparts)
+__global__ void __launch_bounds__(256) fastf_tag_dest_kernel(u64 *__restrict__ keys, u64 n, u32 cell_shift, u32 key_bits, u32 n_cells, u32 nparts)
 {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     u64 k = keys[i];
-    keys[i] = k | ((u64)fastf_cell_dest((u32)(k >> cell_shift), nparts) << key_bits);
+    u32 d = fastf_cell_dest((u32)(k >> cell_shift), n_cells, nparts);
+    keys[i] = k | ((u64)(d < nparts ? d : nparts - 1u) << key_bits);
 }
 // heads of runs of equal keys -> compacted, with the destination tag stripped; part boundaries by binary search
 __global__ void __launch_bounds__(256) fastf_part_bounds_kernel(const u64 *__restrict__ keys, u64 n, u32 key_bits, u32 nparts, u64 *__restrict__ bounds)
@@ -1195,8 +1219,8 @@ __global__ void __launch_bounds__(256) fastf_strip_tag_kernel(u64 *__restrict__ 
     if (i < n) keys[i] &= (1ull << key_bits) - 1ull;
 }
 
-extern "C" int fastf_unique_partition_device(fastf_ctx *ctx, uint64_t *dev_keys, uint64_t n, uint32_t key_bits, uint32_t bits_gene, uint32_t bits_umi, uint32_t nparts, uint64_t *dev_out_keys,
-                                             uint64_t *part_counts)
+extern "C" int fastf_unique_partition_device(fastf_ctx *ctx, uint64_t *dev_keys, uint64_t n, uint32_t key_bits, uint32_t bits_gene, uint32_t bits_umi, uint32_t n_cells, uint32_t nparts,
+                                             uint64_t *dev_out_keys, uint64_t *part_counts)
 {
     CK(cudaSetDevice(ctx->device));
     for (u32 p = 0; p < nparts; p++) part_counts[p] = 0;
@@ -1214,7 +1238,7 @@ extern "C" int fastf_unique_partition_device(fastf_ctx *ctx, uint64_t *dev_keys,
         TRY(dev_reserve(ctx, orand, 2 * sizeof(u64)));
         TRY(dev_reserve(ctx, bounds, 257 * sizeof(u64)));
         TRY(pin_reserve(ctx, host, 257 * sizeof(u64)));
-        FASTF_LAUNCH(fastf_tag_dest_kernel, (u32)((n + 255) / 256), 256, 0, s, dev_keys, n, bits_gene + bits_umi, key_bits, nparts);
+        FASTF_LAUNCH(fastf_tag_dest_kernel, (u32)((n + 255) / 256), 256, 0, s, dev_keys, n, bits_gene + bits_umi, key_bits, n_cells, nparts);
         CKL("tag_dest");
         u64 varying = 0;
         TRY(varying_bits(ctx, orand, host, dev_keys, n, &varying, s));

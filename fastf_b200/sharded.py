@@ -5,9 +5,9 @@ the CPU tests), SURVEY.md section 8(e):
   2. every rank inflates + parses its shard; all-gather of {records, CB-valid reads} gives each rank the global ordinal of its
      first CB-valid read, i.e. its position in the reference's single MT19937 draw sequence (src/bam2db_ds.c:385).
   3. depth sampling on device with stream index d0 + base + local ordinal.
-  4. local sort + unique of the kept keys, partitioned by hash(cell) % world (fastf_unique_partition_device), exchanged with ONE
-     variable-size all-to-all; every (cell, gene) group then lives on exactly one rank.
-  5. local sort + run-length dedup/count -> COO per rank; rank 0 gathers and orders the pieces by (cell, gene).
+  4. local sort + unique of the kept keys, partitioned by an order-preserving hash of the cell (equal ranges of the cell index,
+     fastf_unique_partition_device), exchanged with ONE variable-size all-to-all; every (cell, gene) group then lives on one rank.
+  5. local sort + run-length dedup/count -> COO per rank on the device; the pieces are sent to rank 0 and concatenate in rank order.
 
 The result on rank 0 is byte-identical to the single-GPU job (tests/test_sharded_gloo.py, tests/test_gpu_parity.py)."""
 import ctypes as C
@@ -44,7 +44,7 @@ def index_blocks(lib, buf):
         return io[:nb].copy(), il[:nb].copy(), isz[:nb].copy()
 
 
-def sharded_tail(ctx, job, dist, torch, device, rank, world, want_rows=False):
+def sharded_tail(ctx, job, dist, torch, device, rank, world, n_cells, want_rows=False):
     """steps 2-5 above for a job that has been fed this rank's shard.  Returns on rank 0 (stats, out) like Bam2dbJob.finish; None elsewhere."""
     lib = ctx.lib
     n_rec, n_cbv = job.counts()
@@ -63,10 +63,10 @@ def sharded_tail(ctx, job, dist, torch, device, rank, world, want_rows=False):
         rows = np.zeros(n, dtype=np.uint64)
         if n:
             ctx.check(lib.fastf_memcpy_d2h(ctx.h, C.c_void_p(rows.ctypes.data), C.c_void_p(kp), n * 8), "d2h rows")
-    # 4. unique + partition by destination, then one all-to-all
+    # 4. unique + partition by destination (order-preserving range partition of the cell index), then one all-to-all
     send_buf = torch.empty(max(n, 1), dtype=torch.int64, device=device)
     pc = (C.c_uint64 * world)()
-    ctx.check(lib.fastf_unique_partition_device(ctx.h, C.c_void_p(kp), n, key_bits, bits_gene, bits_umi, world, C.c_void_p(send_buf.data_ptr()), pc), "unique_partition")
+    ctx.check(lib.fastf_unique_partition_device(ctx.h, C.c_void_p(kp), n, key_bits, bits_gene, bits_umi, n_cells, world, C.c_void_p(send_buf.data_ptr()), pc), "unique_partition")
     send = [int(x) for x in pc]
     sc = torch.tensor(send, dtype=torch.int64, device=device)
     rc_t = torch.zeros(world, dtype=torch.int64, device=device)
@@ -77,32 +77,46 @@ def sharded_tail(ctx, job, dist, torch, device, rank, world, want_rows=False):
     dist.all_to_all_single(recv_buf[:m], send_buf[:sum(send)], output_split_sizes=recv, input_split_sizes=send)
     if device != "cpu":
         torch.cuda.current_stream().synchronize()   # the library launches on its own stream
-    # 5. local sort + dedup/count
+    # 5. local sort + dedup/count, results stay on the device
     nnz = C.c_uint64()
-    pg, pcell, pcount = _lib.c_u32p(), _lib.c_u32p(), _lib.c_u32p()
+    coo_dev = torch.empty((3, max(m, 1)), dtype=torch.int32, device=device)
     if m:
         ctx.check(lib.fastf_sort_u64_device(ctx.h, C.c_void_p(recv_buf.data_ptr()), None, m, key_bits), "sort")
-    ctx.check(lib.fastf_dedup_count_device(ctx.h, C.c_void_p(recv_buf.data_ptr()), m, bits_gene, bits_umi, C.byref(nnz), C.byref(pg), C.byref(pcell), C.byref(pcount)), "dedup_count")
+    ctx.check(lib.fastf_dedup_count_device_out(ctx.h, C.c_void_p(recv_buf.data_ptr()), m, bits_gene, bits_umi, C.byref(nnz), C.c_void_p(coo_dev[0].data_ptr()),
+                                               C.c_void_p(coo_dev[1].data_ptr()), C.c_void_p(coo_dev[2].data_ptr())), "dedup_count")
     k = nnz.value
-    z = np.zeros(0, np.uint32)
-    coo = [np.ctypeslib.as_array(p, (k,)).copy() if k else z for p in (pg, pcell, pcount)]
-    for p in (pg, pcell, pcount):
-        lib.fastf_free(p)
-    # gather on rank 0
-    payload = {"coo": coo, "counts": (n_rec, n_cbv, sampled, valid), "rows": rows, "sent": sum(send), "received": m}
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object(payload, gathered, dst=0)
+    # 6. rank 0 collects counters and the COO pieces; pieces are ordered by rank (cells are range partitioned), so they concatenate
+    meta = torch.tensor([n_rec, n_cbv, sampled, valid, k, sum(send), n], dtype=torch.int64, device=device)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    metas = [x.tolist() for x in metas]
+    ks = [x[4] for x in metas]
+    pieces = []
+    for col in range(3):
+        out_sizes = ks if rank == 0 else [0] * world
+        in_sizes = [k] + [0] * (world - 1)
+        dst = torch.empty(max(sum(out_sizes), 1), dtype=torch.int32, device=device)
+        dist.all_to_all_single(dst[:sum(out_sizes)], coo_dev[col][:k].contiguous(), output_split_sizes=out_sizes, input_split_sizes=in_sizes)
+        pieces.append(dst[:sum(out_sizes)])
+    rows_all = None
+    if want_rows:
+        ns = [x[6] for x in metas]
+        out_sizes = ns if rank == 0 else [0] * world
+        dst = torch.empty(max(sum(out_sizes), 1), dtype=torch.int64, device=device)
+        src = torch.empty(max(n, 1), dtype=torch.int64, device=device)
+        if n:
+            ctx.check(lib.fastf_memcpy_h2d(ctx.h, C.c_void_p(src.data_ptr()), C.c_void_p(rows.ctypes.data), n * 8) if device != "cpu" else 0, "rows")
+            if device == "cpu":
+                C.memmove(src.data_ptr(), rows.ctypes.data, n * 8)
+        dist.all_to_all_single(dst[:sum(out_sizes)], src[:n], output_split_sizes=out_sizes, input_split_sizes=[n] + [0] * (world - 1))
+        rows_all = dst[:sum(out_sizes)]
     if rank != 0:
         return None
-    g = np.concatenate([p["coo"][0] for p in gathered])
-    c = np.concatenate([p["coo"][1] for p in gathered])
-    v = np.concatenate([p["coo"][2] for p in gathered])
-    order = np.lexsort((g, c))   # every rank's piece is (cell, gene)-sorted and cells are disjoint across ranks
-    stats = {"total": sum(p["counts"][0] for p in gathered), "cb_valid": sum(p["counts"][1] for p in gathered), "sampled": sum(p["counts"][2] for p in gathered),
-             "valid": sum(p["counts"][3] for p in gathered), "nnz": int(g.size), "bits_cell": bits_cell, "bits_gene": bits_gene, "bits_umi": bits_umi,
-             "umi_max_bytes": (bits_umi - 4) // 8, "exchanged_keys": sum(p["sent"] for p in gathered)}
-    out = {"m_gene": g[order], "m_cell": c[order], "m_count": v[order],
-           "row_keys": np.concatenate([p["rows"] for p in gathered]) if want_rows else np.zeros(0, np.uint64)}
+    g, c, v = (p.cpu().numpy().view(np.uint32) for p in pieces)
+    stats = {"total": sum(x[0] for x in metas), "cb_valid": sum(x[1] for x in metas), "sampled": sum(x[2] for x in metas), "valid": sum(x[3] for x in metas),
+             "nnz": int(g.size), "bits_cell": bits_cell, "bits_gene": bits_gene, "bits_umi": bits_umi, "umi_max_bytes": (bits_umi - 4) // 8,
+             "exchanged_keys": sum(x[5] for x in metas)}
+    out = {"m_gene": g, "m_cell": c, "m_count": v, "row_keys": rows_all.cpu().numpy().view(np.uint64) if want_rows else np.zeros(0, np.uint64)}
     return stats, out
 
 
@@ -135,7 +149,7 @@ def bam2db_sharded(bam_file, db_file, path_out, barcodes_file, features_file, ra
         with B.Bam2dbJob(ctx, inputs, rate_depth, seed, want_rows=True, umi_max_bytes=3, headerless=(rank != 0)) as job:
             if end > start:
                 job.feed(buf.ctypes.data + start, end - start)
-            res = sharded_tail(ctx, job, dist, torch, device, rank, world, want_rows=True)
+            res = sharded_tail(ctx, job, dist, torch, device, rank, world, len(inputs.cells), want_rows=True)
         rc = 0
         if rank == 0:
             stats, out = res

@@ -125,10 +125,14 @@ int fastf_sort_u64_device(fastf_ctx *ctx, uint64_t *dev_keys, uint32_t *dev_vals
 /* sorted packed keys on device -> COO (host arrays, library-owned: free with fastf_free) */
 int fastf_dedup_count_device(fastf_ctx *ctx, const uint64_t *dev_sorted_keys, uint64_t n, uint32_t bits_gene, uint32_t bits_umi,
                              uint64_t *nnz, uint32_t **m_gene, uint32_t **m_cell, uint32_t **m_count);
-/* locally sort + unique kept keys and partition them by hash(cell) % nparts: out_keys (device, capacity n) holds the
- * unique keys grouped by destination; part_counts[nparts] (host) their sizes */
+/* same with the COO left on the device in caller-provided arrays of capacity >= n */
+int fastf_dedup_count_device_out(fastf_ctx *ctx, const uint64_t *dev_sorted_keys, uint64_t n, uint32_t bits_gene, uint32_t bits_umi,
+                                 uint64_t *nnz, uint32_t *dev_gene, uint32_t *dev_cell, uint32_t *dev_count);
+/* locally sort + unique kept keys and partition them by destination rank = (cell_index-1)*nparts/n_cells (an order-preserving
+ * partition of the cell index): out_keys (device, capacity n) holds the unique keys grouped by destination, each group
+ * ascending; part_counts[nparts] (host) their sizes */
 int fastf_unique_partition_device(fastf_ctx *ctx, uint64_t *dev_keys, uint64_t n, uint32_t key_bits, uint32_t bits_gene, uint32_t bits_umi,
-                                  uint32_t nparts, uint64_t *dev_out_keys, uint64_t *part_counts);
+                                  uint32_t n_cells, uint32_t nparts, uint64_t *dev_out_keys, uint64_t *part_counts);
 void fastf_free(void *p);
 
 /* host-buffer wrappers around single kernels (tests, smoke) */
