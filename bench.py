@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--ref-sample-reads", type=int, default=5_000_000)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--engine", default="sm", choices=["sm", "hw"], help="inflate engine of the main line: hand-written SM kernel (default) or the B200 hardware decompression engine")
+    ap.add_argument("--no-hw-extra", action="store_true", help="skip the extra pass that reports the hardware decompression engine beside the main line")
     ap.add_argument("--chunk-mb", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -264,8 +266,11 @@ def main():
         eof_start = int(in_off[rec_hi]) - 18
         chunk = args.chunk_mb << 20
 
+        HW = 0x100   # FASTF_INFLATE_HW_ENGINE
+        engine = {"lanes": args.lanes | (HW if args.engine == "hw" else 0)}
+
         def one_job(device_resident, want_copy=False):
-            with B.Bam2dbJob(ctx, inputs, RATE_DEPTH, SEED, want_rows=False, inflate_lanes=args.lanes, chunk_inflated_bytes=chunk, headerless=(rank != 0)) as job:
+            with B.Bam2dbJob(ctx, inputs, RATE_DEPTH, SEED, want_rows=False, inflate_lanes=engine["lanes"], chunk_inflated_bytes=chunk, headerless=(rank != 0)) as job:
                 for t in range(tiles):
                     if device_resident:
                         lo = 0 if (t == 0 and rank == 0) else rec_lo
@@ -327,6 +332,30 @@ def main():
             d2h = int(estats[-1].get("nnz") or 0) * 12 + 64
             e2e = {"value": world * reads_per_step / (e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(tiles * comp_rec_bytes + hdr_end), "d2h_bytes_per_step": d2h,
                    "ms_per_step": e_ms, "steps": args.e2e_steps, "timing": "host wall clock around begin..finish (pinned host BGZF bytes in, COO out)"}
+        hw_extra = None
+        if args.engine == "sm" and not args.no_hw_extra:
+            # the same job with BGZF inflate on the B200 hardware decompression engine instead of the SM kernel (reported beside the main line)
+            engine["lanes"] = args.lanes | HW
+            try:
+                hw_wall, hw_stats, _, _, hw_dev_ms = timed(True, max(1, min(args.steps, 2)), 1)
+                hw_ms = hw_dev_ms / max(1, min(args.steps, 2))
+                hw_e2e_ms = None
+                if not args.no_e2e:
+                    hw_ew, _, _, _, _ = timed(False, 1, 1)
+                    hw_e2e_ms = 1e3 * hw_ew
+                if dist:
+                    tt = torch.tensor([hw_ms, hw_e2e_ms or 0.0], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    hw_ms, hw_e2e_ms = float(tt[0]), (float(tt[1]) if hw_e2e_ms is not None else None)
+                hs = hw_stats[-1]
+                hw_extra = {"what": "same job, BGZF inflate by the hardware decompression engine (cuMemBatchDecompressAsync, DEFLATE) instead of fastf_bgzf_inflate_kernel; not the headline",
+                            "value": world * reads_per_step / (hw_ms / 1e3), "unit": "reads/s", "ms_per_step": hw_ms,
+                            "e2e_value": (world * reads_per_step / (hw_e2e_ms / 1e3)) if hw_e2e_ms else None,
+                            "inflate_ms": hs.get("ms_inflate"), "inflate_alg_GBps": ((hs["compressed_bytes"] + hs["inflated_bytes"]) / (hs["ms_inflate"] * 1e-3) / 1e9) if hs.get("ms_inflate") else None,
+                            "parse_ms": hs.get("ms_parse")}
+            except Exception as e:   # engine absent on this GPU / driver: say so, the main line stands
+                hw_extra = {"unavailable": str(e)[:200]}
+            engine["lanes"] = args.lanes
         if rank != 0:
             return 0
         peak, peak_src = measured_peak()
@@ -349,7 +378,7 @@ def main():
                            "parallelism": ("single GPU" if world == 1 else f"{world} ranks: contiguous BGZF block shards, all-gather of counts, NCCL all-to-all of locally deduplicated keys by cell hash, gather of COO")},
                 "roofline": {"bound": "hbm", "kernel": "fastf_bgzf_inflate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes_launch, "ms_per_launch": infl_ms_launch},
-                "stages": stages, "gpu_launches": launches, "clocks": clocks, "e2e": e2e}
+                "stages": stages, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "inflate_engine": args.engine, "hw_decompress_engine": hw_extra}
         if not args.no_cpu_baseline:
             d2 = os.path.join(tmp, "refin")
             os.makedirs(d2, exist_ok=True)

@@ -24,13 +24,16 @@
 #include <string.h>
 #include <algorithm>
 #include <vector>
+#ifndef FASTF_EMU
+#include <cuda.h>   // driver API: cuMemBatchDecompressAsync (Blackwell hardware decompression engine)
+#endif
 
 #define FASTF_ABI_VERSION 1
 
 struct PoolEntry { void *p; size_t cap; };
 struct fastf_ctx {
     int device;
-    cudaStream_t compute, copy, mt;
+    cudaStream_t compute, copy, mt, infl;
     char err[1024];
     u32 launches;   // kernels launched through this context (bench: gpu_launches)
     // size-bucketed caches of device / pinned allocations: a job's buffers are recycled by the next job on the same
@@ -117,6 +120,7 @@ static int dev_reserve(fastf_ctx *ctx, DevBuf &b, size_t bytes, size_t keep_byte
         // the old buffer goes back to the pool: nothing in flight on any of our streams may still touch it
         CK(cudaStreamSynchronize(ctx->compute));
         CK(cudaStreamSynchronize(ctx->copy));
+        CK(cudaStreamSynchronize(ctx->infl));
         CK(cudaStreamSynchronize(ctx->mt));
         dev_release(ctx, b);
     }
@@ -143,6 +147,7 @@ static int pin_reserve(fastf_ctx *ctx, PinBuf &b, size_t bytes)
     if (b.p) {
         CK(cudaStreamSynchronize(ctx->compute));
         CK(cudaStreamSynchronize(ctx->copy));
+        CK(cudaStreamSynchronize(ctx->infl));
         CK(cudaStreamSynchronize(ctx->mt));
         pin_release(ctx, b);
     }
@@ -190,7 +195,7 @@ extern "C" int fastf_ctx_create(int device, fastf_ctx **out)
     fastf_ctx *ctx = (fastf_ctx *)calloc(1, sizeof *ctx);
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->mt, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->mt, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->infl, cudaStreamNonBlocking) != cudaSuccess) {
         snprintf(g_create_err, sizeof g_create_err, "cudaStreamCreate failed");
         free(ctx);
         return 1;
@@ -211,6 +216,7 @@ extern "C" void fastf_ctx_destroy(fastf_ctx *ctx)
     cudaStreamDestroy(ctx->compute);
     cudaStreamDestroy(ctx->copy);
     cudaStreamDestroy(ctx->mt);
+    cudaStreamDestroy(ctx->infl);
     free(ctx);
 }
 extern "C" const char *fastf_last_error(const fastf_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
@@ -222,7 +228,7 @@ extern "C" int fastf_device_alloc(fastf_ctx *ctx, size_t bytes, void **out) { CK
 extern "C" void fastf_device_free(fastf_ctx *ctx, void *p) { (void)ctx; if (p) cudaFree(p); }
 extern "C" int fastf_memcpy_h2d(fastf_ctx *ctx, void *d, const void *s, size_t n) { CK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, ctx->compute)); CK(cudaStreamSynchronize(ctx->compute)); return 0; }
 extern "C" int fastf_memcpy_d2h(fastf_ctx *ctx, void *d, const void *s, size_t n) { CK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, ctx->compute)); CK(cudaStreamSynchronize(ctx->compute)); return 0; }
-extern "C" int fastf_synchronize(fastf_ctx *ctx) { CK(cudaStreamSynchronize(ctx->copy)); CK(cudaStreamSynchronize(ctx->mt)); CK(cudaStreamSynchronize(ctx->compute)); return 0; }
+extern "C" int fastf_synchronize(fastf_ctx *ctx) { CK(cudaStreamSynchronize(ctx->copy)); CK(cudaStreamSynchronize(ctx->infl)); CK(cudaStreamSynchronize(ctx->mt)); CK(cudaStreamSynchronize(ctx->compute)); return 0; }
 extern "C" void fastf_free(void *p) { free(p); }
 extern "C" void fastf_ctx_trim(fastf_ctx *ctx) { if (ctx) { cudaSetDevice(ctx->device); cudaDeviceSynchronize(); pools_trim(ctx); } }
 
@@ -347,10 +353,68 @@ extern "C" int64_t fastf_bgzf_index_host(const void *buf, size_t n, uint64_t *in
 // ---------------------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------------------
-static int launch_inflate(fastf_ctx *ctx, int lanes, const u8 *comp, u64 comp_total, const u64 *in_off, const u32 *in_len, const u64 *out_off, const u32 *isize, u32 nblocks, u8 *out,
-                          u32 *status, cudaStream_t s)
+#define FASTF_INFLATE_HW_ENGINE 0x100u   // flag in the `inflate_lanes` argument (include/fastf_gpu.h)
+
+// after a hardware-engine batch: actual byte counts -> status words
+__global__ void __launch_bounds__(256) fastf_de_check_kernel(u32 *__restrict__ act_status, const u32 *__restrict__ isize, u32 n)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) act_status[i] = (isize[i] != 0 && act_status[i] != isize[i]) ? (u32)FASTF_ST_SIZE_MISMATCH : 0u;
+}
+
+struct DeScratch {   // parameter array of a hardware-engine batch; must stay alive until the batch has run
+#ifndef FASTF_EMU
+    std::vector<CUmemDecompressParams> params;
+#endif
+};
+
+// h_* = host copies of the block index (needed to build the engine's parameter array)
+static int launch_inflate(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_total, const u64 *in_off, const u32 *in_len, const u64 *out_off, const u32 *isize, u32 nblocks, u8 *out,
+                          u32 *status, cudaStream_t s, DeScratch *de, const u64 *h_in_off, const u32 *h_in_len, const u64 *h_out_off, const u32 *h_isize)
 {
     if (nblocks == 0) return 0;
+    if (lanes & FASTF_INFLATE_HW_ENGINE) {
+#ifdef FASTF_EMU
+        return ctx_fail(ctx, "inflate: the hardware decompression engine does not exist in the emulator build");
+#else
+        // Blackwell decompression engine: one DEFLATE operation per BGZF block, submitted as one batch in stream order.
+        // dstActBytes lands in the status array and is turned into status bits by a small kernel afterwards.
+        de->params.clear();
+        de->params.reserve(nblocks);
+        for (u32 i = 0; i < nblocks; i++) {
+            if (h_isize[i] == 0) continue;   // empty (EOF) blocks produce nothing
+            CUmemDecompressParams p;
+            memset(&p, 0, sizeof p);
+            p.srcNumBytes = h_in_len[i];
+            p.dstNumBytes = h_isize[i];
+            p.dstActBytes = (cuuint32_t *)(status + i);
+            p.src = comp + h_in_off[i];
+            p.dst = out + h_out_off[i];
+            p.algo = CU_MEM_DECOMPRESS_ALGORITHM_DEFLATE;
+            de->params.push_back(p);
+        }
+        CK(cudaMemsetAsync(status, 0, (size_t)nblocks * sizeof(u32), s));
+        if (!de->params.empty()) {
+            // the driver entry point is resolved through the runtime: no link-time dependency on libcuda (absent on build hosts)
+            typedef CUresult (*decompress_fn)(CUmemDecompressParams *, size_t, unsigned int, size_t *, CUstream);
+            static decompress_fn fn = nullptr;
+            if (!fn) {
+                void *sym = nullptr;
+                cudaDriverEntryPointQueryResult q;
+                if (cudaGetDriverEntryPoint("cuMemBatchDecompressAsync", &sym, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !sym)
+                    return ctx_fail(ctx, "inflate: this driver does not export cuMemBatchDecompressAsync (hardware decompression engine unavailable)");
+                fn = (decompress_fn)sym;
+            }
+            size_t erri = 0;
+            CUresult r = fn(de->params.data(), de->params.size(), 0, &erri, (CUstream)s);
+            if (r != CUDA_SUCCESS)
+                return ctx_fail(ctx, "inflate: cuMemBatchDecompressAsync failed (CUresult %d) at operation %zu; is the hardware decompression engine available on this GPU?", (int)r, erri);
+        }
+        FASTF_LAUNCH(fastf_de_check_kernel, (nblocks + 255) / 256, 256, 0, s, status, isize, nblocks);
+        CKL("de_check");
+        return 0;
+#endif
+    }
     if (lanes == 8) {
         FASTF_LAUNCH(fastf_bgzf_inflate_kernel<8>, (nblocks + 3) / 4, 32, 0, s, comp, comp_total, in_off, in_len, out_off, isize, nblocks, out, status);
     } else if (lanes == 16) {
@@ -572,6 +636,9 @@ struct ChunkSlot {
     BlockIndexDev idx;
     DevBuf comp;          // compressed bytes of the chunk (host feeds only)
     DevBuf stage;         // per-block candidate staging
+    DevBuf infl;          // inflated bytes of the chunk (double buffered: chunk i+1 inflates while chunk i is parsed)
+    DeScratch de;
+    cudaEvent_t ev_infl = nullptr;
     PinBuf snap;          // counters snapshot {n_records, n_candidates, status_or, chunk_candidates}
     cudaEvent_t ev_copy = nullptr, ev_done = nullptr;
     u32 nblocks = 0;
@@ -583,11 +650,10 @@ struct fastf_bam2db_job {
     fastf_bam2db_params prm;
     FastfKeyLayout L;
     DevTable cells, genes;
-    int lanes;
+    u32 lanes;
     u64 chunk_bytes;
     ChunkSlot slot[2];
     u32 next_slot = 0;
-    DevBuf infl;              // inflated bytes of the chunk in flight
     DevBuf counters;          // u64[4]: n_records, n_candidates, status_or, (unused)
     DevBuf hdr_off;           // u64: offset of the first alignment record inside the current chunk
     DevBuf cand;              // all candidates (CB-valid reads) in file order
@@ -626,11 +692,13 @@ extern "C" void fastf_bam2db_job_free(fastf_bam2db_job *job)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->compute);
     cudaStreamSynchronize(ctx->copy);
+    cudaStreamSynchronize(ctx->infl);
     cudaStreamSynchronize(ctx->mt);
     for (int i = 0; i < 2; i++) {
         ChunkSlot &S = job->slot[i];
-        index_release(ctx, S.idx); dev_release(ctx, S.comp); dev_release(ctx, S.stage); pin_release(ctx, S.snap);
+        index_release(ctx, S.idx); dev_release(ctx, S.comp); dev_release(ctx, S.stage); dev_release(ctx, S.infl); pin_release(ctx, S.snap);
         if (S.ev_copy) cudaEventDestroy(S.ev_copy);
+        if (S.ev_infl) cudaEventDestroy(S.ev_infl);
         if (S.ev_done) cudaEventDestroy(S.ev_done);
         job->t_infl[i].destroy(); job->t_parse[i].destroy(); job->t_gather[i].destroy();
     }
@@ -639,7 +707,7 @@ extern "C" void fastf_bam2db_job_free(fastf_bam2db_job *job)
     if (job->ev_first) cudaEventDestroy(job->ev_first);
     if (job->ev_last) cudaEventDestroy(job->ev_last);
     dev_release(ctx, job->cells.slots); dev_release(ctx, job->cells.pool); dev_release(ctx, job->genes.slots); dev_release(ctx, job->genes.pool);
-    dev_release(ctx, job->infl); dev_release(ctx, job->counters); dev_release(ctx, job->hdr_off); dev_release(ctx, job->cand); dev_release(ctx, job->mt_state); dev_release(ctx, job->keepbits);
+    dev_release(ctx, job->counters); dev_release(ctx, job->hdr_off); dev_release(ctx, job->cand); dev_release(ctx, job->mt_state); dev_release(ctx, job->keepbits);
     dev_release(ctx, job->tile_valid); dev_release(ctx, job->tile_tot); dev_release(ctx, job->sample_counters); dev_release(ctx, job->kept); dev_release(ctx, job->orand);
     pin_release(ctx, job->small_host);
     sort_scratch_release(ctx, job->sortS);
@@ -657,7 +725,10 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
     job->ctx = ctx;
     job->prm = *p;
     job->launches0 = ctx->launches;
-    job->lanes = (p->inflate_lanes == 8 || p->inflate_lanes == 16 || p->inflate_lanes == 32) ? (int)p->inflate_lanes : 32;
+    {
+        const u32 l = p->inflate_lanes & 0xffu;
+        job->lanes = ((l == 8 || l == 16 || l == 32) ? l : 32u) | (p->inflate_lanes & FASTF_INFLATE_HW_ENGINE);
+    }
     job->chunk_bytes = p->chunk_inflated_bytes ? std::max<u64>(p->chunk_inflated_bytes, 1u << 20) : FASTF_DEFAULT_CHUNK;
     FastfKeyLayout &L = job->L;
     L.umi_max_bytes = p->umi_max_bytes ? p->umi_max_bytes : 3;
@@ -679,6 +750,7 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
         rc = rc || pin_reserve(ctx, job->slot[i].snap, 4 * sizeof(u64));
         rc = rc || cudaEventCreateWithFlags(&job->slot[i].ev_copy, cudaEventDisableTiming) != cudaSuccess;
         rc = rc || cudaEventCreateWithFlags(&job->slot[i].ev_done, cudaEventDisableTiming) != cudaSuccess;
+        rc = rc || cudaEventCreateWithFlags(&job->slot[i].ev_infl, cudaEventDisableTiming) != cudaSuccess;
         rc = rc || job->t_infl[i].init() || job->t_parse[i].init() || job->t_gather[i].init();
     }
     rc = rc || job->t_mt[0].init() || job->t_mt[1].init() || job->t_sample.init() || job->t_sort.init() || job->t_count.init();
@@ -778,30 +850,34 @@ static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb
         // the previous user of S.comp (chunk i-2) finished inflating: its ev_done was waited for in finalize_slot
         CK(cudaMemcpyAsync(S.comp.p, host_src, host_bytes, cudaMemcpyHostToDevice, ctx->copy));
         CK(cudaEventRecord(S.ev_copy, ctx->copy));
-        CK(cudaStreamWaitEvent(ctx->compute, S.ev_copy, 0));
+        CK(cudaStreamWaitEvent(ctx->infl, S.ev_copy, 0));
         comp_dev = S.comp.as<u8>();
         comp_total = padded;
     }
-    // infl / stage are written by this chunk; infl is shared by both slots (same stream -> ordered)
-    TRY(dev_reserve(ctx, job->infl, out_total + 64));
+    // S.infl / S.stage / S.idx were last used by chunk i-2, whose parse and gather have completed (finalize_slot above)
+    TRY(dev_reserve(ctx, S.infl, out_total + 64));
     TRY(dev_reserve(ctx, S.stage, stage_total * sizeof(u64) + 64));
-    if (!job->first_recorded) { CK(cudaEventRecord(job->ev_first, ctx->compute)); job->first_recorded = true; }
-    TRY(index_upload(ctx, S.idx, ctx->compute));
+    if (!job->first_recorded) { CK(cudaEventRecord(job->ev_first, ctx->infl)); job->first_recorded = true; }
+    // inflate runs on its own stream so that chunk i+1 inflates (SM kernel or hardware engine) while chunk i is parsed
+    TRY(index_upload(ctx, S.idx, ctx->infl));
     job->t_infl[si].collect(&job->ms_inflate);
-    job->t_infl[si].start(ctx->compute);
-    TRY(launch_inflate(ctx, job->lanes, comp_dev, comp_total, S.idx.in_off, S.idx.in_len, S.idx.out_off, S.idx.isize, nb, job->infl.as<u8>(), S.idx.st_infl, ctx->compute));
-    job->t_infl[si].stop(ctx->compute);
+    job->t_infl[si].start(ctx->infl);
+    TRY(launch_inflate(ctx, job->lanes, comp_dev, comp_total, S.idx.in_off, S.idx.in_len, S.idx.out_off, S.idx.isize, nb, S.infl.as<u8>(), S.idx.st_infl, ctx->infl, &S.de, S.idx.h_in_off,
+                       S.idx.h_in_len, S.idx.h_out_off, S.idx.h_isize));
+    job->t_infl[si].stop(ctx->infl);
+    CK(cudaEventRecord(S.ev_infl, ctx->infl));
+    CK(cudaStreamWaitEvent(ctx->compute, S.ev_infl, 0));
     job->t_parse[si].collect(&job->ms_parse);
     job->t_parse[si].start(ctx->compute);
     if (!job->header_done) {
-        FASTF_LAUNCH(fastf_bam_header_kernel, 1, 32, 0, ctx->compute, (const u8 *)job->infl.as<u8>(), out_total, job->hdr_off.as<u64>(), (u32 *)(job->counters.as<u64>() + 2));
+        FASTF_LAUNCH(fastf_bam_header_kernel, 1, 32, 0, ctx->compute, (const u8 *)S.infl.as<u8>(), out_total, job->hdr_off.as<u64>(), (u32 *)(job->counters.as<u64>() + 2));
         CKL("bam_header");
         job->header_done = true;
     } else {
         CK(cudaMemsetAsync(job->hdr_off.p, 0, sizeof(u64), ctx->compute));
     }
     if (nb) {
-        FASTF_LAUNCH(fastf_bam_parse_kernel, (nb + FASTF_PARSE_WARPS - 1) / FASTF_PARSE_WARPS, FASTF_PARSE_WARPS * 32, 0, ctx->compute, (const u8 *)job->infl.as<u8>(), (u64)((out_total + 15) & ~15ull),
+        FASTF_LAUNCH(fastf_bam_parse_kernel, (nb + FASTF_PARSE_WARPS - 1) / FASTF_PARSE_WARPS, FASTF_PARSE_WARPS * 32, 0, ctx->compute, (const u8 *)S.infl.as<u8>(), (u64)((out_total + 15) & ~15ull),
                      (const u64 *)S.idx.out_off, (const u32 *)S.idx.isize, nb, (const u64 *)job->hdr_off.as<u64>(), job->cells.view, job->genes.view, job->L, (const u64 *)S.idx.stage_off,
                      S.stage.as<u64>(), S.idx.nrec, S.idx.ncbv, S.idx.st_parse);
         CKL("bam_parse");
@@ -1274,6 +1350,7 @@ extern "C" int fastf_unique_partition_device(fastf_ctx *ctx, uint64_t *dev_keys,
 // ---------------------------------------------------------------------------------------------------
 struct InflatedFile {
     DevBuf comp, infl;
+    DeScratch de;
     BlockIndexDev idx;
     u64 n_blocks = 0, infl_bytes = 0;
     u32 status = 0;
@@ -1281,7 +1358,7 @@ struct InflatedFile {
 static void inflated_release(fastf_ctx *ctx, InflatedFile &F) { dev_release(ctx, F.comp); dev_release(ctx, F.infl); index_release(ctx, F.idx); }
 
 // Inflate a whole BGZF image (host bytes, or device bytes + host index) into F.infl in one launch.
-static int inflate_whole(fastf_ctx *ctx, InflatedFile &F, const void *host_bytes, size_t n, const u8 *dev_bytes, const std::vector<FastfBgzfBlock> *pre, int lanes, float *ms, cudaStream_t s)
+static int inflate_whole(fastf_ctx *ctx, InflatedFile &F, const void *host_bytes, size_t n, const u8 *dev_bytes, const std::vector<FastfBgzfBlock> *pre, u32 lanes, float *ms, cudaStream_t s)
 {
     std::vector<FastfBgzfBlock> local;
     const std::vector<FastfBgzfBlock> *blocks = pre;
@@ -1313,7 +1390,12 @@ static int inflate_whole(fastf_ctx *ctx, InflatedFile &F, const void *host_bytes
     TRY(index_upload(ctx, F.idx, s));
     cudaEvent_t a = nullptr, b = nullptr;
     if (ms) { CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); CK(cudaEventRecord(a, s)); }
-    TRY(launch_inflate(ctx, lanes, comp, comp_total, F.idx.in_off, F.idx.in_len, F.idx.out_off, F.idx.isize, (u32)nb, F.infl.as<u8>(), F.idx.st_infl, s));
+    {
+        const u32 l = lanes & 0xffu;
+        lanes = ((l == 8 || l == 16 || l == 32) ? l : 32u) | (lanes & FASTF_INFLATE_HW_ENGINE);
+    }
+    TRY(launch_inflate(ctx, lanes, comp, comp_total, F.idx.in_off, F.idx.in_len, F.idx.out_off, F.idx.isize, (u32)nb, F.infl.as<u8>(), F.idx.st_infl, s, &F.de, F.idx.h_in_off, F.idx.h_in_len,
+                       F.idx.h_out_off, F.idx.h_isize));
     if (ms) { CK(cudaEventRecord(b, s)); }
     // OR of the per-block status words
     std::vector<u32> st(nb);
@@ -1337,7 +1419,7 @@ extern "C" int fastf_inflate_host(fastf_ctx *ctx, const void *bgzf_bytes, size_t
     *out = nullptr;
     *out_n = 0;
     InflatedFile F;
-    int rc = inflate_whole(ctx, F, bgzf_bytes, n, nullptr, nullptr, lanes ? lanes : 32, ms, ctx->compute);
+    int rc = inflate_whole(ctx, F, bgzf_bytes, n, nullptr, nullptr, (u32)lanes, ms, ctx->compute);
     if (!rc) {
         *out = malloc(F.infl_bytes ? F.infl_bytes : 1);
         if (!*out) rc = ctx_fail(ctx, "inflate_host: out of host memory");
@@ -1546,7 +1628,7 @@ static int freq_common(fastf_ctx *ctx, const void *host_bytes, size_t n, const u
         }
         // the inflate launch is timed separately; the device-total clock starts before it
         cudaEventRecord(e0, s);
-        rc = inflate_whole(ctx, F, host_bytes, n, dev_bytes, pre, lanes ? (int)lanes : 32, &res->ms_inflate, s);
+        rc = inflate_whole(ctx, F, host_bytes, n, dev_bytes, pre, lanes, &res->ms_inflate, s);
         text = F.infl.as<u8>();
         text_n = F.infl_bytes;
         res->n_blocks = F.n_blocks;

@@ -24,6 +24,10 @@
 extern "C" {
 #endif
 
+/* OR this into any `inflate_lanes` argument to inflate with the B200 hardware decompression engine (driver API
+ * cuMemBatchDecompressAsync, DEFLATE) instead of the hand-written SM kernel.  Fails loudly where the engine is absent. */
+#define FASTF_INFLATE_HW_ENGINE 0x100u
+
 typedef struct fastf_ctx fastf_ctx;
 typedef struct fastf_bam2db_job fastf_bam2db_job;
 
@@ -73,7 +77,7 @@ typedef struct {
     uint64_t keep_threshold;    /* fastf_keep_threshold(rate_depth) */
     uint32_t umi_max_bytes;     /* 0 = 3 (UMIs up to 12 bases); up to 4 */
     uint32_t want_rows;         /* also return the kept rows in read order (the sqlite `umi` table) */
-    uint32_t inflate_lanes;     /* 0 = default; lanes per BGZF block in the inflate kernel: 32, 16 or 8 */
+    uint32_t inflate_lanes;     /* 0 = default; lanes per BGZF block in the inflate kernel: 32, 16 or 8; | FASTF_INFLATE_HW_ENGINE */
     uint64_t chunk_inflated_bytes; /* 0 = default streaming chunk size */
     uint32_t headerless;        /* 1: the fed blocks start at an alignment record (a later shard of a BAM; the BAM header went to another job) */
 } fastf_bam2db_params;

@@ -119,6 +119,21 @@ def test_radix_sort_is_a_stable_sort(gpu_ctx, n, bits):
     assert np.array_equal(k3, k2)
 
 
+HW = 0x100   # FASTF_INFLATE_HW_ENGINE
+
+
+def test_hw_decompress_engine_matches_zlib_and_sm_kernel(gpu_ctx, synth, oracle, tmp_path):
+    """optional engine: the B200 hardware decompression engine must give the same bytes as zlib / our SM kernel and the same bam2db result"""
+    from fastf_b200 import bam2db_host as B
+    paths, _ = synth.write_bam_set(str(tmp_path), n_reads=200000, n_cells=500, n_genes=800, seed=21, p_umi_n=0.004)
+    bam = open(paths["bam"], "rb").read()
+    got = _inflate(gpu_ctx, bam, HW)
+    if got is None and b"unavailable" in gpu_ctx.lib.fastf_last_error(gpu_ctx.h):
+        pytest.skip("hardware decompression engine not available on this GPU / driver")
+    assert got == oracle.inflate(bam)
+    _check_against_oracle(gpu_ctx, oracle, paths, 0.5, 0.5, 926, inflate_lanes=HW, chunk_inflated_bytes=8 << 20)
+
+
 # ------------------------------------------------------------------------------------------------ bam2db
 def _oracle_rows_as_keys(o, stats):
     bg, bu, mb = stats["bits_gene"], stats["bits_umi"], stats["umi_max_bytes"]
