@@ -638,7 +638,7 @@ struct ChunkSlot {
     DevBuf stage;         // per-block candidate staging
     DevBuf infl;          // inflated bytes of the chunk (double buffered: chunk i+1 inflates while chunk i is parsed)
     DeScratch de;
-    cudaEvent_t ev_infl = nullptr;
+    cudaEvent_t ev_infl = nullptr, ev_gather = nullptr;
     PinBuf snap;          // counters snapshot {n_records, n_candidates, status_or, chunk_candidates}
     cudaEvent_t ev_copy = nullptr, ev_done = nullptr;
     u32 nblocks = 0;
@@ -699,6 +699,7 @@ extern "C" void fastf_bam2db_job_free(fastf_bam2db_job *job)
         index_release(ctx, S.idx); dev_release(ctx, S.comp); dev_release(ctx, S.stage); dev_release(ctx, S.infl); pin_release(ctx, S.snap);
         if (S.ev_copy) cudaEventDestroy(S.ev_copy);
         if (S.ev_infl) cudaEventDestroy(S.ev_infl);
+        if (S.ev_gather) cudaEventDestroy(S.ev_gather);
         if (S.ev_done) cudaEventDestroy(S.ev_done);
         job->t_infl[i].destroy(); job->t_parse[i].destroy(); job->t_gather[i].destroy();
     }
@@ -751,6 +752,7 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
         rc = rc || cudaEventCreateWithFlags(&job->slot[i].ev_copy, cudaEventDisableTiming) != cudaSuccess;
         rc = rc || cudaEventCreateWithFlags(&job->slot[i].ev_done, cudaEventDisableTiming) != cudaSuccess;
         rc = rc || cudaEventCreateWithFlags(&job->slot[i].ev_infl, cudaEventDisableTiming) != cudaSuccess;
+        rc = rc || cudaEventCreateWithFlags(&job->slot[i].ev_gather, cudaEventDisableTiming) != cudaSuccess;
         rc = rc || job->t_infl[i].init() || job->t_parse[i].init() || job->t_gather[i].init();
     }
     rc = rc || job->t_mt[0].init() || job->t_mt[1].init() || job->t_sample.init() || job->t_sort.init() || job->t_count.init();
@@ -815,6 +817,7 @@ static int finalize_slot(fastf_bam2db_job *job, u32 si)
         CKL("stage_gather");
     }
     job->t_gather[si].stop(ctx->compute);
+    CK(cudaEventRecord(S.ev_gather, ctx->compute));   // the slot's index arrays are free for the next upload (inflate stream) after this
     CK(cudaEventRecord(job->ev_last, ctx->compute));
     job->n_records = n_records;
     job->n_cand = n_cand;
@@ -858,7 +861,9 @@ static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb
     TRY(dev_reserve(ctx, S.infl, out_total + 64));
     TRY(dev_reserve(ctx, S.stage, stage_total * sizeof(u64) + 64));
     if (!job->first_recorded) { CK(cudaEventRecord(job->ev_first, ctx->infl)); job->first_recorded = true; }
-    // inflate runs on its own stream so that chunk i+1 inflates (SM kernel or hardware engine) while chunk i is parsed
+    // inflate runs on its own stream so that chunk i+1 inflates (SM kernel or hardware engine) while chunk i is parsed;
+    // the gather of the slot's previous chunk (compute stream) still reads the index arrays we are about to overwrite
+    CK(cudaStreamWaitEvent(ctx->infl, S.ev_gather, 0));
     TRY(index_upload(ctx, S.idx, ctx->infl));
     job->t_infl[si].collect(&job->ms_inflate);
     job->t_infl[si].start(ctx->infl);
