@@ -1,0 +1,574 @@
+// K1 (v3) -- BGZF / raw-DEFLATE inflate, "thread per stream".
+//
+// The lock-step kernel (bgzf_inflate.cuh) spends a whole warp on one serial Huffman chain: every lane repeats the same
+// ~50 instructions per symbol, and ncu shows it bound by instruction issue (77 % of issue slots, 1 % of DRAM).  This kernel
+// removes the redundancy by splitting the work by role inside one persistent CTA per SM:
+//
+//   decoder warps  (2 warps = 64 lanes)  lane = one BGZF block ("stream").  Pure scalar Huffman decoding out of that stream's
+//                                        own shared-memory tables; emits 4-byte TOKENS (literal | match(len, dist) | end)
+//                                        into the stream's shared-memory ring.  No global stores, no warp collectives.
+//   service warps  (8 warps, lock step)  own 8 streams each.  (a) LZ77: take up to 32 tokens of one stream, prefix-sum their
+//                                        output lengths, store the literals and copy the matches with all 32 lanes
+//                                        (coalesced; source loads of several matches are issued before any is stored so the L2
+//                                        round trips overlap).  (b) stream set-up: fetch the next BGZF block from a global
+//                                        counter, parse deflate block headers, copy stored blocks, build the Huffman tables
+//                                        cooperatively -- decoders never run that code, so they never wait for one another.
+//
+// Tables per stream: 10-bit literal/length table and 7-bit distance table with 16-bit entries (code length, kind, symbol),
+// canonical walk for longer codes, length/distance base+extra bits in a CTA-wide table.  64 streams x 3.3 KB + rings fill the
+// SM's shared memory (214 KB): the number of streams in flight per SM, not registers or threads, is what bounds the kernel.
+#pragma once
+#include "bgzf_inflate.cuh"
+
+#define FASTF_TPS_LBITS 10
+#define FASTF_TPS_DBITS 7
+#define FASTF_TPS_DEC_WARPS 2
+#define FASTF_TPS_SVC_WARPS 8
+#define FASTF_TPS_STREAMS (FASTF_TPS_DEC_WARPS * 32)
+#define FASTF_TPS_THREADS ((FASTF_TPS_DEC_WARPS + FASTF_TPS_SVC_WARPS) * 32)
+#define FASTF_TPS_PER_SVC (FASTF_TPS_STREAMS / FASTF_TPS_SVC_WARPS)
+#define FASTF_TPS_RING 64u
+
+// 16-bit table entry: bits 0-3 code length (0 = longer than the table), bits 4-5 kind, bits 6-15 payload
+#define FASTF_T16_LIT 0u     // payload = literal byte / code-length symbol
+#define FASTF_T16_SYM 1u     // payload = length symbol - 257, or distance symbol
+#define FASTF_T16_EOB 2u
+#define FASTF_T16_BAD 3u
+// tokens
+#define FASTF_TOK_LIT 0u
+#define FASTF_TOK_MATCH (1u << 30)   // bits 0-8 length, bits 9-24 distance
+#define FASTF_TOK_END (2u << 30)     // bits 0-15 status bits of the decoder
+// stream states
+enum { FASTF_TPS_NEXT = 0, FASTF_TPS_RUN = 1, FASTF_TPS_BUILD = 2, FASTF_TPS_DONE = 3 };
+
+struct FastfTpsStream {
+    u16 lit[1 << FASTF_TPS_LBITS];
+    u16 dist[1 << FASTF_TPS_DBITS];
+    u16 lit_sorted[288];
+    u16 dist_sorted[32];
+    u16 lit_cnt[16];
+    u16 dist_cnt[16];
+    u32 ring[FASTF_TPS_RING];
+    // control block (volatile accesses; every hand-over is fenced)
+    u32 state, wr, rd, last;
+    u32 bitpos_lo, bitpos_hi;        // absolute bit offset of the next unread bit inside `comp`
+    u32 pos, isize;                  // decoder's output position / block size
+    u32 lit_walk, dist_walk;         // canonical-walk start for codes longer than the table: first code << 16 | index
+    u32 blk, opos;                   // service side: block index, bytes written
+    u32 inend_lo, inend_hi;          // absolute bit offset of the end of the payload
+    u32 obase_lo, obase_hi;          // offset of the block in the inflated buffer
+};
+
+struct FastfTpsShared {
+    u32 lenK[32], distK[32];         // base << 8 | extra bits
+    u8 cl_order[20];
+    u8 lens[FASTF_TPS_SVC_WARPS][320];    // code lengths of the block a service warp is setting up
+    u16 scratch[FASTF_TPS_SVC_WARPS][32]; // first[16], start[16] while building
+};
+
+#ifdef FASTF_EMU
+#define FASTF_DYN_SMEM(ptr) u8 *ptr = emu::dyn_smem()
+#else
+#define FASTF_DYN_SMEM(ptr) extern __shared__ __align__(16) u8 fastf_dyn_smem_[]; u8 *ptr = fastf_dyn_smem_
+#endif
+
+__device__ __forceinline__ u32 fastf_ldv(const u32 *p) { return *(const volatile u32 *)p; }
+__device__ __forceinline__ void fastf_stv(u32 *p, u32 v) { *(volatile u32 *)p = v; }
+
+__device__ __forceinline__ u32 fastf_make16(u32 alpha, u32 sym)
+{
+    if (alpha == FASTF_ALPHA_PLAIN) return (FASTF_T16_LIT << 4) | (sym << 6);
+    if (alpha == FASTF_ALPHA_LITLEN) {
+        if (sym < 256) return (FASTF_T16_LIT << 4) | (sym << 6);
+        if (sym == 256) return FASTF_T16_EOB << 4;
+        if (sym > 285) return FASTF_T16_BAD << 4;
+        return (FASTF_T16_SYM << 4) | ((sym - 257) << 6);
+    }
+    if (sym >= 30) return FASTF_T16_BAD << 4;
+    return (FASTF_T16_SYM << 4) | (sym << 6);
+}
+
+// Cooperative (32 lanes, lock step) construction of one 16-bit decode table.  Returns non-zero for an invalid code.
+// *walk = (first canonical code of length tbits+1) << 16 | (index of its first symbol in sorted[]).
+__device__ __forceinline__ u32 fastf_tps_build(u32 alpha, const u8 *lens, u32 n, u16 *cnt, u16 *sorted, u16 *lut, u32 tbits, u16 *first, u16 *start, u32 *walk, u32 lane)
+{
+    for (u32 i = lane; i < (1u << tbits); i += 32) lut[i] = 0;
+    u32 bad = 0, wk = 0;
+    if (lane == 0) {
+        for (u32 l = 0; l < 16; l++) cnt[l] = 0;
+        for (u32 s = 0; s < n; s++) cnt[lens[s]]++;
+        i32 left = 1;
+        u32 used = 0;
+        for (u32 l = 1; l < 16; l++) {
+            left = (left << 1) - (i32)cnt[l];
+            if (left < 0) bad = 1;
+            used += cnt[l];
+        }
+        if (left > 0 && used > 1) bad = 1;
+        u32 code = 0, idx = 0;
+        for (u32 l = 1; l < 16; l++) {
+            first[l] = (u16)code;
+            start[l] = (u16)idx;
+            if (l == tbits + 1) wk = (code << 16) | idx;
+            code = (code + cnt[l]) << 1;
+            idx += cnt[l];
+        }
+        if (!bad) {
+            u16 offs[16];
+            for (u32 l = 1; l < 16; l++) offs[l] = start[l];
+            for (u32 s = 0; s < n; s++) {
+                u32 l = lens[s];
+                if (l) sorted[offs[l]++] = (u16)s;
+            }
+        }
+        first[0] = (u16)used;
+    }
+    bad = __shfl_sync(FASTF_FULL_MASK, bad, 0);
+    wk = __shfl_sync(FASTF_FULL_MASK, wk, 0);
+    __syncwarp();
+    if (bad) return 1;
+    const u32 used = first[0];
+    for (u32 i = lane; i < used; i += 32) {
+        const u32 sym = sorted[i];
+        const u32 l = lens[sym];
+        if (l <= tbits) {
+            const u32 code = (u32)first[l] + (i - (u32)start[l]);
+            const u32 rev = __brev(code) >> (32 - l);
+            const u16 e = (u16)(fastf_make16(alpha, sym) | l);
+            for (u32 j = rev; j < (1u << tbits); j += (1u << l)) lut[j] = e;
+        }
+    }
+    __syncwarp();
+    *walk = wk;
+    return 0;
+}
+
+// lock-step lookup used by the service warp while it reads the code-length code (7-bit table in the distance table's storage)
+__device__ __forceinline__ u32 fastf_tps_decode16(const FastfBitReader<32> &br, const u16 *lut, u32 tbits, const u16 *cnt, const u16 *sorted, u32 alpha)
+{
+    u32 e = lut[(u32)br.buf & ((1u << tbits) - 1u)];
+    if (e & 15u) return e;
+    u32 code = 0, first = 0, index = 0;
+    u32 bits = (u32)br.buf;
+    for (u32 len = 1; len < 16; len++) {
+        code |= bits & 1u;
+        bits >>= 1;
+        u32 c = cnt[len];
+        if (code < first + c) return fastf_make16(alpha, sorted[index + (code - first)]) | len;
+        index += c;
+        first = (first + c) << 1;
+        code <<= 1;
+    }
+    return FASTF_T16_BAD << 4;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// service side
+// ------------------------------------------------------------------------------------------------------------------
+struct FastfTpsArgs {
+    const u8 *comp;
+    u64 comp_total;
+    const u64 *in_off;
+    const u32 *in_len;
+    const u64 *out_off;
+    const u32 *isize;
+    u32 nblocks;
+    u8 *out;
+    u32 *status;
+    u32 *next_block;   // global work counter (zeroed before the launch)
+};
+
+// Parse deflate block headers of stream S from its current bit position until a Huffman block is ready for the decoder
+// (state RUN) or the BGZF block is finished / broken (status written, state NEXT).  Stored blocks are copied here.
+__device__ __forceinline__ void fastf_tps_setup(const FastfTpsArgs &A, FastfTpsStream &S, FastfTpsShared &G, u32 sw, u32 lane)
+{
+    const u32 b = S.blk;
+    u8 *out = A.out + (((u64)S.obase_hi << 32) | S.obase_lo);
+    const u64 in_end = ((u64)S.inend_hi << 32) | S.inend_lo;
+    u64 bitpos = ((u64)S.bitpos_hi << 32) | S.bitpos_lo;
+    u32 opos = S.opos, err = 0;
+    u8 *lens = G.lens[sw];
+    u16 *first = G.scratch[sw], *start = G.scratch[sw] + 16;
+    for (;;) {
+        if (bitpos + 3 > in_end) { err |= FASTF_ST_IN_OVERRUN; break; }
+        FastfBitReader<32> br;
+        br.init(A.comp, A.comp_total, bitpos >> 3, FASTF_FULL_MASK, lane);
+        br.drop((u32)(bitpos & 7u));
+        const u64 origin = (bitpos >> 3) * 8ull;   // bits consumed are counted from here
+        br.refill();
+        const u32 last = br.take(1);
+        const u32 btype = br.take(2);
+        if (btype == 3) { err |= FASTF_ST_BAD_BTYPE; break; }
+        if (btype == 0) {
+            br.drop(br.nbits & 7u);
+            br.refill();
+            const u32 len = br.take(16);
+            br.refill();
+            const u32 nlen = br.take(16);
+            if ((len ^ nlen) != 0xffffu) { err |= FASTF_ST_BAD_STORED; break; }
+            if (opos + len > S.isize) { err |= FASTF_ST_OUT_OVERFLOW; break; }
+            const u64 consumed = (u64)br.widx * 32u - br.nbits - br.skip_bits;
+            const u64 src = (origin + consumed) >> 3;
+            if ((src + len) * 8ull > in_end) { err |= FASTF_ST_BAD_STORED; break; }
+            for (u32 i = lane; i < len; i += 32) out[opos + i] = A.comp[src + i];
+            opos += len;
+            bitpos = (src + len) * 8ull;
+            if (last) break;   // block complete
+            continue;
+        }
+        u32 hlit = 288, hdist = 32;
+        if (btype == 1) {
+            for (u32 i = lane; i < 288; i += 32) lens[i] = (u8)(i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8)));
+            if (lane < 32) lens[288 + lane] = 5;
+            __syncwarp();
+        } else {
+            br.refill();
+            hlit = br.take(5) + 257;
+            hdist = br.take(5) + 1;
+            const u32 hclen = br.take(4) + 4;
+            if (hlit > 286 || hdist > 30) { err |= FASTF_ST_BAD_CODELENS; break; }
+            if (lane < 19) lens[lane] = 0;
+            __syncwarp();
+            for (u32 i = 0; i < hclen; i++) {
+                br.refill();
+                const u32 v = br.take(3);
+                if (lane == 0) lens[G.cl_order[i]] = (u8)v;
+            }
+            __syncwarp();
+            u32 wk;
+            if (fastf_tps_build(FASTF_ALPHA_PLAIN, lens, 19, S.dist_cnt, S.dist_sorted, S.dist, 7, first, start, &wk, lane)) { err |= FASTF_ST_BAD_CODELENS; break; }
+            const u32 n = hlit + hdist;
+            u32 i = 0, prev = 0;
+            while (i < n) {
+                br.refill();
+                const u32 e = fastf_tps_decode16(br, S.dist, 7, S.dist_cnt, S.dist_sorted, FASTF_ALPHA_PLAIN);
+                if ((e & 15u) == 0) { err |= FASTF_ST_BAD_CODELENS; break; }
+                br.drop(e & 15u);
+                const u32 sym = e >> 6;
+                u32 rep, val;
+                if (sym < 16) { rep = 1; val = sym; prev = sym; }
+                else if (sym == 16) { if (i == 0) { err |= FASTF_ST_BAD_CODELENS; break; } rep = 3 + br.take(2); val = prev; }
+                else if (sym == 17) { rep = 3 + br.take(3); val = 0; prev = 0; }
+                else { rep = 11 + br.take(7); val = 0; prev = 0; }
+                if (i + rep > n) { err |= FASTF_ST_BAD_CODELENS; break; }
+                for (u32 k = lane; k < rep; k += 32) lens[i + k] = (u8)val;
+                i += rep;
+            }
+            if (err) break;
+            __syncwarp();
+            if (lens[256] == 0) { err |= FASTF_ST_BAD_CODELENS; break; }
+        }
+        u32 wl, wd;
+        // the distance lengths sit behind the literal/length ones in `lens`; the distance table's storage was the code-length table
+        if (fastf_tps_build(FASTF_ALPHA_LITLEN, lens, hlit, S.lit_cnt, S.lit_sorted, S.lit, FASTF_TPS_LBITS, first, start, &wl, lane)) { err |= FASTF_ST_BAD_CODELENS; break; }
+        if (fastf_tps_build(FASTF_ALPHA_DIST, lens + hlit, hdist, S.dist_cnt, S.dist_sorted, S.dist, FASTF_TPS_DBITS, first, start, &wd, lane)) { err |= FASTF_ST_BAD_CODELENS; break; }
+        const u64 consumed = (u64)br.widx * 32u - br.nbits - br.skip_bits;
+        bitpos = origin + consumed;
+        if (lane == 0) {
+            S.bitpos_lo = (u32)bitpos; S.bitpos_hi = (u32)(bitpos >> 32);
+            S.lit_walk = wl; S.dist_walk = wd;
+            S.last = last; S.pos = opos; S.opos = opos;
+            __threadfence_block();
+            fastf_stv(&S.state, FASTF_TPS_RUN);
+        }
+        __syncwarp();
+        return;
+    }
+    // the BGZF block ended inside this routine (stored-only block, or an error)
+    if (!err && opos != S.isize) err |= FASTF_ST_SIZE_MISMATCH;
+    if (lane == 0) {
+        A.status[b] = err;
+        S.opos = opos;
+        __threadfence_block();
+        fastf_stv(&S.state, FASTF_TPS_NEXT);
+    }
+    __syncwarp();
+}
+
+// LZ77 resolution of up to 32 tokens of one stream by a whole warp.  Returns the number of tokens consumed.
+__device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStream &S, u32 rd, u32 n, u32 lane)
+{
+    u8 *out = A.out + (((u64)S.obase_hi << 32) | S.obase_lo);
+    const u32 opos = S.opos;
+    u32 tok = (lane < n) ? S.ring[(rd + lane) & (FASTF_TPS_RING - 1u)] : FASTF_TOK_END;
+    // an END token closes the batch (nothing follows it until the stream is set up again)
+    const u32 endm = __ballot_sync(FASTF_FULL_MASK, lane < n && (tok >> 30) == 2u);
+    u32 ntok = n;
+    if (endm) ntok = (u32)__ffs((int)endm) - 1u;
+    const bool is_lit = lane < ntok && (tok >> 30) == 0u;
+    const bool is_match = lane < ntok && (tok >> 30) == 1u;
+    const u32 mylen = is_lit ? 1u : (is_match ? (tok & 511u) : 0u);
+    // exclusive prefix sum of the output lengths
+    u32 inc = mylen;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(FASTF_FULL_MASK, inc, o);
+        if ((int)lane >= o) inc += t;
+    }
+    const u32 off = inc - mylen;
+    const u32 total = __shfl_sync(FASTF_FULL_MASK, inc, 31);
+    if (is_lit) out[opos + off] = (u8)tok;
+    u32 mm = __ballot_sync(FASTF_FULL_MASK, is_match);
+    // matches in token order.  Fast path: up to 4 matches that are short (<= 32 bytes), non-overlapping (dist >= len) and read
+    // only bytes written before this batch have their source loads issued back to back, then their stores.  Anything else
+    // (long, overlapping, or reading this batch's own output) goes one at a time behind a __syncwarp.
+    __syncwarp();
+    while (mm) {
+        u32 dpos[4], dlen[4], dbyte[4];
+        int nfast = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            dlen[u] = 0; dpos[u] = 0; dbyte[u] = 0;
+            if (mm) {
+                const u32 m = (u32)__ffs((int)mm) - 1u;
+                const u32 t = __shfl_sync(FASTF_FULL_MASK, tok, (int)m);
+                const u32 o = __shfl_sync(FASTF_FULL_MASK, off, (int)m);
+                const u32 len = t & 511u, dist = (t >> 9) & 0xffffu;
+                const u32 dst = opos + o;
+                const bool fast = len <= 32u && dist >= len && (dst - dist + len) <= opos;
+                if (fast && nfast == u) {
+                    mm &= mm - 1u;
+                    dpos[u] = dst; dlen[u] = len;
+                    if (lane < len) dbyte[u] = out[dst - dist + lane];
+                    nfast++;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (lane < dlen[u]) out[dpos[u] + lane] = (u8)dbyte[u];
+        if (nfast == 0) {
+            // slow path for the first pending match
+            const u32 m = (u32)__ffs((int)mm) - 1u;
+            mm &= mm - 1u;
+            const u32 t = __shfl_sync(FASTF_FULL_MASK, tok, (int)m);
+            const u32 o = __shfl_sync(FASTF_FULL_MASK, off, (int)m);
+            const u32 len = t & 511u, dist = (t >> 9) & 0xffffu;
+            const u32 dst = opos + o;
+            __syncwarp();   // everything stored so far in this batch is ordered before these loads
+            const u8 *src = out + dst - dist;
+            for (u32 k = 0; k < len; k += 32) {
+                const u32 j = k + lane;
+                u32 bb = 0;
+                if (j < len) bb = src[dist >= len ? j : j % dist];
+                if (j < len) out[dst + j] = (u8)bb;
+            }
+            __syncwarp();
+        }
+    }
+    u32 consumed = ntok;
+    u32 new_opos = opos + total;
+    if (endm) {
+        // END: the decoder's verdict plus the size check; the stream goes back to set-up
+        const u32 e = __shfl_sync(FASTF_FULL_MASK, tok, (int)ntok) & 0xffffu;
+        if (lane == 0) A.status[S.blk] = e | ((e == 0 && new_opos != S.isize) ? (u32)FASTF_ST_SIZE_MISMATCH : 0u);
+        consumed = ntok + 1;
+    }
+    __syncwarp();   // the stores of this batch are ordered before the next batch's loads
+    if (lane == 0) {
+        S.opos = new_opos;
+        __threadfence_block();
+        fastf_stv(&S.rd, rd + consumed);
+    }
+    __syncwarp();
+    return consumed;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// decoder side (one thread = one stream)
+// ------------------------------------------------------------------------------------------------------------------
+struct FastfTpsReader {
+    const u32 *words;
+    u32 max_words;
+    u32 widx;      // next word to load into nextw
+    u32 nextw;
+    u64 buf;
+    u32 nbits;
+    __device__ __forceinline__ u32 ldw(u32 i) const { return i < max_words ? __ldg(words + i) : 0u; }
+    __device__ __forceinline__ void init(const u8 *comp, u64 comp_total, u64 bitpos)
+    {
+        words = (const u32 *)comp;
+        const u64 mw = comp_total >> 2;
+        max_words = mw > 0xffffffffull ? 0xffffffffu : (u32)mw;
+        const u32 w0 = (u32)(bitpos >> 5), sh = (u32)(bitpos & 31u);
+        buf = (u64)(ldw(w0) >> sh);
+        nbits = 32u - sh;
+        widx = w0 + 1;
+        nextw = ldw(widx);
+        refill();
+    }
+    __device__ __forceinline__ void refill()
+    {
+        if (nbits <= 32u) {
+            buf |= (u64)nextw << nbits;
+            nbits += 32u;
+            widx++;
+            nextw = ldw(widx);
+        }
+    }
+    __device__ __forceinline__ u32 take(u32 n) { u32 v = (u32)buf & ((1u << n) - 1u); buf >>= n; nbits -= n; return v; }
+    __device__ __forceinline__ void drop(u32 n) { buf >>= n; nbits -= n; }
+    __device__ __forceinline__ u64 bitpos() const { return (u64)widx * 32u - nbits; }   // words [0, widx) are in buf or consumed
+};
+
+// entry of a code longer than the primary table (canonical walk starting at length tbits + 1)
+__device__ __forceinline__ u32 fastf_tps_walk(u64 buf, u32 tbits, u32 walk, const u16 *cnt, const u16 *sorted, u32 alpha)
+{
+    const u32 code15 = __brev((u32)buf) >> 17;   // the next 15 stream bits, first bit most significant
+    u32 first = walk >> 16, index = walk & 0xffffu;
+    for (u32 len = tbits + 1; len < 16; len++) {
+        const u32 c = cnt[len];
+        const u32 v = code15 >> (15u - len);
+        if (v - first < c) return fastf_make16(alpha, sorted[index + (v - first)]) | len;
+        index += c;
+        first = (first + c) << 1;
+    }
+    return FASTF_T16_BAD << 4;
+}
+
+__global__ void __launch_bounds__(FASTF_TPS_THREADS, 1) fastf_bgzf_inflate_tps_kernel(FastfTpsArgs A)
+{
+    FASTF_DYN_SMEM(smem);
+    FastfTpsStream *streams = reinterpret_cast<FastfTpsStream *>(smem);
+    FastfTpsShared &G = *reinterpret_cast<FastfTpsShared *>(smem + sizeof(FastfTpsStream) * FASTF_TPS_STREAMS);
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    // CTA-wide constants and stream control blocks
+    if (threadIdx.x < 32) {
+        G.lenK[lane] = ((u32)FASTF_LEN_BASE[lane] << 8) | FASTF_LEN_EXTRA[lane];
+        G.distK[lane] = ((u32)FASTF_DIST_BASE[lane] << 8) | FASTF_DIST_EXTRA[lane];
+        if (lane < 20) G.cl_order[lane] = FASTF_CL_ORDER[lane];
+    }
+    if (threadIdx.x < FASTF_TPS_STREAMS) {
+        FastfTpsStream &S = streams[threadIdx.x];
+        S.state = FASTF_TPS_NEXT; S.wr = 0; S.rd = 0; S.last = 0; S.pos = 0; S.isize = 0; S.opos = 0; S.blk = 0;
+    }
+    __syncthreads();
+
+    if (warp < FASTF_TPS_DEC_WARPS) {
+        // ---------------- decoder: lane = stream ----------------
+        FastfTpsStream &S = streams[warp * 32 + lane];
+        FastfTpsReader br;
+        bool have = false;
+        u32 wr = 0, rd_cache = 0, pos = 0, isize = 0, last = 0, lit_walk = 0, dist_walk = 0;
+        u64 in_end = 0;
+        for (;;) {
+            if (!have) {
+                const u32 st = fastf_ldv(&S.state);
+                if (st == FASTF_TPS_DONE) break;
+                if (st != FASTF_TPS_RUN) { fastf_spin_pause(); continue; }
+                __threadfence_block();
+                br.init(A.comp, A.comp_total, ((u64)S.bitpos_hi << 32) | S.bitpos_lo);
+                pos = S.pos; isize = S.isize; last = S.last; lit_walk = S.lit_walk; dist_walk = S.dist_walk;
+                in_end = ((u64)S.inend_hi << 32) | S.inend_lo;
+                wr = S.wr;
+                have = true;
+            }
+            if (wr - rd_cache >= FASTF_TPS_RING) {
+                rd_cache = fastf_ldv(&S.rd);
+                if (wr - rd_cache >= FASTF_TPS_RING) { fastf_stv(&S.wr, wr); fastf_spin_pause(); continue; }
+            }
+            // ---- one token ----
+            br.refill();
+            u32 e = S.lit[(u32)br.buf & ((1u << FASTF_TPS_LBITS) - 1u)];
+            if ((e & 15u) == 0) e = fastf_tps_walk(br.buf, FASTF_TPS_LBITS, lit_walk, S.lit_cnt, S.lit_sorted, FASTF_ALPHA_LITLEN);
+            const u32 kind = (e >> 4) & 3u;
+            u32 tok, err = 0;
+            bool end_stream = false, end_block = false;
+            br.drop(e & 15u);
+            if (kind == FASTF_T16_LIT) {
+                tok = e >> 6;
+                if (pos >= isize) { err = FASTF_ST_OUT_OVERFLOW; }
+                pos++;
+            } else if (kind == FASTF_T16_SYM) {
+                const u32 K = G.lenK[e >> 6];
+                const u32 len = (K >> 8) + br.take(K & 255u);
+                br.refill();
+                u32 d = S.dist[(u32)br.buf & ((1u << FASTF_TPS_DBITS) - 1u)];
+                if ((d & 15u) == 0) d = fastf_tps_walk(br.buf, FASTF_TPS_DBITS, dist_walk, S.dist_cnt, S.dist_sorted, FASTF_ALPHA_DIST);
+                if (((d >> 4) & 3u) != FASTF_T16_SYM) { err = FASTF_ST_BAD_SYMBOL; tok = 0; }
+                else {
+                    br.drop(d & 15u);
+                    const u32 K2 = G.distK[d >> 6];
+                    const u32 dist = (K2 >> 8) + br.take(K2 & 255u);
+                    if (dist > pos) err = FASTF_ST_BAD_DISTANCE;
+                    else if (pos + len > isize) err = FASTF_ST_OUT_OVERFLOW;
+                    tok = FASTF_TOK_MATCH | len | (dist << 9);
+                    pos += len;
+                }
+            } else if (kind == FASTF_T16_EOB) {
+                tok = 0;
+                end_block = true;
+                if (last) end_stream = true;
+            } else {
+                tok = 0;
+                err = FASTF_ST_BAD_SYMBOL;
+            }
+            if (err) { end_stream = true; end_block = true; }
+            if (!end_block) {
+                S.ring[wr & (FASTF_TPS_RING - 1u)] = tok;
+                wr++;
+                if ((wr & 7u) == 0) { __threadfence_block(); fastf_stv(&S.wr, wr); }
+                continue;
+            }
+            // ---- end of a deflate block: hand the stream to its service warp ----
+            const u64 bp = br.bitpos();
+            if (end_stream) {
+                if (!err && bp > in_end) err = FASTF_ST_IN_OVERRUN;
+                if (!err && pos != isize) err = FASTF_ST_SIZE_MISMATCH;
+                S.ring[wr & (FASTF_TPS_RING - 1u)] = FASTF_TOK_END | err;
+                wr++;
+            }
+            S.bitpos_lo = (u32)bp; S.bitpos_hi = (u32)(bp >> 32);
+            S.pos = pos;
+            __threadfence_block();
+            fastf_stv(&S.wr, wr);
+            __threadfence_block();
+            fastf_stv(&S.state, end_stream ? (u32)FASTF_TPS_NEXT : (u32)FASTF_TPS_BUILD);
+            have = false;
+        }
+    } else {
+        // ---------------- service: lock-step warp, owns FASTF_TPS_PER_SVC streams ----------------
+        const u32 sw = warp - FASTF_TPS_DEC_WARPS;
+        for (;;) {
+            bool all_done = true, did = false;
+            for (u32 k = 0; k < FASTF_TPS_PER_SVC; k++) {
+                FastfTpsStream &S = streams[sw + k * FASTF_TPS_SVC_WARPS];
+                const u32 st = fastf_ldv(&S.state);
+                if (st == FASTF_TPS_DONE) continue;
+                all_done = false;
+                __threadfence_block();
+                const u32 wr = fastf_ldv(&S.wr), rd = fastf_ldv(&S.rd);
+                const u32 avail = wr - rd;
+                if (avail >= 32u || (avail > 0 && st != FASTF_TPS_RUN)) {
+                    fastf_tps_copy(A, S, rd, avail < 32u ? avail : 32u, lane);
+                    did = true;
+                } else if (avail == 0 && st == FASTF_TPS_NEXT) {
+                    // fetch the next BGZF block for this stream
+                    u32 b = 0;
+                    if (lane == 0) b = atomicAdd(A.next_block, 1u);
+                    b = __shfl_sync(FASTF_FULL_MASK, b, 0);
+                    if (b >= A.nblocks) {
+                        if (lane == 0) fastf_stv(&S.state, FASTF_TPS_DONE);
+                        __syncwarp();
+                    } else {
+                        if (lane == 0) {
+                            const u64 bp = A.in_off[b] * 8ull, be = (A.in_off[b] + A.in_len[b]) * 8ull, ob = A.out_off[b];
+                            S.blk = b; S.isize = A.isize[b]; S.opos = 0; S.pos = 0;
+                            S.bitpos_lo = (u32)bp; S.bitpos_hi = (u32)(bp >> 32);
+                            S.inend_lo = (u32)be; S.inend_hi = (u32)(be >> 32);
+                            S.obase_lo = (u32)ob; S.obase_hi = (u32)(ob >> 32);
+                        }
+                        __syncwarp();
+                        fastf_tps_setup(A, S, G, sw, lane);
+                    }
+                    did = true;
+                } else if (avail == 0 && st == FASTF_TPS_BUILD) {
+                    fastf_tps_setup(A, S, G, sw, lane);
+                    did = true;
+                }
+            }
+            if (all_done) break;
+            if (!did) fastf_spin_pause();
+        }
+    }
+}

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "bgzf_index.h"
 #include "bgzf_inflate.cuh"
+#include "bgzf_inflate_tps.cuh"
 #include "bam_parse.cuh"
 #include "scan_mt_sample.cuh"
 #include "radix_dedup.cuh"
@@ -36,6 +37,8 @@ struct fastf_ctx {
     cudaStream_t compute, copy, mt, infl;
     char err[1024];
     u32 launches;   // kernels launched through this context (bench: gpu_launches)
+    int n_sm;
+    bool tps_attr_set;
     // size-bucketed caches of device / pinned allocations: a job's buffers are recycled by the next job on the same
     // context, so steady-state calls do not pay cudaMalloc / cudaMallocHost (both synchronise the device)
     std::vector<PoolEntry> *dev_pool, *pin_pool;
@@ -200,6 +203,11 @@ extern "C" int fastf_ctx_create(int device, fastf_ctx **out)
         free(ctx);
         return 1;
     }
+#ifdef FASTF_EMU
+    ctx->n_sm = 2;
+#else
+    if (cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->n_sm <= 0) ctx->n_sm = 148;
+#endif
     ctx->dev_pool = new std::vector<PoolEntry>();
     ctx->pin_pool = new std::vector<PoolEntry>();
     *out = ctx;
@@ -362,11 +370,13 @@ __global__ void __launch_bounds__(256) fastf_de_check_kernel(u32 *__restrict__ a
     if (i < n) act_status[i] = (isize[i] != 0 && act_status[i] != isize[i]) ? (u32)FASTF_ST_SIZE_MISMATCH : 0u;
 }
 
-struct DeScratch {   // parameter array of a hardware-engine batch; must stay alive until the batch has run
+struct DeScratch {   // per-launch state of the inflate engines
 #ifndef FASTF_EMU
-    std::vector<CUmemDecompressParams> params;
+    std::vector<CUmemDecompressParams> params;   // parameter array of a hardware-engine batch; must stay alive until the batch has run
 #endif
+    DevBuf counter;                               // work counter of the persistent thread-per-stream kernel
 };
+#define FASTF_INFLATE_TPS 1u   // inflate_lanes value selecting the thread-per-stream kernel
 
 // h_* = host copies of the block index (needed to build the engine's parameter array)
 static int launch_inflate(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_total, const u64 *in_off, const u32 *in_len, const u64 *out_off, const u32 *isize, u32 nblocks, u8 *out,
@@ -414,6 +424,26 @@ static int launch_inflate(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_to
         CKL("de_check");
         return 0;
 #endif
+    }
+    if (lanes == FASTF_INFLATE_TPS) {
+        // persistent CTAs (one per SM): 64 decoder lanes + 8 service warps each; blocks are handed out by a global counter
+        const size_t smem = sizeof(FastfTpsStream) * FASTF_TPS_STREAMS + sizeof(FastfTpsShared);
+#ifndef FASTF_EMU
+        if (!ctx->tps_attr_set) {
+            CK(cudaFuncSetAttribute(fastf_bgzf_inflate_tps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->tps_attr_set = true;
+        }
+#endif
+        TRY(dev_reserve(ctx, de->counter, 64));
+        CK(cudaMemsetAsync(de->counter.p, 0, sizeof(u32), s));
+        FastfTpsArgs A;
+        A.comp = comp; A.comp_total = comp_total; A.in_off = in_off; A.in_len = in_len; A.out_off = out_off; A.isize = isize; A.nblocks = nblocks; A.out = out; A.status = status;
+        A.next_block = de->counter.as<u32>();
+        u32 grid = (nblocks + FASTF_TPS_STREAMS - 1) / FASTF_TPS_STREAMS;
+        if (grid > (u32)ctx->n_sm) grid = (u32)ctx->n_sm;
+        FASTF_LAUNCH(fastf_bgzf_inflate_tps_kernel, grid, FASTF_TPS_THREADS, smem, s, A);
+        CKL("bgzf_inflate_tps");
+        return 0;
     }
     if (lanes == 8) {
         FASTF_LAUNCH(fastf_bgzf_inflate_kernel<8>, (nblocks + 3) / 4, 32, 0, s, comp, comp_total, in_off, in_len, out_off, isize, nblocks, out, status);
@@ -696,7 +726,7 @@ extern "C" void fastf_bam2db_job_free(fastf_bam2db_job *job)
     cudaStreamSynchronize(ctx->mt);
     for (int i = 0; i < 2; i++) {
         ChunkSlot &S = job->slot[i];
-        index_release(ctx, S.idx); dev_release(ctx, S.comp); dev_release(ctx, S.stage); dev_release(ctx, S.infl); pin_release(ctx, S.snap);
+        index_release(ctx, S.idx); dev_release(ctx, S.comp); dev_release(ctx, S.stage); dev_release(ctx, S.infl); dev_release(ctx, S.de.counter); pin_release(ctx, S.snap);
         if (S.ev_copy) cudaEventDestroy(S.ev_copy);
         if (S.ev_infl) cudaEventDestroy(S.ev_infl);
         if (S.ev_gather) cudaEventDestroy(S.ev_gather);
@@ -728,7 +758,7 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
     job->launches0 = ctx->launches;
     {
         const u32 l = p->inflate_lanes & 0xffu;
-        job->lanes = ((l == 8 || l == 16 || l == 32) ? l : 32u) | (p->inflate_lanes & FASTF_INFLATE_HW_ENGINE);
+        job->lanes = ((l == 8 || l == 16 || l == 32 || l == FASTF_INFLATE_TPS) ? l : 32u) | (p->inflate_lanes & FASTF_INFLATE_HW_ENGINE);
     }
     job->chunk_bytes = p->chunk_inflated_bytes ? std::max<u64>(p->chunk_inflated_bytes, 1u << 20) : FASTF_DEFAULT_CHUNK;
     FastfKeyLayout &L = job->L;
@@ -1360,7 +1390,7 @@ struct InflatedFile {
     u64 n_blocks = 0, infl_bytes = 0;
     u32 status = 0;
 };
-static void inflated_release(fastf_ctx *ctx, InflatedFile &F) { dev_release(ctx, F.comp); dev_release(ctx, F.infl); index_release(ctx, F.idx); }
+static void inflated_release(fastf_ctx *ctx, InflatedFile &F) { dev_release(ctx, F.comp); dev_release(ctx, F.infl); dev_release(ctx, F.de.counter); index_release(ctx, F.idx); }
 
 // Inflate a whole BGZF image (host bytes, or device bytes + host index) into F.infl in one launch.
 static int inflate_whole(fastf_ctx *ctx, InflatedFile &F, const void *host_bytes, size_t n, const u8 *dev_bytes, const std::vector<FastfBgzfBlock> *pre, u32 lanes, float *ms, cudaStream_t s)
@@ -1397,7 +1427,7 @@ static int inflate_whole(fastf_ctx *ctx, InflatedFile &F, const void *host_bytes
     if (ms) { CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); CK(cudaEventRecord(a, s)); }
     {
         const u32 l = lanes & 0xffu;
-        lanes = ((l == 8 || l == 16 || l == 32) ? l : 32u) | (lanes & FASTF_INFLATE_HW_ENGINE);
+        lanes = ((l == 8 || l == 16 || l == 32 || l == FASTF_INFLATE_TPS) ? l : 32u) | (lanes & FASTF_INFLATE_HW_ENGINE);
     }
     TRY(launch_inflate(ctx, lanes, comp, comp_total, F.idx.in_off, F.idx.in_len, F.idx.out_off, F.idx.isize, (u32)nb, F.infl.as<u8>(), F.idx.st_infl, s, &F.de, F.idx.h_in_off, F.idx.h_in_len,
                        F.idx.h_out_off, F.idx.h_isize));

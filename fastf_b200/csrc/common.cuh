@@ -43,6 +43,13 @@ enum : u32 {
     FASTF_ST_BAD_HEADER = 1u << 12,      // BAM magic / header does not fit the first chunk
 };
 
+// polite spin while another warp of the CTA makes progress
+#ifdef FASTF_EMU
+__device__ __forceinline__ void fastf_spin_pause() { emu::spin_yield(); }
+#else
+__device__ __forceinline__ void fastf_spin_pause() { __nanosleep(40); }
+#endif
+
 __device__ __forceinline__ u32 fastf_lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ u32 fastf_lanemask_lt() { return (1u << (threadIdx.x & 31u)) - 1u; }
 

@@ -101,11 +101,17 @@ struct State {
     std::map<uint64_t, Rdv> rdv;   // key = warp << 32 | mask
     std::function<void()> body;
     uint64_t shuffle_seed = 0;
+    std::vector<unsigned char> dyn;   // dynamic shared memory of the running CTA
+    uint64_t spin_rounds = 0;
+    bool spun = false;
 };
 inline State g;
 static const size_t STACK_BYTES = 256 * 1024;
 
 inline void yield() { fastf_emu_switch(&g.fibers[g.cur].sp, g.sched_sp); }
+// a thread polling shared memory for another warp: lets the others run; endless polling by everybody is reported
+inline void spin_yield() { g.spun = true; yield(); }
+inline unsigned char *dyn_smem() { return g.dyn.data(); }
 inline void fiber_entry()
 {
     g.body();
@@ -123,8 +129,9 @@ inline void set_tid(int i)
     threadIdx.y = (i / blockDim.x) % blockDim.y;
     threadIdx.z = i / (blockDim.x * blockDim.y);
 }
-template <class F> void launch(dim3 grid, dim3 block, size_t, F &&body)
+template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F &&body)
 {
+    g.dyn.assign(smem_bytes + 16, 0);
     const char *sh = getenv("FASTF_EMU_SHUFFLE");
     g.shuffle_seed = sh ? strtoull(sh, 0, 10) : 0;
     gridDim = grid; blockDim = block;
@@ -159,6 +166,14 @@ template <class F> void launch(dim3 grid, dim3 block, size_t, F &&body)
                 set_tid(i);
                 fastf_emu_switch(&g.sched_sp, g.fibers[i].sp);
             }
+            if (!g.progress && g.spun && g.live > 0) {
+                // only pollers ran: fine as long as it does not go on forever
+                g.spun = false;
+                if (++g.spin_rounds > 200000000ull) { fprintf(stderr, "cuda_emu: LIVELOCK in block %u (threads only poll)\n", bx); abort(); }
+                continue;
+            }
+            g.spun = false;
+            if (g.progress) g.spin_rounds = 0;
             if (!g.progress && g.live > 0) {
                 fprintf(stderr, "cuda_emu: DEADLOCK in block %u (%d live threads blocked; divergent barrier/collective?)\n", bx, g.live);
                 abort();
@@ -210,6 +225,7 @@ inline void __syncthreads() { emu::syncthreads(); }
 inline void __syncwarp(uint32_t mask = 0xffffffffu) { emu::exchange(mask, 0); }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
+inline void __nanosleep(unsigned) {}
 
 template <class T> inline uint64_t emu_bits(T v) { uint64_t b = 0; memcpy(&b, &v, sizeof(T)); return b; }
 template <class T> inline T emu_unbits(uint64_t b) { T v; memcpy(&v, &b, sizeof(T)); return v; }

@@ -3,6 +3,7 @@
 // Without a file it runs adversarial synthetic streams (stored / fixed / dynamic / RLE / huffman-only /
 // empty / 64 KiB / multi-stored).
 #include "../../fastf_b200/csrc/bgzf_inflate.cuh"
+#include "../../fastf_b200/csrc/bgzf_inflate_tps.cuh"
 #include "../../fastf_b200/csrc/bgzf_index.h"
 #include <zlib.h>
 #include <string>
@@ -47,9 +48,19 @@ template <int G> static int run(const std::vector<uint8_t> &file, size_t max_blo
     u32 *comp_words = (u32 *)calloc(padded / 4 + 1, 4);
     memcpy(comp_words, file.data(), file.size());
     std::vector<u8> out(total + 64, 0xAA);
-    u32 grid = (u32)((nb + (32 / G) - 1) / (32 / G));
-    auto kern = fastf_bgzf_inflate_kernel<G>;
-    FASTF_LAUNCH(kern, grid, 32, 0, 0, (const u8 *)comp_words, (u64)padded, in_off.data(), in_len.data(), out_off.data(), isize.data(), (u32)nb, out.data(), status.data());
+    if constexpr (G == 1) {
+        // thread-per-stream kernel: persistent CTAs, blocks from a global counter
+        u32 counter = 0;
+        FastfTpsArgs A;
+        A.comp = (const u8 *)comp_words; A.comp_total = padded; A.in_off = in_off.data(); A.in_len = in_len.data(); A.out_off = out_off.data(); A.isize = isize.data();
+        A.nblocks = (u32)nb; A.out = out.data(); A.status = status.data(); A.next_block = &counter;
+        const size_t smem = sizeof(FastfTpsStream) * FASTF_TPS_STREAMS + sizeof(FastfTpsShared);
+        FASTF_LAUNCH(fastf_bgzf_inflate_tps_kernel, 2, FASTF_TPS_THREADS, smem, 0, A);
+    } else {
+        u32 grid = (u32)((nb + (32 / G) - 1) / (32 / G));
+        auto kern = fastf_bgzf_inflate_kernel<G>;
+        FASTF_LAUNCH(kern, grid, 32, 0, 0, (const u8 *)comp_words, (u64)padded, in_off.data(), in_len.data(), out_off.data(), isize.data(), (u32)nb, out.data(), status.data());
+    }
     int bad = 0;
     for (size_t i = 0; i < nb; i++) {
         std::vector<u8> ref(isize[i] + 1);
@@ -97,8 +108,16 @@ template <int G> static int run_corrupt()
         u32 *cw = (u32 *)calloc(padded / 4 + 1, 4);
         memcpy(cw, f.data(), f.size());
         std::vector<u8> out(isize + 64, 0xAA);
-        auto kern = fastf_bgzf_inflate_kernel<G>;
-        FASTF_LAUNCH(kern, 1, 32, 0, 0, (const u8 *)cw, (u64)padded, &in_off, &in_len, &out_off, &isize, 1u, out.data(), &status);
+        if constexpr (G == 1) {
+            u32 counter = 0;
+            FastfTpsArgs A;
+            A.comp = (const u8 *)cw; A.comp_total = padded; A.in_off = &in_off; A.in_len = &in_len; A.out_off = &out_off; A.isize = &isize;
+            A.nblocks = 1; A.out = out.data(); A.status = &status; A.next_block = &counter;
+            FASTF_LAUNCH(fastf_bgzf_inflate_tps_kernel, 1, FASTF_TPS_THREADS, sizeof(FastfTpsStream) * FASTF_TPS_STREAMS + sizeof(FastfTpsShared), 0, A);
+        } else {
+            auto kern = fastf_bgzf_inflate_kernel<G>;
+            FASTF_LAUNCH(kern, 1, 32, 0, 0, (const u8 *)cw, (u64)padded, &in_off, &in_len, &out_off, &isize, 1u, out.data(), &status);
+        }
         for (size_t k = isize; k < isize + 64; k++) if (out[k] != 0xAA) { printf("FAIL corrupt: wrote past the end (trial %d)\n", t); bad++; break; }
         // either flagged, or (bit flip in a literal) decodes to the right size with different bytes -- CRC would catch that
         if (status == 0xdeadbeef) { printf("FAIL corrupt: no status written\n"); bad++; }
@@ -124,6 +143,7 @@ int main(int argc, char **argv)
         bad += run<32>(file, maxb, argv[1]);
         bad += run<16>(file, maxb, argv[1]);
         bad += run<8>(file, maxb, argv[1]);
+        bad += run<1>(file, maxb, argv[1]);
         return bad ? 1 : 0;
     }
     struct Case { const char *name; int level, strategy; size_t n; int kind; };
@@ -163,7 +183,9 @@ int main(int argc, char **argv)
     bad += run<32>(file, 1000, "synthetic");
     bad += run<16>(file, 1000, "synthetic");
     bad += run<8>(file, 1000, "synthetic");
+    bad += run<1>(file, 1000, "synthetic");      // G == 1: the thread-per-stream kernel
     bad += run_corrupt<32>();
     bad += run_corrupt<8>();
+    bad += run_corrupt<1>();
     return bad ? 1 : 0;
 }

@@ -57,7 +57,7 @@ def _inflate(gpu_ctx, img, lanes):
     return data
 
 
-@pytest.mark.parametrize("lanes", [32, 16, 8])
+@pytest.mark.parametrize("lanes", [32, 16, 8, 1])   # 1 = thread-per-stream kernel
 def test_inflate_adversarial_blocks(gpu_ctx, lanes):
     import bamgen
     rng = np.random.default_rng(3)
@@ -85,6 +85,7 @@ def test_inflate_flags_corrupt_streams(gpu_ctx):
         bad[pos] ^= 0xFF
         img = bytes(bad) + bamgen.EOF_BLOCK
         out = _inflate(gpu_ctx, img, 32)
+        assert (_inflate(gpu_ctx, img, 1) is None) == (out is None)
         want = None
         try:
             want = zlib.decompress(bytes(bad[18:-8]), -15)
@@ -99,7 +100,7 @@ def test_inflate_synthetic_bam_vs_zlib(gpu_ctx, synth, oracle):
     p = synth.params(n_reads=100000, n_cells=500, n_genes=800, seed=21)
     bam, st = synth.bam(p)
     want = oracle.inflate(bam)
-    for lanes in (32, 16, 8):
+    for lanes in (32, 16, 8, 1):
         assert _inflate(gpu_ctx, bam, lanes) == want
 
 
@@ -171,7 +172,7 @@ def test_bam2db_config1_shape(gpu_ctx, oracle, synth, tmp_path):
     assert stats["total"] == 1000000
 
 
-@pytest.mark.parametrize("lanes,chunk,piece", [(32, 1 << 20, 0), (16, 3 << 20, 1000003), (8, 0, 65536), (32, 1 << 20, 777)])
+@pytest.mark.parametrize("lanes,chunk,piece", [(32, 1 << 20, 0), (16, 3 << 20, 1000003), (8, 0, 65536), (32, 1 << 20, 777), (1, 2 << 20, 0), (1, 0, 250000)])
 def test_bam2db_streaming_is_invariant(gpu_ctx, oracle, synth, tmp_path, lanes, chunk, piece):
     """any chunking of the inflated stream and any split of the compressed bytes (also inside BGZF blocks) gives the same result"""
     paths, _ = synth.write_bam_set(str(tmp_path), n_reads=60000, n_cells=300, n_genes=500, seed=9, p_umi_n=0.01, n_molecules=20000)
