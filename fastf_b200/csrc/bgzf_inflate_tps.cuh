@@ -7,7 +7,7 @@
 //   decoder warps  (2 warps = 64 lanes)  lane = one BGZF block ("stream").  Pure scalar Huffman decoding out of that stream's
 //                                        own shared-memory tables; emits 4-byte TOKENS (literal | match(len, dist) | end)
 //                                        into the stream's shared-memory ring.  No global stores, no warp collectives.
-//   service warps  (8 warps, lock step)  own 8 streams each.  (a) LZ77: take up to 32 tokens of one stream, prefix-sum their
+//   service warps  (16 warps, lock step) own 4 streams each.  (a) LZ77: take up to 32 tokens of one stream, prefix-sum their
 //                                        output lengths, store the literals and copy the matches with all 32 lanes
 //                                        (coalesced; source loads of several matches are issued before any is stored so the L2
 //                                        round trips overlap).  (b) stream set-up: fetch the next BGZF block from a global
@@ -23,11 +23,12 @@
 #define FASTF_TPS_LBITS 10
 #define FASTF_TPS_DBITS 7
 #define FASTF_TPS_DEC_WARPS 2
-#define FASTF_TPS_SVC_WARPS 8
+#define FASTF_TPS_SVC_WARPS 16
 #define FASTF_TPS_STREAMS (FASTF_TPS_DEC_WARPS * 32)
 #define FASTF_TPS_THREADS ((FASTF_TPS_DEC_WARPS + FASTF_TPS_SVC_WARPS) * 32)
 #define FASTF_TPS_PER_SVC (FASTF_TPS_STREAMS / FASTF_TPS_SVC_WARPS)
 #define FASTF_TPS_RING 64u
+#define FASTF_TPS_FAR 16             // far matches whose source loads are in flight together
 
 // 16-bit table entry: bits 0-3 code length (0 = longer than the table), bits 4-5 kind, bits 6-15 payload
 #define FASTF_T16_LIT 0u     // payload = literal byte / code-length symbol
@@ -308,52 +309,64 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
     const u32 off = inc - mylen;
     const u32 total = __shfl_sync(FASTF_FULL_MASK, inc, 31);
     if (is_lit) out[opos + off] = (u8)tok;
-    u32 mm = __ballot_sync(FASTF_FULL_MASK, is_match);
-    // matches in token order.  Fast path: up to 4 matches that are short (<= 32 bytes), non-overlapping (dist >= len) and read
-    // only bytes written before this batch have their source loads issued back to back, then their stores.  Anything else
-    // (long, overlapping, or reading this batch's own output) goes one at a time behind a __syncwarp.
+    // Matches.  "Far" ones -- short (<= 32 bytes), non-overlapping (dist >= len) and reading only bytes written before this
+    // batch -- depend on nothing in the batch: the source loads of up to FASTF_TPS_FAR of them are issued back to back (one L2
+    // round trip for all), then stored.  The rest (long, overlapping, or reading this batch's own output) goes afterwards,
+    // one at a time in token order behind a __syncwarp.  A far match never reads what a later-handled one writes, and the
+    // bytes a slow match reads lie before its own position, so handling the far ones first preserves the result.
+    u32 farm, slowm;
+    {
+        const u32 len = tok & 511u, dist = (tok >> 9) & 0xffffu;
+        const bool far = is_match && len <= 32u && off + len <= dist;   // source ends before the batch starts (implies dist >= len)
+        farm = __ballot_sync(FASTF_FULL_MASK, far);
+        slowm = __ballot_sync(FASTF_FULL_MASK, is_match && !far);
+    }
     __syncwarp();
-    while (mm) {
-        u32 dpos[4], dlen[4], dbyte[4];
-        int nfast = 0;
+    while (farm) {
+        u32 dpos[FASTF_TPS_FAR], dlen[FASTF_TPS_FAR], dbyte[FASTF_TPS_FAR];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < FASTF_TPS_FAR; u++) {
             dlen[u] = 0; dpos[u] = 0; dbyte[u] = 0;
-            if (mm) {
-                const u32 m = (u32)__ffs((int)mm) - 1u;
+            if (farm) {
+                const u32 m = (u32)__ffs((int)farm) - 1u;
+                farm &= farm - 1u;
                 const u32 t = __shfl_sync(FASTF_FULL_MASK, tok, (int)m);
                 const u32 o = __shfl_sync(FASTF_FULL_MASK, off, (int)m);
                 const u32 len = t & 511u, dist = (t >> 9) & 0xffffu;
-                const u32 dst = opos + o;
-                const bool fast = len <= 32u && dist >= len && (dst - dist + len) <= opos;
-                if (fast && nfast == u) {
-                    mm &= mm - 1u;
-                    dpos[u] = dst; dlen[u] = len;
-                    if (lane < len) dbyte[u] = out[dst - dist + lane];
-                    nfast++;
-                }
+                dpos[u] = opos + o; dlen[u] = len;
+                if (lane < len) dbyte[u] = out[opos + o - dist + lane];
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++)
+        for (int u = 0; u < FASTF_TPS_FAR; u++)
             if (lane < dlen[u]) out[dpos[u] + lane] = (u8)dbyte[u];
-        if (nfast == 0) {
-            // slow path for the first pending match
-            const u32 m = (u32)__ffs((int)mm) - 1u;
-            mm &= mm - 1u;
-            const u32 t = __shfl_sync(FASTF_FULL_MASK, tok, (int)m);
-            const u32 o = __shfl_sync(FASTF_FULL_MASK, off, (int)m);
-            const u32 len = t & 511u, dist = (t >> 9) & 0xffffu;
-            const u32 dst = opos + o;
-            __syncwarp();   // everything stored so far in this batch is ordered before these loads
-            const u8 *src = out + dst - dist;
+    }
+    while (slowm) {
+        const u32 m = (u32)__ffs((int)slowm) - 1u;
+        slowm &= slowm - 1u;
+        const u32 t = __shfl_sync(FASTF_FULL_MASK, tok, (int)m);
+        const u32 o = __shfl_sync(FASTF_FULL_MASK, off, (int)m);
+        const u32 len = t & 511u, dist = (t >> 9) & 0xffffu;
+        const u32 dst = opos + o;
+        __syncwarp();   // everything stored so far in this batch is ordered before these loads
+        const u8 *src = out + dst - dist;
+        if (dist >= len) {
             for (u32 k = 0; k < len; k += 32) {
                 const u32 j = k + lane;
-                u32 bb = 0;
-                if (j < len) bb = src[dist >= len ? j : j % dist];
-                if (j < len) out[dst + j] = (u8)bb;
+                if (j < len) out[dst + j] = src[j];
             }
-            __syncwarp();
+        } else {
+            // overlapping copy: the pattern src[0..dist) repeats; j % dist by a reciprocal multiply (exact for j < 258)
+            const u32 rcp = (u32)(1048576.0f * __frcp_rn((float)dist)) + 2u;
+            for (u32 k = 0; k < len; k += 32) {
+                const u32 j = k + lane;
+                if (j < len) {
+                    const u32 q = (j * rcp) >> 20;
+                    u32 r = j - q * dist;
+                    if (r >= dist) r += dist;   // q overshoots by at most one
+                    out[dst + j] = src[r];
+                }
+            }
         }
     }
     u32 consumed = ntok;
@@ -536,8 +549,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS, 1) fastf_bgzf_inflate_tps_k
                 const u32 st = fastf_ldv(&S.state);
                 if (st == FASTF_TPS_DONE) continue;
                 all_done = false;
-                __threadfence_block();
-                const u32 wr = fastf_ldv(&S.wr), rd = fastf_ldv(&S.rd);
+                const u32 wr = fastf_ldv(&S.wr), rd = fastf_ldv(&S.rd);   // volatile shared-memory reads stay in program order
                 const u32 avail = wr - rd;
                 if (avail >= 32u || (avail > 0 && st != FASTF_TPS_RUN)) {
                     fastf_tps_copy(A, S, rd, avail < 32u ? avail : 32u, lane);

@@ -761,6 +761,8 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
         job->lanes = ((l == 8 || l == 16 || l == 32 || l == FASTF_INFLATE_TPS) ? l : 32u) | (p->inflate_lanes & FASTF_INFLATE_HW_ENGINE);
     }
     job->chunk_bytes = p->chunk_inflated_bytes ? std::max<u64>(p->chunk_inflated_bytes, 1u << 20) : FASTF_DEFAULT_CHUNK;
+    // the persistent thread-per-stream kernel keeps 64 streams per SM busy: give every launch several blocks per stream
+    if (!p->chunk_inflated_bytes && (p->inflate_lanes & 0xffu) == FASTF_INFLATE_TPS) job->chunk_bytes = 4 * FASTF_DEFAULT_CHUNK;
     FastfKeyLayout &L = job->L;
     L.umi_max_bytes = p->umi_max_bytes ? p->umi_max_bytes : 3;
     if (L.umi_max_bytes > 4) { delete job; return ctx_fail(ctx, "bam2db_begin: umi_max_bytes must be 1..4 (UMIs up to 16 bases)"); }

@@ -313,6 +313,7 @@ inline uint32_t __reduce_min_sync(uint32_t mask, uint32_t v)
     return r;
 }
 
+inline float __frcp_rn(float x) { return 1.0f / x; }
 inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 inline int __popcll(uint64_t v) { return __builtin_popcountll(v); }
 inline int __clz(int v) { return v ? __builtin_clz((uint32_t)v) : 32; }
