@@ -73,6 +73,14 @@ struct FastfTpsShared {
 #define FASTF_DYN_SMEM(ptr) extern __shared__ __align__(16) u8 fastf_dyn_smem_[]; u8 *ptr = fastf_dyn_smem_
 #endif
 
+// Hand-over between warps of the CTA goes through shared memory only.  One thread's shared-memory stores are performed in
+// program order and so are another thread's volatile loads, so publishing "data, then counter" needs no MEMBAR on the hot
+// path -- a real fence would also wait for the decoder's outstanding global prefetch.  The compiler must not reorder, though.
+#ifdef FASTF_EMU
+#define FASTF_SMEM_ORDER() ((void)0)
+#else
+#define FASTF_SMEM_ORDER() __asm__ __volatile__("" ::: "memory")
+#endif
 __device__ __forceinline__ u32 fastf_ldv(const u32 *p) { return *(const volatile u32 *)p; }
 __device__ __forceinline__ void fastf_stv(u32 *p, u32 v) { *(volatile u32 *)p = v; }
 
@@ -291,7 +299,7 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
 {
     u8 *out = A.out + (((u64)S.obase_hi << 32) | S.obase_lo);
     const u32 opos = S.opos;
-    u32 tok = (lane < n) ? S.ring[(rd + lane) & (FASTF_TPS_RING - 1u)] : FASTF_TOK_END;
+    u32 tok = (lane < n) ? fastf_ldv(&S.ring[(rd + lane) & (FASTF_TPS_RING - 1u)]) : FASTF_TOK_END;
     // an END token closes the batch (nothing follows it until the stream is set up again)
     const u32 endm = __ballot_sync(FASTF_FULL_MASK, lane < n && (tok >> 30) == 2u);
     u32 ntok = n;
@@ -380,7 +388,7 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
     __syncwarp();   // the stores of this batch are ordered before the next batch's loads
     if (lane == 0) {
         S.opos = new_opos;
-        __threadfence_block();
+        FASTF_SMEM_ORDER();
         fastf_stv(&S.rd, rd + consumed);
     }
     __syncwarp();
@@ -468,7 +476,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS, 1) fastf_bgzf_inflate_tps_k
             if (!have) {
                 const u32 st = fastf_ldv(&S.state);
                 if (st == FASTF_TPS_DONE) break;
-                if (st != FASTF_TPS_RUN) { fastf_spin_pause(); continue; }
+                if (st != FASTF_TPS_RUN) { fastf_spin_poll(); continue; }
                 __threadfence_block();
                 br.init(A.comp, A.comp_total, ((u64)S.bitpos_hi << 32) | S.bitpos_lo);
                 pos = S.pos; isize = S.isize; last = S.last; lit_walk = S.lit_walk; dist_walk = S.dist_walk;
@@ -478,7 +486,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS, 1) fastf_bgzf_inflate_tps_k
             }
             if (wr - rd_cache >= FASTF_TPS_RING) {
                 rd_cache = fastf_ldv(&S.rd);
-                if (wr - rd_cache >= FASTF_TPS_RING) { fastf_stv(&S.wr, wr); fastf_spin_pause(); continue; }
+                if (wr - rd_cache >= FASTF_TPS_RING) { fastf_stv(&S.wr, wr); fastf_spin_poll(); continue; }
             }
             // ---- one token ----
             br.refill();
@@ -518,9 +526,9 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS, 1) fastf_bgzf_inflate_tps_k
             }
             if (err) { end_stream = true; end_block = true; }
             if (!end_block) {
-                S.ring[wr & (FASTF_TPS_RING - 1u)] = tok;
+                fastf_stv(&S.ring[wr & (FASTF_TPS_RING - 1u)], tok);
                 wr++;
-                if ((wr & 7u) == 0) { __threadfence_block(); fastf_stv(&S.wr, wr); }
+                if ((wr & 7u) == 0) { FASTF_SMEM_ORDER(); fastf_stv(&S.wr, wr); }
                 continue;
             }
             // ---- end of a deflate block: hand the stream to its service warp ----

@@ -43,11 +43,15 @@ enum : u32 {
     FASTF_ST_BAD_HEADER = 1u << 12,      // BAM magic / header does not fit the first chunk
 };
 
-// polite spin while another warp of the CTA makes progress
+// polite spin while another warp of the CTA makes progress.  fastf_spin_pause: the WHOLE warp has nothing to do (sleeps);
+// fastf_spin_poll: only some lanes of a warp wait while others work -- a sleep there would stall the working lanes at the next
+// reconvergence point, so on the GPU it is a no-op (the emulator still has to let the other fibers run).
 #ifdef FASTF_EMU
 __device__ __forceinline__ void fastf_spin_pause() { emu::spin_yield(); }
+__device__ __forceinline__ void fastf_spin_poll() { emu::spin_yield(); }
 #else
-__device__ __forceinline__ void fastf_spin_pause() { __nanosleep(40); }
+__device__ __forceinline__ void fastf_spin_pause() { __nanosleep(64); }
+__device__ __forceinline__ void fastf_spin_poll() {}
 #endif
 
 __device__ __forceinline__ u32 fastf_lane_id() { return threadIdx.x & 31u; }
