@@ -4,10 +4,12 @@
 // ~50 instructions per symbol, and ncu shows it bound by instruction issue (77 % of issue slots, 1 % of DRAM).  This kernel
 // removes the redundancy by splitting the work by role inside one persistent CTA per SM:
 //
-//   decoder warps  (2 warps = 64 lanes)  lane = one BGZF block ("stream").  Pure scalar Huffman decoding out of that stream's
+//   decoder warps  (8 warps x 8 lanes)   lane = one BGZF block ("stream"); only 8 lanes of a decoder warp work, because the
+//                                        divergent paths of a warp execute one after the other (ncu: a 32-lane decoder warp
+//                                        needs ~1300 cycles per round of tokens) while different warps overlap.  Pure scalar Huffman decoding out of that stream's
 //                                        own shared-memory tables; emits 4-byte TOKENS (literal | match(len, dist) | end)
 //                                        into the stream's shared-memory ring.  No global stores, no warp collectives.
-//   service warps  (16 warps, lock step) own 4 streams each.  (a) LZ77: take up to 32 tokens of one stream, prefix-sum their
+//   service warps  (8 warps, lock step)  own 8 streams each.  (a) LZ77: take up to 32 tokens of one stream, prefix-sum their
 //                                        output lengths, store the literals and copy the matches with all 32 lanes
 //                                        (coalesced; source loads of several matches are issued before any is stored so the L2
 //                                        round trips overlap).  (b) stream set-up: fetch the next BGZF block from a global
@@ -22,11 +24,15 @@
 
 #define FASTF_TPS_LBITS 10
 #define FASTF_TPS_DBITS 7
-#define FASTF_TPS_DEC_WARPS 2
-#define FASTF_TPS_SVC_WARPS 16
-#define FASTF_TPS_STREAMS (FASTF_TPS_DEC_WARPS * 32)
-#define FASTF_TPS_THREADS ((FASTF_TPS_DEC_WARPS + FASTF_TPS_SVC_WARPS) * 32)
-#define FASTF_TPS_PER_SVC (FASTF_TPS_STREAMS / FASTF_TPS_SVC_WARPS)
+// kernel shape (template parameters L = decoding lanes per decoder warp, SVC = service warps): 64 streams per CTA,
+// 64 / L decoder warps.  Divergent paths of a warp serialise, so few lanes and many warps decode faster.
+#define FASTF_TPS_STREAMS 64
+#define FASTF_TPS_MAX_SVC 16
+#define FASTF_TPS_THREADS_OF(L, SVC) ((FASTF_TPS_STREAMS / (L) + (SVC)) * 32)
+// defaults (used by the host launch and the emulator test)
+#define FASTF_TPS_LANES 8
+#define FASTF_TPS_SVC_WARPS 8
+#define FASTF_TPS_THREADS FASTF_TPS_THREADS_OF(FASTF_TPS_LANES, FASTF_TPS_SVC_WARPS)
 #define FASTF_TPS_RING 64u
 #define FASTF_TPS_FAR 16             // far matches whose source loads are in flight together
 
@@ -63,8 +69,8 @@ struct FastfTpsStream {
 struct FastfTpsShared {
     u32 lenK[32], distK[32];         // base << 8 | extra bits
     u8 cl_order[20];
-    u8 lens[FASTF_TPS_SVC_WARPS][320];    // code lengths of the block a service warp is setting up
-    u16 scratch[FASTF_TPS_SVC_WARPS][32]; // first[16], start[16] while building
+    u8 lens[FASTF_TPS_MAX_SVC][320];      // code lengths of the block a service warp is setting up
+    u16 scratch[FASTF_TPS_MAX_SVC][32];   // first[16], start[16] while building
 };
 
 #ifdef FASTF_EMU
@@ -432,22 +438,31 @@ struct FastfTpsReader {
     __device__ __forceinline__ u64 bitpos() const { return (u64)widx * 32u - nbits; }   // words [0, widx) are in buf or consumed
 };
 
-// entry of a code longer than the primary table (canonical walk starting at length tbits + 1)
-__device__ __forceinline__ u32 fastf_tps_walk(u64 buf, u32 tbits, u32 walk, const u16 *cnt, const u16 *sorted, u32 alpha)
+// entry of a code longer than the primary table (canonical walk starting at length tbits + 1).  The per-length counts are
+// fetched up front (independent shared-memory loads) so that the walk itself is register arithmetic.
+template <int TBITS>
+__device__ __forceinline__ u32 fastf_tps_walk(u64 buf, u32 walk, const u16 *cnt, const u16 *sorted, u32 alpha)
 {
     const u32 code15 = __brev((u32)buf) >> 17;   // the next 15 stream bits, first bit most significant
+    u32 c[15 - TBITS];
+#pragma unroll
+    for (int k = 0; k < 15 - TBITS; k++) c[k] = cnt[TBITS + 1 + k];
     u32 first = walk >> 16, index = walk & 0xffffu;
-    for (u32 len = tbits + 1; len < 16; len++) {
-        const u32 c = cnt[len];
+    u32 found_len = 0, found_idx = 0;
+#pragma unroll
+    for (int k = 0; k < 15 - TBITS; k++) {
+        const u32 len = TBITS + 1 + k;
         const u32 v = code15 >> (15u - len);
-        if (v - first < c) return fastf_make16(alpha, sorted[index + (v - first)]) | len;
-        index += c;
-        first = (first + c) << 1;
+        if (!found_len && v - first < c[k]) { found_len = len; found_idx = index + (v - first); }
+        index += c[k];
+        first = (first + c[k]) << 1;
     }
-    return FASTF_T16_BAD << 4;
+    if (!found_len) return FASTF_T16_BAD << 4;
+    return fastf_make16(alpha, sorted[found_idx]) | found_len;
 }
 
-__global__ void __launch_bounds__(FASTF_TPS_THREADS, 1) fastf_bgzf_inflate_tps_kernel(FastfTpsArgs A)
+template <int L, int SVC>
+__global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_inflate_tps_kernel(FastfTpsArgs A)
 {
     FASTF_DYN_SMEM(smem);
     FastfTpsStream *streams = reinterpret_cast<FastfTpsStream *>(smem);
@@ -465,9 +480,12 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS, 1) fastf_bgzf_inflate_tps_k
     }
     __syncthreads();
 
-    if (warp < FASTF_TPS_DEC_WARPS) {
+    // The SM's warp arbiter favours higher warp ids; the two decoder warps carry the critical path, so they take the LAST two
+    // warp slots of the CTA and the (mostly polling) service warps the lower ones.
+    if (warp >= (u32)SVC) {
         // ---------------- decoder: lane = stream ----------------
-        FastfTpsStream &S = streams[warp * 32 + lane];
+        if (lane >= (u32)L) return;
+        FastfTpsStream &S = streams[(warp - (u32)SVC) * (u32)L + lane];
         FastfTpsReader br;
         bool have = false;
         u32 wr = 0, rd_cache = 0, pos = 0, isize = 0, last = 0, lit_walk = 0, dist_walk = 0;
@@ -491,7 +509,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS, 1) fastf_bgzf_inflate_tps_k
             // ---- one token ----
             br.refill();
             u32 e = S.lit[(u32)br.buf & ((1u << FASTF_TPS_LBITS) - 1u)];
-            if ((e & 15u) == 0) e = fastf_tps_walk(br.buf, FASTF_TPS_LBITS, lit_walk, S.lit_cnt, S.lit_sorted, FASTF_ALPHA_LITLEN);
+            if ((e & 15u) == 0) e = fastf_tps_walk<FASTF_TPS_LBITS>(br.buf, lit_walk, S.lit_cnt, S.lit_sorted, FASTF_ALPHA_LITLEN);
             const u32 kind = (e >> 4) & 3u;
             u32 tok, err = 0;
             bool end_stream = false, end_block = false;
@@ -505,7 +523,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS, 1) fastf_bgzf_inflate_tps_k
                 const u32 len = (K >> 8) + br.take(K & 255u);
                 br.refill();
                 u32 d = S.dist[(u32)br.buf & ((1u << FASTF_TPS_DBITS) - 1u)];
-                if ((d & 15u) == 0) d = fastf_tps_walk(br.buf, FASTF_TPS_DBITS, dist_walk, S.dist_cnt, S.dist_sorted, FASTF_ALPHA_DIST);
+                if ((d & 15u) == 0) d = fastf_tps_walk<FASTF_TPS_DBITS>(br.buf, dist_walk, S.dist_cnt, S.dist_sorted, FASTF_ALPHA_DIST);
                 if (((d >> 4) & 3u) != FASTF_T16_SYM) { err = FASTF_ST_BAD_SYMBOL; tok = 0; }
                 else {
                     br.drop(d & 15u);
@@ -549,11 +567,11 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS, 1) fastf_bgzf_inflate_tps_k
         }
     } else {
         // ---------------- service: lock-step warp, owns FASTF_TPS_PER_SVC streams ----------------
-        const u32 sw = warp - FASTF_TPS_DEC_WARPS;
+        const u32 sw = warp;
         for (;;) {
             bool all_done = true, did = false;
-            for (u32 k = 0; k < FASTF_TPS_PER_SVC; k++) {
-                FastfTpsStream &S = streams[sw + k * FASTF_TPS_SVC_WARPS];
+            for (u32 k = 0; k < (u32)(FASTF_TPS_STREAMS / SVC); k++) {
+                FastfTpsStream &S = streams[sw + k * (u32)SVC];
                 const u32 st = fastf_ldv(&S.state);
                 if (st == FASTF_TPS_DONE) continue;
                 all_done = false;
@@ -588,7 +606,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS, 1) fastf_bgzf_inflate_tps_k
                 }
             }
             if (all_done) break;
-            if (!did) fastf_spin_pause();
+            if (!did) fastf_spin_pause();   // nothing to copy or set up: leave the issue slots to the decoders
         }
     }
 }

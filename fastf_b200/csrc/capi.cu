@@ -376,7 +376,8 @@ struct DeScratch {   // per-launch state of the inflate engines
 #endif
     DevBuf counter;                               // work counter of the persistent thread-per-stream kernel
 };
-#define FASTF_INFLATE_TPS 1u   // inflate_lanes value selecting the thread-per-stream kernel
+#define FASTF_INFLATE_TPS 1u   // inflate_lanes 1..4 select a shape of the thread-per-stream kernel; 8/16/32 the lock-step kernel
+#define FASTF_INFLATE_DEFAULT 3u   // 0 = default: thread-per-stream, 4 decoding lanes x 16 decoder warps + 16 service warps (fastest measured on B200)
 
 // h_* = host copies of the block index (needed to build the engine's parameter array)
 static int launch_inflate(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_total, const u64 *in_off, const u32 *in_len, const u64 *out_off, const u32 *isize, u32 nblocks, u8 *out,
@@ -425,15 +426,10 @@ static int launch_inflate(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_to
         return 0;
 #endif
     }
-    if (lanes == FASTF_INFLATE_TPS) {
-        // persistent CTAs (one per SM): 64 decoder lanes + 8 service warps each; blocks are handed out by a global counter
+    if (lanes >= 1 && lanes <= 4) {
+        // thread-per-stream kernel: persistent CTAs (one per SM), 64 streams each; blocks are handed out by a global counter.
+        // lanes selects the shape: 1 = 8 lanes x 8 decoder warps + 8 service warps (default), 2 = 4 x 16 + 8, 3 = 4 x 16 + 16, 4 = 16 x 4 + 8
         const size_t smem = sizeof(FastfTpsStream) * FASTF_TPS_STREAMS + sizeof(FastfTpsShared);
-#ifndef FASTF_EMU
-        if (!ctx->tps_attr_set) {
-            CK(cudaFuncSetAttribute(fastf_bgzf_inflate_tps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ctx->tps_attr_set = true;
-        }
-#endif
         TRY(dev_reserve(ctx, de->counter, 64));
         CK(cudaMemsetAsync(de->counter.p, 0, sizeof(u32), s));
         FastfTpsArgs A;
@@ -441,7 +437,14 @@ static int launch_inflate(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_to
         A.next_block = de->counter.as<u32>();
         u32 grid = (nblocks + FASTF_TPS_STREAMS - 1) / FASTF_TPS_STREAMS;
         if (grid > (u32)ctx->n_sm) grid = (u32)ctx->n_sm;
-        FASTF_LAUNCH(fastf_bgzf_inflate_tps_kernel, grid, FASTF_TPS_THREADS, smem, s, A);
+#ifndef FASTF_EMU
+#define FASTF_TPS_ATTR(L, SVC) CK(cudaFuncSetAttribute(fastf_bgzf_inflate_tps_kernel<L, SVC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+        if (!ctx->tps_attr_set) { FASTF_TPS_ATTR(8, 8); FASTF_TPS_ATTR(4, 8); FASTF_TPS_ATTR(4, 16); FASTF_TPS_ATTR(16, 8); ctx->tps_attr_set = true; }
+#endif
+        if (lanes == 1) { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<8, 8>), grid, FASTF_TPS_THREADS_OF(8, 8), smem, s, A); }
+        else if (lanes == 2) { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<4, 8>), grid, FASTF_TPS_THREADS_OF(4, 8), smem, s, A); }
+        else if (lanes == 3) { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<4, 16>), grid, FASTF_TPS_THREADS_OF(4, 16), smem, s, A); }
+        else { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<16, 8>), grid, FASTF_TPS_THREADS_OF(16, 8), smem, s, A); }
         CKL("bgzf_inflate_tps");
         return 0;
     }
@@ -758,11 +761,11 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
     job->launches0 = ctx->launches;
     {
         const u32 l = p->inflate_lanes & 0xffu;
-        job->lanes = ((l == 8 || l == 16 || l == 32 || l == FASTF_INFLATE_TPS) ? l : 32u) | (p->inflate_lanes & FASTF_INFLATE_HW_ENGINE);
+        job->lanes = ((l == 8 || l == 16 || l == 32 || (l >= 1 && l <= 4)) ? l : FASTF_INFLATE_DEFAULT) | (p->inflate_lanes & FASTF_INFLATE_HW_ENGINE);
     }
     job->chunk_bytes = p->chunk_inflated_bytes ? std::max<u64>(p->chunk_inflated_bytes, 1u << 20) : FASTF_DEFAULT_CHUNK;
     // the persistent thread-per-stream kernel keeps 64 streams per SM busy: give every launch several blocks per stream
-    if (!p->chunk_inflated_bytes && (p->inflate_lanes & 0xffu) == FASTF_INFLATE_TPS) job->chunk_bytes = 4 * FASTF_DEFAULT_CHUNK;
+    if (!p->chunk_inflated_bytes && (job->lanes & 0xffu) >= 1 && (job->lanes & 0xffu) <= 4) job->chunk_bytes = 4 * FASTF_DEFAULT_CHUNK;
     FastfKeyLayout &L = job->L;
     L.umi_max_bytes = p->umi_max_bytes ? p->umi_max_bytes : 3;
     if (L.umi_max_bytes > 4) { delete job; return ctx_fail(ctx, "bam2db_begin: umi_max_bytes must be 1..4 (UMIs up to 16 bases)"); }
@@ -1429,7 +1432,7 @@ static int inflate_whole(fastf_ctx *ctx, InflatedFile &F, const void *host_bytes
     if (ms) { CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); CK(cudaEventRecord(a, s)); }
     {
         const u32 l = lanes & 0xffu;
-        lanes = ((l == 8 || l == 16 || l == 32 || l == FASTF_INFLATE_TPS) ? l : 32u) | (lanes & FASTF_INFLATE_HW_ENGINE);
+        lanes = ((l == 8 || l == 16 || l == 32 || (l >= 1 && l <= 4)) ? l : FASTF_INFLATE_DEFAULT) | (lanes & FASTF_INFLATE_HW_ENGINE);
     }
     TRY(launch_inflate(ctx, lanes, comp, comp_total, F.idx.in_off, F.idx.in_len, F.idx.out_off, F.idx.isize, (u32)nb, F.infl.as<u8>(), F.idx.st_infl, s, &F.de, F.idx.h_in_off, F.idx.h_in_len,
                        F.idx.h_out_off, F.idx.h_isize));

@@ -50,7 +50,7 @@ enum : u32 {
 __device__ __forceinline__ void fastf_spin_pause() { emu::spin_yield(); }
 __device__ __forceinline__ void fastf_spin_poll() { emu::spin_yield(); }
 #else
-__device__ __forceinline__ void fastf_spin_pause() { __nanosleep(64); }
+__device__ __forceinline__ void fastf_spin_pause() { __nanosleep(400); }
 __device__ __forceinline__ void fastf_spin_poll() {}
 #endif
 

@@ -77,7 +77,8 @@ typedef struct {
     uint64_t keep_threshold;    /* fastf_keep_threshold(rate_depth) */
     uint32_t umi_max_bytes;     /* 0 = 3 (UMIs up to 12 bases); up to 4 */
     uint32_t want_rows;         /* also return the kept rows in read order (the sqlite `umi` table) */
-    uint32_t inflate_lanes;     /* 0 = default; lanes per BGZF block in the inflate kernel: 32, 16 or 8; | FASTF_INFLATE_HW_ENGINE */
+    uint32_t inflate_lanes;     /* inflate kernel: 0 = default (thread-per-stream), 1..4 = shapes of it, 32/16/8 = lock-step kernel with that many
+                                 * lanes per BGZF block; | FASTF_INFLATE_HW_ENGINE = hardware decompression engine */
     uint64_t chunk_inflated_bytes; /* 0 = default streaming chunk size */
     uint32_t headerless;        /* 1: the fed blocks start at an alignment record (a later shard of a BAM; the BAM header went to another job) */
 } fastf_bam2db_params;

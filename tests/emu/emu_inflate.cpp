@@ -55,7 +55,7 @@ template <int G> static int run(const std::vector<uint8_t> &file, size_t max_blo
         A.comp = (const u8 *)comp_words; A.comp_total = padded; A.in_off = in_off.data(); A.in_len = in_len.data(); A.out_off = out_off.data(); A.isize = isize.data();
         A.nblocks = (u32)nb; A.out = out.data(); A.status = status.data(); A.next_block = &counter;
         const size_t smem = sizeof(FastfTpsStream) * FASTF_TPS_STREAMS + sizeof(FastfTpsShared);
-        FASTF_LAUNCH(fastf_bgzf_inflate_tps_kernel, 2, FASTF_TPS_THREADS, smem, 0, A);
+        FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<FASTF_TPS_LANES, FASTF_TPS_SVC_WARPS>), 2, FASTF_TPS_THREADS, smem, 0, A);
     } else {
         u32 grid = (u32)((nb + (32 / G) - 1) / (32 / G));
         auto kern = fastf_bgzf_inflate_kernel<G>;
@@ -113,7 +113,7 @@ template <int G> static int run_corrupt()
             FastfTpsArgs A;
             A.comp = (const u8 *)cw; A.comp_total = padded; A.in_off = &in_off; A.in_len = &in_len; A.out_off = &out_off; A.isize = &isize;
             A.nblocks = 1; A.out = out.data(); A.status = &status; A.next_block = &counter;
-            FASTF_LAUNCH(fastf_bgzf_inflate_tps_kernel, 1, FASTF_TPS_THREADS, sizeof(FastfTpsStream) * FASTF_TPS_STREAMS + sizeof(FastfTpsShared), 0, A);
+            FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<4, 16>), 1, FASTF_TPS_THREADS_OF(4, 16), sizeof(FastfTpsStream) * FASTF_TPS_STREAMS + sizeof(FastfTpsShared), 0, A);
         } else {
             auto kern = fastf_bgzf_inflate_kernel<G>;
             FASTF_LAUNCH(kern, 1, 32, 0, 0, (const u8 *)cw, (u64)padded, &in_off, &in_len, &out_off, &isize, 1u, out.data(), &status);
