@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--chunk-mb", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="bam2db", choices=["bam2db", "freq"], help="bam2db = BASELINE.json configs[2] (the headline); freq = configs[1] (use --reads 100000000)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -195,6 +196,37 @@ def main():
     workload = f"bam2db synthetic 10x-v3 BAM: {args.reads} reads/GPU, {N_CELLS} cells, {N_GENES} genes, -c {RATE_CELL} -r {RATE_DEPTH} -s {SEED} (BASELINE.json configs[2])"
 
     # ------------------------------------------------------------------ reference arm: the reference's own CPU path
+    if args.impl == "reference" and args.workload == "freq":
+        if rank != 0:
+            return 0
+        import synth_binding
+        S = synth_binding.load()
+        n = min(args.ref_sample_reads, 3_000_000)
+        fq, _ = S.fastq(S.params(n_reads=n, n_cells=20000, seed=DATA_SEED, p_umi_n=0.001), threads)
+        tmp = tempfile.mkdtemp(prefix="fastf_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            open(os.path.join(tmp, "R1.fastq.gz"), "wb").write(fq)
+            os.makedirs(os.path.join(tmp, "o"))
+            ref = os.path.join(ROOT, "oracle", "_ref", "fastF_ref")
+            kind = "reference" if os.path.exists(ref) else "port"
+            cmd = [ref, "freq", "-R", os.path.join(tmp, "R1.fastq.gz"), "-o", os.path.join(tmp, "o"), "-l", "16", "-u", "12"] if kind == "reference" else \
+                  [os.path.join(ROOT, "oracle", "_build", "oracle_cli"), "freq", os.path.join(tmp, "R1.fastq.gz"), "16", "12", os.path.join(tmp, "o", "whitelist.txt")]
+            times = []
+            for i in range(args.warmup + args.steps):
+                t0 = time.time()
+                subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                if i >= args.warmup:
+                    times.append(time.time() - t0)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        ms = 1e3 * sum(times) / len(times)
+        v = n / (ms / 1e3)
+        sample = f"{n}-read synthetic R1 FASTQ per step (whole run of the reference CLI `freq -l 16 -u 12`; wall clock)"
+        print(json.dumps({"impl": "reference", "metric": "freq reads/sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": {"workload": "freq (BASELINE.json configs[1] shape)", "sample": sample},
+                          "cpu_baseline": {"value": v, "unit": "reads/s", "cores": 1, "kind": kind, "sample": sample, "cpu": cpu_model(), "host_cores": threads},
+                          "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
     if args.impl == "reference":
         if rank != 0:
             return 0
@@ -221,6 +253,11 @@ def main():
                           "cpu_baseline": {"value": v, "unit": "reads/s", "cores": 1, "kind": kind, "sample": sample, "cpu": cpu_model(), "host_cores": threads},
                           "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
+
+    if args.workload == "freq":
+        if args.reads == 500_000_000:
+            args.reads = 100_000_000
+        return bench_freq(args)
 
     # ------------------------------------------------------------------ our arm
     import torch
@@ -389,6 +426,108 @@ def main():
         print(json.dumps(line))
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+    return 0
+
+
+def bench_freq(args):
+    """`fastF freq` (BASELINE.json configs[1]): R1 FASTQ, 20k true barcodes + 5 % single-base errors, -l 16 -u 12.  One step = one
+    fastf_freq_gpu call over the whole BGZF image (value: image + index resident in HBM; e2e: pinned host bytes in, histogram out)."""
+    import torch
+    import synth_binding
+    from fastf_b200 import _lib
+    threads = os.cpu_count() or 1
+    ctx = _lib.Context(0)
+    lib = ctx.lib
+    S = synth_binding.load()
+    base_reads = min(args.base_reads, args.reads)
+    p = S.params(n_reads=base_reads, n_cells=20000, seed=DATA_SEED, p_umi_n=0.001)
+    t = time.time()
+    fq, st = S.fastq(p, threads)
+    log(f"[bench] generated {base_reads} FASTQ reads: {st.compressed_bytes / 1e6:.0f} MB BGZF, {st.inflated_bytes / 1e6:.0f} MB text in {time.time() - t:.1f}s")
+    tiles = max(1, -(-args.reads // base_reads))
+    body = fq[:-28]   # without the EOF block
+    img = np.frombuffer(body * tiles + fq[-28:], dtype=np.uint8)
+    n_reads = tiles * base_reads
+    cap = int(st.n_blocks) * tiles + 8
+    io, il, isz = np.zeros(cap, np.uint64), np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+    used = C.c_size_t()
+    nb = lib.fastf_bgzf_index_host(C.c_void_p(img.ctypes.data), img.size, io.ctypes.data_as(_lib.c_u64p), il.ctypes.data_as(_lib.c_u32p), isz.ctypes.data_as(_lib.c_u32p), cap, C.byref(used))
+    assert nb > 0 and used.value == img.size
+    dptr, hptr = C.c_void_p(), C.c_void_p()
+    ctx.check(lib.fastf_device_alloc(ctx.h, img.size + 64, C.byref(dptr)), "device_alloc")
+    ctx.check(lib.fastf_memcpy_h2d(ctx.h, dptr, C.c_void_p(img.ctypes.data), img.size), "h2d")
+    ctx.check(lib.fastf_host_alloc(ctx.h, img.size, C.byref(hptr)), "host_alloc")
+    C.memmove(hptr, img.ctypes.data, img.size)
+    klen = 28
+    lib_stream = torch.cuda.ExternalStream(lib.fastf_compute_stream(ctx.h), device=torch.device("cuda", 0))
+
+    def one(device_resident):
+        res = _lib.FreqResult()
+        if device_resident:
+            ctx.check(lib.fastf_freq_gpu_device(ctx.h, dptr, img.size, io.ctypes.data_as(_lib.c_u64p), il.ctypes.data_as(_lib.c_u32p), isz.ctypes.data_as(_lib.c_u32p), nb, klen, args.lanes, C.byref(res)), "freq_gpu_device")
+        else:
+            ctx.check(lib.fastf_freq_gpu(ctx.h, hptr, img.size, klen, args.lanes, C.byref(res)), "freq_gpu")
+        st_ = {f: getattr(res, f) for f, t_ in _lib.FreqResult._fields_ if t_ in (C.c_uint64, C.c_uint32, C.c_float, C.c_uint8)}
+        lib.fastf_freq_result_free(C.byref(res))
+        return st_
+
+    def timed(device_resident, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            one(device_resident)
+        torch.cuda.synchronize()
+        l0 = ctx.launches
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record(lib_stream)
+        sts = [one(device_resident) for _ in range(steps)]
+        e1.record(lib_stream)
+        ctx.check(lib.fastf_synchronize(ctx.h), "sync")
+        torch.cuda.synchronize()
+        wall = time.time() - t0
+        return wall, sts, ctx.launches - l0, (sampler.stop() if sampler else None), e0.elapsed_time(e1)
+
+    sampler = ClockSampler(0)
+    wall, sts, launches, clocks, dev_ms = timed(True, args.steps, args.warmup, sampler)
+    ms_step = dev_ms / args.steps
+    stq = sts[-1]
+    e2e = None
+    if not args.no_e2e:
+        ew, ests, _, _, _ = timed(False, args.e2e_steps, 1)
+        e_ms = 1e3 * ew / args.e2e_steps
+        e2e = {"value": n_reads / (e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(img.size), "d2h_bytes_per_step": int(ests[-1]["n_keys"] * 16 + ests[-1]["n_exceptions"] * 36),
+               "ms_per_step": e_ms, "steps": args.e2e_steps, "timing": "host wall clock around fastf_freq_gpu (pinned host BGZF bytes in, (key, count, first) + exceptions out)"}
+    peak, peak_src = measured_peak()
+    alg = stq["compressed_bytes"] + stq["inflated_bytes"]
+    ach = alg / (stq["ms_inflate"] * 1e-3) / 1e9
+    line = {"metric": "freq reads/sec (device-timed)", "value": n_reads / (ms_step / 1e3), "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"freq on synthetic R1 FASTQ: {n_reads} reads, 16 bp barcode + 12 bp UMI, 20000 true cells + 5 % error variants, -l 16 -u 12 (BASELINE.json configs[1])",
+                       "tiling": f"{base_reads}-read BGZF segment x {tiles}", "l2": "inputs larger than L2", "ms_per_step_wall": 1e3 * wall / args.steps,
+                       "counters": {k: stq[k] for k in ("n_reads", "n_keys", "n_exceptions", "n_blocks")}},
+            "roofline": {"bound": "hbm", "kernel": "fastf_bgzf_inflate_tps_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg, "ms_per_launch": stq["ms_inflate"]},
+            "stages": {k: round(stq["ms_" + k], 3) for k in ("inflate", "keys", "sort", "rle")}, "gpu_launches": launches, "clocks": clocks, "e2e": e2e}
+    if not args.no_cpu_baseline:
+        tmp = tempfile.mkdtemp(prefix="fastf_freq_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            sub = S.params(n_reads=min(base_reads, 3_000_000), n_cells=20000, seed=DATA_SEED, p_umi_n=0.001)
+            sfq, _ = S.fastq(sub, threads)
+            open(os.path.join(tmp, "R1.fastq.gz"), "wb").write(sfq)
+            os.makedirs(os.path.join(tmp, "o"))
+            ref = os.path.join(ROOT, "oracle", "_ref", "fastF_ref")
+            kind = "reference" if os.path.exists(ref) else "port"
+            cmd = [ref, "freq", "-R", os.path.join(tmp, "R1.fastq.gz"), "-o", os.path.join(tmp, "o"), "-l", "16", "-u", "12"] if kind == "reference" else \
+                  [os.path.join(ROOT, "oracle", "_build", "oracle_cli"), "freq", os.path.join(tmp, "R1.fastq.gz"), "16", "12", os.path.join(tmp, "o", "whitelist.txt")]
+            t0 = time.time()
+            subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            dt = time.time() - t0
+            line["cpu_baseline"] = {"value": sub.n_reads / dt, "unit": "reads/s", "cores": 1, "kind": kind, "cpu": cpu_model(), "host_cores": threads,
+                                    "sample": f"one run of the reference CLI `freq -l 16 -u 12` on {sub.n_reads} reads of the same shape ({dt:.1f}s wall)"}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    print(json.dumps(line))
     return 0
 
 
