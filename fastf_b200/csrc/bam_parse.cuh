@@ -37,13 +37,32 @@ inline void fastf_prefetch_l1(const void *) {}
 // global memory (records larger than the window).  off is an offset into the chunk's inflated buffer.
 struct FastfWinAcc {
     const u8 *W;
-    u64 wbase;
+    u64 wbase;   // multiple of 16
     __device__ __forceinline__ u32 byte(u64 off) const { return W[off - wbase]; }
+    // the aligned 32-bit word that holds byte `off` (off rounded down to a multiple of 4)
+    __device__ __forceinline__ u32 word(u64 off) const { return *reinterpret_cast<const u32 *>(W + ((off - wbase) & ~3ull)); }
 };
 struct FastfGlobAcc {
-    const u8 *infl;
+    const u8 *infl;   // 16-byte aligned base
     __device__ __forceinline__ u32 byte(u64 off) const { return infl[off]; }
+    __device__ __forceinline__ u32 word(u64 off) const { return *reinterpret_cast<const u32 *>(infl + (off & ~3ull)); }
 };
+// position of the first NUL byte in [s, rend), or rend if there is none: four bytes per load
+template <class Acc> __device__ __forceinline__ u64 fastf_find_nul(const Acc &A, u64 s, u64 rend)
+{
+    while (s < rend) {
+        const u64 a = s & ~3ull;
+        u32 w = A.word(s);
+        w |= (1u << (8u * (u32)(s & 3ull))) - 1u;               // bytes in front of s do not count
+        const u32 z = (w - 0x01010101u) & ~w & 0x80808080u;     // 0x80 in every byte that is zero
+        if (z) {
+            const u64 p = a + (((u32)__ffs((int)z) - 1u) >> 3);
+            return p < rend ? p : rend;
+        }
+        s = a + 4;
+    }
+    return rend;
+}
 template <class Acc> __device__ __forceinline__ u32 fastf_acc_u16(const Acc &A, u64 off) { return A.byte(off) | (A.byte(off + 1) << 8); }
 template <class Acc> __device__ __forceinline__ u32 fastf_acc_u32(const Acc &A, u64 off) { return A.byte(off) | (A.byte(off + 1) << 8) | (A.byte(off + 2) << 16) | (A.byte(off + 3) << 24); }
 
@@ -269,8 +288,7 @@ __device__ __forceinline__ u32 fastf_parse_record_lane(const Acc &A, u64 rec, u6
         u64 next;
         u32 vlen = 0;
         if (ty == 'Z' || ty == 'H') {
-            u64 s = v;
-            while (s < rend && A.byte(s) != 0) s++;
+            const u64 s = fastf_find_nul(A, v, rend);
             if (s >= rend) break;   // unterminated: this and every later tag is invisible (htslib)
             vlen = (u32)(s - v);
             next = s + 1;
