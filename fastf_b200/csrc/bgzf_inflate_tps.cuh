@@ -16,22 +16,24 @@
 //                                        counter, parse deflate block headers, copy stored blocks, build the Huffman tables
 //                                        cooperatively -- decoders never run that code, so they never wait for one another.
 //
-// Tables per stream: 10-bit literal/length table and 7-bit distance table with 16-bit entries (code length, kind, symbol),
-// canonical walk for longer codes, length/distance base+extra bits in a CTA-wide table.  64 streams x 3.3 KB + rings fill the
-// SM's shared memory (214 KB): the number of streams in flight per SM, not registers or threads, is what bounds the kernel.
+// Tables per stream: 9-bit literal/length table and 7-bit distance table with 16-bit entries (code length, kind, symbol) and the
+// per-length code counts in shared memory; the canonical walk for longer codes fetches its symbol from a per-stream list in global
+// memory (L2); length/distance base+extra bits sit in a CTA-wide table.  The decoders are latency-bound on their serial chains,
+// so throughput follows the number of streams in flight per SM: 128 streams x 1.6 KB fill the SM's shared memory (214 KB).
 #pragma once
 #include "bgzf_inflate.cuh"
 
-#define FASTF_TPS_LBITS 10
+#define FASTF_TPS_LBITS 9
 #define FASTF_TPS_DBITS 7
-// kernel shape (template parameters L = decoding lanes per decoder warp, SVC = service warps): 64 streams per CTA,
-// 64 / L decoder warps.  Divergent paths of a warp serialise, so few lanes and many warps decode faster.
-#define FASTF_TPS_STREAMS 64
-#define FASTF_TPS_MAX_SVC 16
+// kernel shape (template parameters L = decoding lanes per decoder warp, SVC = service warps): 128 streams per CTA,
+// 128 / L decoder warps.  Divergent paths of a warp serialise, so few lanes and many warps decode faster.
+#define FASTF_TPS_STREAMS 128
+#define FASTF_TPS_MAX_SVC 28
 #define FASTF_TPS_THREADS_OF(L, SVC) ((FASTF_TPS_STREAMS / (L) + (SVC)) * 32)
 // defaults (used by the host launch and the emulator test)
 #define FASTF_TPS_LANES 8
-#define FASTF_TPS_SVC_WARPS 8
+#define FASTF_TPS_SVC_WARPS 16
+#define FASTF_TPS_SORTED_U16 320   // per stream in GLOBAL scratch: symbols sorted by code length (288 lit/len + 32 dist), read only for codes longer than the tables
 #define FASTF_TPS_THREADS FASTF_TPS_THREADS_OF(FASTF_TPS_LANES, FASTF_TPS_SVC_WARPS)
 #define FASTF_TPS_RING 64u
 #define FASTF_TPS_FAR 16             // far matches whose source loads are in flight together
@@ -51,8 +53,6 @@ enum { FASTF_TPS_NEXT = 0, FASTF_TPS_RUN = 1, FASTF_TPS_BUILD = 2, FASTF_TPS_DON
 struct FastfTpsStream {
     u16 lit[1 << FASTF_TPS_LBITS];
     u16 dist[1 << FASTF_TPS_DBITS];
-    u16 lit_sorted[288];
-    u16 dist_sorted[32];
     u16 lit_cnt[16];
     u16 dist_cnt[16];
     u32 ring[FASTF_TPS_RING];
@@ -86,6 +86,13 @@ struct FastfTpsShared {
 #define FASTF_SMEM_ORDER() ((void)0)
 #else
 #define FASTF_SMEM_ORDER() __asm__ __volatile__("" ::: "memory")
+#endif
+// the sorted-symbol lists live in global memory, are rewritten for every deflate block by a service warp and read by another warp
+// of the same CTA: read them through L2 (ld.cg), never through a possibly stale L1 line
+#ifdef FASTF_EMU
+__device__ __forceinline__ u32 fastf_ld_sorted(const u16 *p) { return *p; }
+#else
+__device__ __forceinline__ u32 fastf_ld_sorted(const u16 *p) { return __ldcg(p); }
 #endif
 __device__ __forceinline__ u32 fastf_ldv(const u32 *p) { return *(const volatile u32 *)p; }
 __device__ __forceinline__ void fastf_stv(u32 *p, u32 v) { *(volatile u32 *)p = v; }
@@ -144,7 +151,7 @@ __device__ __forceinline__ u32 fastf_tps_build(u32 alpha, const u8 *lens, u32 n,
     if (bad) return 1;
     const u32 used = first[0];
     for (u32 i = lane; i < used; i += 32) {
-        const u32 sym = sorted[i];
+        const u32 sym = fastf_ld_sorted(sorted + i);
         const u32 l = lens[sym];
         if (l <= tbits) {
             const u32 code = (u32)first[l] + (i - (u32)start[l]);
@@ -169,7 +176,7 @@ __device__ __forceinline__ u32 fastf_tps_decode16(const FastfBitReader<32> &br, 
         code |= bits & 1u;
         bits >>= 1;
         u32 c = cnt[len];
-        if (code < first + c) return fastf_make16(alpha, sorted[index + (code - first)]) | len;
+        if (code < first + c) return fastf_make16(alpha, fastf_ld_sorted(sorted + index + (code - first))) | len;
         index += c;
         first = (first + c) << 1;
         code <<= 1;
@@ -191,12 +198,14 @@ struct FastfTpsArgs {
     u8 *out;
     u32 *status;
     u32 *next_block;   // global work counter (zeroed before the launch)
+    u16 *sorted;       // gridDim.x * FASTF_TPS_STREAMS * FASTF_TPS_SORTED_U16 entries of scratch
 };
 
 // Parse deflate block headers of stream S from its current bit position until a Huffman block is ready for the decoder
 // (state RUN) or the BGZF block is finished / broken (status written, state NEXT).  Stored blocks are copied here.
-__device__ __forceinline__ void fastf_tps_setup(const FastfTpsArgs &A, FastfTpsStream &S, FastfTpsShared &G, u32 sw, u32 lane)
+__device__ __forceinline__ void fastf_tps_setup(const FastfTpsArgs &A, FastfTpsStream &S, u16 *lit_sorted, FastfTpsShared &G, u32 sw, u32 lane)
 {
+    u16 *dist_sorted = lit_sorted + 288;
     const u32 b = S.blk;
     u8 *out = A.out + (((u64)S.obase_hi << 32) | S.obase_lo);
     const u64 in_end = ((u64)S.inend_hi << 32) | S.inend_lo;
@@ -251,12 +260,12 @@ __device__ __forceinline__ void fastf_tps_setup(const FastfTpsArgs &A, FastfTpsS
             }
             __syncwarp();
             u32 wk;
-            if (fastf_tps_build(FASTF_ALPHA_PLAIN, lens, 19, S.dist_cnt, S.dist_sorted, S.dist, 7, first, start, &wk, lane)) { err |= FASTF_ST_BAD_CODELENS; break; }
+            if (fastf_tps_build(FASTF_ALPHA_PLAIN, lens, 19, S.dist_cnt, dist_sorted, S.dist, 7, first, start, &wk, lane)) { err |= FASTF_ST_BAD_CODELENS; break; }
             const u32 n = hlit + hdist;
             u32 i = 0, prev = 0;
             while (i < n) {
                 br.refill();
-                const u32 e = fastf_tps_decode16(br, S.dist, 7, S.dist_cnt, S.dist_sorted, FASTF_ALPHA_PLAIN);
+                const u32 e = fastf_tps_decode16(br, S.dist, 7, S.dist_cnt, dist_sorted, FASTF_ALPHA_PLAIN);
                 if ((e & 15u) == 0) { err |= FASTF_ST_BAD_CODELENS; break; }
                 br.drop(e & 15u);
                 const u32 sym = e >> 6;
@@ -275,8 +284,8 @@ __device__ __forceinline__ void fastf_tps_setup(const FastfTpsArgs &A, FastfTpsS
         }
         u32 wl, wd;
         // the distance lengths sit behind the literal/length ones in `lens`; the distance table's storage was the code-length table
-        if (fastf_tps_build(FASTF_ALPHA_LITLEN, lens, hlit, S.lit_cnt, S.lit_sorted, S.lit, FASTF_TPS_LBITS, first, start, &wl, lane)) { err |= FASTF_ST_BAD_CODELENS; break; }
-        if (fastf_tps_build(FASTF_ALPHA_DIST, lens + hlit, hdist, S.dist_cnt, S.dist_sorted, S.dist, FASTF_TPS_DBITS, first, start, &wd, lane)) { err |= FASTF_ST_BAD_CODELENS; break; }
+        if (fastf_tps_build(FASTF_ALPHA_LITLEN, lens, hlit, S.lit_cnt, lit_sorted, S.lit, FASTF_TPS_LBITS, first, start, &wl, lane)) { err |= FASTF_ST_BAD_CODELENS; break; }
+        if (fastf_tps_build(FASTF_ALPHA_DIST, lens + hlit, hdist, S.dist_cnt, dist_sorted, S.dist, FASTF_TPS_DBITS, first, start, &wd, lane)) { err |= FASTF_ST_BAD_CODELENS; break; }
         const u64 consumed = (u64)br.widx * 32u - br.nbits - br.skip_bits;
         bitpos = origin + consumed;
         if (lane == 0) {
@@ -458,7 +467,7 @@ __device__ __forceinline__ u32 fastf_tps_walk(u64 buf, u32 walk, const u16 *cnt,
         first = (first + c[k]) << 1;
     }
     if (!found_len) return FASTF_T16_BAD << 4;
-    return fastf_make16(alpha, sorted[found_idx]) | found_len;
+    return fastf_make16(alpha, fastf_ld_sorted(sorted + found_idx)) | found_len;
 }
 
 template <int L, int SVC>
@@ -468,6 +477,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
     FastfTpsStream *streams = reinterpret_cast<FastfTpsStream *>(smem);
     FastfTpsShared &G = *reinterpret_cast<FastfTpsShared *>(smem + sizeof(FastfTpsStream) * FASTF_TPS_STREAMS);
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    u16 *sorted_base = A.sorted + (size_t)blockIdx.x * FASTF_TPS_STREAMS * FASTF_TPS_SORTED_U16;
     // CTA-wide constants and stream control blocks
     if (threadIdx.x < 32) {
         G.lenK[lane] = ((u32)FASTF_LEN_BASE[lane] << 8) | FASTF_LEN_EXTRA[lane];
@@ -485,7 +495,9 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
     if (warp >= (u32)SVC) {
         // ---------------- decoder: lane = stream ----------------
         if (lane >= (u32)L) return;
-        FastfTpsStream &S = streams[(warp - (u32)SVC) * (u32)L + lane];
+        const u32 sidx = (warp - (u32)SVC) * (u32)L + lane;
+        FastfTpsStream &S = streams[sidx];
+        const u16 *lit_sorted = sorted_base + (size_t)sidx * FASTF_TPS_SORTED_U16, *dist_sorted = lit_sorted + 288;
         FastfTpsReader br;
         bool have = false;
         u32 wr = 0, rd_cache = 0, pos = 0, isize = 0, last = 0, lit_walk = 0, dist_walk = 0;
@@ -509,7 +521,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
             // ---- one token ----
             br.refill();
             u32 e = S.lit[(u32)br.buf & ((1u << FASTF_TPS_LBITS) - 1u)];
-            if ((e & 15u) == 0) e = fastf_tps_walk<FASTF_TPS_LBITS>(br.buf, lit_walk, S.lit_cnt, S.lit_sorted, FASTF_ALPHA_LITLEN);
+            if ((e & 15u) == 0) e = fastf_tps_walk<FASTF_TPS_LBITS>(br.buf, lit_walk, S.lit_cnt, lit_sorted, FASTF_ALPHA_LITLEN);
             const u32 kind = (e >> 4) & 3u;
             u32 tok, err = 0;
             bool end_stream = false, end_block = false;
@@ -523,7 +535,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
                 const u32 len = (K >> 8) + br.take(K & 255u);
                 br.refill();
                 u32 d = S.dist[(u32)br.buf & ((1u << FASTF_TPS_DBITS) - 1u)];
-                if ((d & 15u) == 0) d = fastf_tps_walk<FASTF_TPS_DBITS>(br.buf, dist_walk, S.dist_cnt, S.dist_sorted, FASTF_ALPHA_DIST);
+                if ((d & 15u) == 0) d = fastf_tps_walk<FASTF_TPS_DBITS>(br.buf, dist_walk, S.dist_cnt, dist_sorted, FASTF_ALPHA_DIST);
                 if (((d >> 4) & 3u) != FASTF_T16_SYM) { err = FASTF_ST_BAD_SYMBOL; tok = 0; }
                 else {
                     br.drop(d & 15u);
@@ -570,8 +582,11 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
         const u32 sw = warp;
         for (;;) {
             bool all_done = true, did = false;
-            for (u32 k = 0; k < (u32)(FASTF_TPS_STREAMS / SVC); k++) {
-                FastfTpsStream &S = streams[sw + k * (u32)SVC];
+            for (u32 k = 0; k < (u32)((FASTF_TPS_STREAMS + SVC - 1) / SVC); k++) {
+                const u32 sidx = sw + k * (u32)SVC;
+                if (sidx >= FASTF_TPS_STREAMS) break;   // SVC need not divide the stream count
+                FastfTpsStream &S = streams[sidx];
+                u16 *ssorted = sorted_base + (size_t)sidx * FASTF_TPS_SORTED_U16;
                 const u32 st = fastf_ldv(&S.state);
                 if (st == FASTF_TPS_DONE) continue;
                 all_done = false;
@@ -597,11 +612,11 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
                             S.obase_lo = (u32)ob; S.obase_hi = (u32)(ob >> 32);
                         }
                         __syncwarp();
-                        fastf_tps_setup(A, S, G, sw, lane);
+                        fastf_tps_setup(A, S, ssorted, G, sw, lane);
                     }
                     did = true;
                 } else if (avail == 0 && st == FASTF_TPS_BUILD) {
-                    fastf_tps_setup(A, S, G, sw, lane);
+                    fastf_tps_setup(A, S, ssorted, G, sw, lane);
                     did = true;
                 }
             }

@@ -375,9 +375,10 @@ struct DeScratch {   // per-launch state of the inflate engines
     std::vector<CUmemDecompressParams> params;   // parameter array of a hardware-engine batch; must stay alive until the batch has run
 #endif
     DevBuf counter;                               // work counter of the persistent thread-per-stream kernel
+    DevBuf sorted;                                // its per-stream sorted-symbol lists (global scratch)
 };
 #define FASTF_INFLATE_TPS 1u   // inflate_lanes 1..4 select a shape of the thread-per-stream kernel; 8/16/32 the lock-step kernel
-#define FASTF_INFLATE_DEFAULT 3u   // 0 = default: thread-per-stream, 4 decoding lanes x 16 decoder warps + 16 service warps (fastest measured on B200)
+#define FASTF_INFLATE_DEFAULT 1u   // 0 = default: thread-per-stream, 128 streams per SM: 8 decoding lanes x 16 decoder warps + 16 service warps
 
 // h_* = host copies of the block index (needed to build the engine's parameter array)
 static int launch_inflate(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_total, const u64 *in_off, const u32 *in_len, const u64 *out_off, const u32 *isize, u32 nblocks, u8 *out,
@@ -428,7 +429,7 @@ static int launch_inflate(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_to
     }
     if (lanes >= 1 && lanes <= 4) {
         // thread-per-stream kernel: persistent CTAs (one per SM), 64 streams each; blocks are handed out by a global counter.
-        // lanes selects the shape: 1 = 8 lanes x 8 decoder warps + 8 service warps (default), 2 = 4 x 16 + 8, 3 = 4 x 16 + 16, 4 = 16 x 4 + 8
+        // lanes selects the shape <decoding lanes per decoder warp, service warps>: 1 = <8, 16> (default), 2 = <16, 24>, 3 = <16, 16>, 4 = <32, 28>
         const size_t smem = sizeof(FastfTpsStream) * FASTF_TPS_STREAMS + sizeof(FastfTpsShared);
         TRY(dev_reserve(ctx, de->counter, 64));
         CK(cudaMemsetAsync(de->counter.p, 0, sizeof(u32), s));
@@ -437,14 +438,16 @@ static int launch_inflate(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_to
         A.next_block = de->counter.as<u32>();
         u32 grid = (nblocks + FASTF_TPS_STREAMS - 1) / FASTF_TPS_STREAMS;
         if (grid > (u32)ctx->n_sm) grid = (u32)ctx->n_sm;
+        TRY(dev_reserve(ctx, de->sorted, (size_t)grid * FASTF_TPS_STREAMS * FASTF_TPS_SORTED_U16 * sizeof(u16)));
+        A.sorted = de->sorted.as<u16>();
 #ifndef FASTF_EMU
 #define FASTF_TPS_ATTR(L, SVC) CK(cudaFuncSetAttribute(fastf_bgzf_inflate_tps_kernel<L, SVC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
-        if (!ctx->tps_attr_set) { FASTF_TPS_ATTR(8, 8); FASTF_TPS_ATTR(4, 8); FASTF_TPS_ATTR(4, 16); FASTF_TPS_ATTR(16, 8); ctx->tps_attr_set = true; }
+        if (!ctx->tps_attr_set) { FASTF_TPS_ATTR(8, 16); FASTF_TPS_ATTR(16, 24); FASTF_TPS_ATTR(16, 16); FASTF_TPS_ATTR(32, 28); ctx->tps_attr_set = true; }
 #endif
-        if (lanes == 1) { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<8, 8>), grid, FASTF_TPS_THREADS_OF(8, 8), smem, s, A); }
-        else if (lanes == 2) { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<4, 8>), grid, FASTF_TPS_THREADS_OF(4, 8), smem, s, A); }
-        else if (lanes == 3) { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<4, 16>), grid, FASTF_TPS_THREADS_OF(4, 16), smem, s, A); }
-        else { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<16, 8>), grid, FASTF_TPS_THREADS_OF(16, 8), smem, s, A); }
+        if (lanes == 1) { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<8, 16>), grid, FASTF_TPS_THREADS_OF(8, 16), smem, s, A); }
+        else if (lanes == 2) { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<16, 24>), grid, FASTF_TPS_THREADS_OF(16, 24), smem, s, A); }
+        else if (lanes == 3) { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<16, 16>), grid, FASTF_TPS_THREADS_OF(16, 16), smem, s, A); }
+        else { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<32, 28>), grid, FASTF_TPS_THREADS_OF(32, 28), smem, s, A); }
         CKL("bgzf_inflate_tps");
         return 0;
     }
@@ -729,7 +732,7 @@ extern "C" void fastf_bam2db_job_free(fastf_bam2db_job *job)
     cudaStreamSynchronize(ctx->mt);
     for (int i = 0; i < 2; i++) {
         ChunkSlot &S = job->slot[i];
-        index_release(ctx, S.idx); dev_release(ctx, S.comp); dev_release(ctx, S.stage); dev_release(ctx, S.infl); dev_release(ctx, S.de.counter); pin_release(ctx, S.snap);
+        index_release(ctx, S.idx); dev_release(ctx, S.comp); dev_release(ctx, S.stage); dev_release(ctx, S.infl); dev_release(ctx, S.de.counter); dev_release(ctx, S.de.sorted); pin_release(ctx, S.snap);
         if (S.ev_copy) cudaEventDestroy(S.ev_copy);
         if (S.ev_infl) cudaEventDestroy(S.ev_infl);
         if (S.ev_gather) cudaEventDestroy(S.ev_gather);
@@ -1395,7 +1398,7 @@ struct InflatedFile {
     u64 n_blocks = 0, infl_bytes = 0;
     u32 status = 0;
 };
-static void inflated_release(fastf_ctx *ctx, InflatedFile &F) { dev_release(ctx, F.comp); dev_release(ctx, F.infl); dev_release(ctx, F.de.counter); index_release(ctx, F.idx); }
+static void inflated_release(fastf_ctx *ctx, InflatedFile &F) { dev_release(ctx, F.comp); dev_release(ctx, F.infl); dev_release(ctx, F.de.counter); dev_release(ctx, F.de.sorted); index_release(ctx, F.idx); }
 
 // Inflate a whole BGZF image (host bytes, or device bytes + host index) into F.infl in one launch.
 static int inflate_whole(fastf_ctx *ctx, InflatedFile &F, const void *host_bytes, size_t n, const u8 *dev_bytes, const std::vector<FastfBgzfBlock> *pre, u32 lanes, float *ms, cudaStream_t s)

@@ -51,7 +51,9 @@ template <int G> static int run(const std::vector<uint8_t> &file, size_t max_blo
     if constexpr (G == 1) {
         // thread-per-stream kernel: persistent CTAs, blocks from a global counter
         u32 counter = 0;
+        std::vector<u16> sorted((size_t)2 * FASTF_TPS_STREAMS * FASTF_TPS_SORTED_U16);
         FastfTpsArgs A;
+        A.sorted = sorted.data();
         A.comp = (const u8 *)comp_words; A.comp_total = padded; A.in_off = in_off.data(); A.in_len = in_len.data(); A.out_off = out_off.data(); A.isize = isize.data();
         A.nblocks = (u32)nb; A.out = out.data(); A.status = status.data(); A.next_block = &counter;
         const size_t smem = sizeof(FastfTpsStream) * FASTF_TPS_STREAMS + sizeof(FastfTpsShared);
@@ -110,10 +112,12 @@ template <int G> static int run_corrupt()
         std::vector<u8> out(isize + 64, 0xAA);
         if constexpr (G == 1) {
             u32 counter = 0;
+            std::vector<u16> sorted((size_t)FASTF_TPS_STREAMS * FASTF_TPS_SORTED_U16);
             FastfTpsArgs A;
+            A.sorted = sorted.data();
             A.comp = (const u8 *)cw; A.comp_total = padded; A.in_off = &in_off; A.in_len = &in_len; A.out_off = &out_off; A.isize = &isize;
             A.nblocks = 1; A.out = out.data(); A.status = &status; A.next_block = &counter;
-            FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<4, 16>), 1, FASTF_TPS_THREADS_OF(4, 16), sizeof(FastfTpsStream) * FASTF_TPS_STREAMS + sizeof(FastfTpsShared), 0, A);
+            FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<16, 8>), 1, FASTF_TPS_THREADS_OF(16, 8), sizeof(FastfTpsStream) * FASTF_TPS_STREAMS + sizeof(FastfTpsShared), 0, A);
         } else {
             auto kern = fastf_bgzf_inflate_kernel<G>;
             FASTF_LAUNCH(kern, 1, 32, 0, 0, (const u8 *)cw, (u64)padded, &in_off, &in_len, &out_off, &isize, 1u, out.data(), &status);
