@@ -76,6 +76,7 @@ _SIGS = {
     "fastf_free": (None, [C.c_void_p]),
     "fastf_inflate_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_float)]),
     "fastf_mt19937_host": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, c_u32p]),
+    "fastf_mt19937_host_from": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, c_u32p]),
     "fastf_mt19937_keepbits_host": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, c_u32p]),
     "fastf_sort_u64_host": (C.c_int, [C.c_void_p, c_u64p, c_u32p, C.c_uint64, C.c_uint32]),
     "fastf_freq_gpu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.POINTER(FreqResult)]),

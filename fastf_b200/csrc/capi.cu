@@ -18,12 +18,14 @@
 #include "bam_parse.cuh"
 #include "scan_mt_sample.cuh"
 #include "radix_dedup.cuh"
+#include "mt_jump.h"
 #include "freq.cuh"
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <thread>
 #include <vector>
 #ifndef FASTF_EMU
 #include <cuda.h>   // driver API: cuMemBatchDecompressAsync (Blackwell hardware decompression engine)
@@ -39,6 +41,8 @@ struct fastf_ctx {
     u32 launches;   // kernels launched through this context (bench: gpu_launches)
     int n_sm;
     bool tps_attr_set;
+    void *mtj_polys;   // device copy of x^(2^k) mod phi, k = 0..44 (uploaded on first use)
+    void *mtj_scratch;
     // size-bucketed caches of device / pinned allocations: a job's buffers are recycled by the next job on the same
     // context, so steady-state calls do not pay cudaMalloc / cudaMallocHost (both synchronise the device)
     std::vector<PoolEntry> *dev_pool, *pin_pool;
@@ -218,6 +222,8 @@ extern "C" void fastf_ctx_destroy(fastf_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    if (ctx->mtj_polys) cudaFree(ctx->mtj_polys);
+    if (ctx->mtj_scratch) cudaFree(ctx->mtj_scratch);
     pools_trim(ctx);
     delete ctx->dev_pool;
     delete ctx->pin_pool;
@@ -700,7 +706,9 @@ struct fastf_bam2db_job {
     std::vector<u8> carry;    // partial BGZF block left over by fastf_bam2db_feed
     // MT19937 keep bits
     DevBuf mt_state, keepbits;
-    u64 mt_pairs_done = 0;
+    u64 mt_pairs_done = 0;     // twist pairs generated since mt_origin
+    u64 mt_origin = 0;         // stream index of bit 0 of keepbits (0 unless the job jumped ahead)
+    bool mt_seeded = false;
     cudaEvent_t ev_mt = nullptr;
     // sampling / sort / count
     bool sampled_done = false;
@@ -798,16 +806,18 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
     rc = rc || cudaEventCreate(&job->ev_first) != cudaSuccess || cudaEventCreate(&job->ev_last) != cudaSuccess;
     if (!rc) rc = cudaMemsetAsync(job->counters.p, 0, 4 * sizeof(u64), ctx->compute) != cudaSuccess;
     job->header_done = p->headerless != 0;
+    if (p->headerless) std::thread([] { fastf_mtj::tables(); }).detach();   // a later shard will jump: build the GF(2) tables while the GPU inflates
     if (rc) { if (!ctx->err[0]) ctx_fail(ctx, "bam2db_begin: resource setup failed"); fastf_bam2db_job_free(job); return 1; }
     *out = job;
     return 0;
 }
 
-// Extend the keep-bit stream so that it covers stream indices [0, n_draws).  Runs on the mt stream.
+// Extend the keep-bit stream so that it covers stream indices [mt_origin, n_draws).  Runs on the mt stream.
 static int mt_extend(fastf_bam2db_job *job, u64 n_draws)
 {
     fastf_ctx *ctx = job->ctx;
-    const u64 pairs = (n_draws + 1247) / 1248;
+    if (n_draws <= job->mt_origin) return 0;
+    const u64 pairs = (n_draws - job->mt_origin + 1247) / 1248;
     if (pairs <= job->mt_pairs_done) return 0;
     const size_t need = (size_t)pairs * 39 * sizeof(u32);
     if (need > job->keepbits.cap) {
@@ -818,11 +828,52 @@ static int mt_extend(fastf_bam2db_job *job, u64 n_draws)
     Timer &tm = job->t_mt[job->mt_launches++ & 1u];   // the launch two extensions back has long finished
     tm.collect(&job->ms_mt);
     tm.start(ctx->mt);
-    FASTF_LAUNCH(fastf_mt19937_kernel, 1, FASTF_MT_THREADS, 0, ctx->mt, job->prm.seed, job->mt_state.as<u32>(), job->mt_pairs_done, pairs - job->mt_pairs_done, job->prm.keep_threshold,
-                 (u32 *)nullptr, job->keepbits.as<u32>());
+    FASTF_LAUNCH(fastf_mt19937_kernel, 1, FASTF_MT_THREADS, 0, ctx->mt, job->prm.seed, job->mt_state.as<u32>(), job->mt_seeded ? 0u : 1u, job->mt_pairs_done, pairs - job->mt_pairs_done,
+                 job->prm.keep_threshold, (u32 *)nullptr, job->keepbits.as<u32>());
     CKL("mt19937");
     tm.stop(ctx->mt);
+    job->mt_seeded = true;
     job->mt_pairs_done = pairs;
+    return 0;
+}
+
+// Leave in `state` (624 words, device) the MT19937 window at stream index `origin`: seed, then apply x^(2^k) mod phi for every
+// set bit k of origin (jump-ahead, mt_jump.h).  Returns 1 when the polynomial tables are unavailable.
+static int mt_state_at(fastf_ctx *ctx, u32 seed, u64 origin, u32 *state, cudaStream_t s)
+{
+    const fastf_mtj::Tables &T = fastf_mtj::tables();
+    if (!T.ok || (origin >> T.pow2.size()) != 0) return 1;
+    if (!ctx->mtj_polys) {
+        std::vector<uint64_t> flat(T.pow2.size() * FASTF_MT_POLY_WORDS);
+        for (size_t k = 0; k < T.pow2.size(); k++) memcpy(flat.data() + k * FASTF_MT_POLY_WORDS, T.pow2[k].data(), FASTF_MT_POLY_WORDS * sizeof(uint64_t));
+        CK(cudaMalloc(&ctx->mtj_polys, flat.size() * sizeof(uint64_t)));
+        CK(cudaMalloc(&ctx->mtj_scratch, (size_t)(FASTF_MT_DEG + 624 + 64) * sizeof(u32)));
+        CK(cudaMemcpy(ctx->mtj_polys, flat.data(), flat.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
+    // seed only (no pairs): leaves the window x_0 .. x_623 in state
+    FASTF_LAUNCH(fastf_mt19937_kernel, 1, FASTF_MT_THREADS, 0, s, seed, state, 1u, (u64)0, (u64)0, (u64)0, (u32 *)nullptr, (u32 *)nullptr);
+    CKL("mt19937_seed");
+    for (u32 k = 0; k < T.pow2.size(); k++) {
+        if (!((origin >> k) & 1ull)) continue;
+        FASTF_LAUNCH(fastf_mt_jump_kernel, 1, FASTF_MTJ_THREADS, 0, s, state, (const u64 *)ctx->mtj_polys + (size_t)k * FASTF_MT_POLY_WORDS, (u32 *)ctx->mtj_scratch);
+        CKL("mt_jump");
+    }
+    return 0;
+}
+
+// Restart the job's keep-bit stream at stream index `origin`; whatever was generated before is dropped.
+static int mt_jump_to(fastf_bam2db_job *job, u64 origin)
+{
+    fastf_ctx *ctx = job->ctx;
+    Timer &tm = job->t_mt[job->mt_launches++ & 1u];
+    tm.collect(&job->ms_mt);
+    tm.start(ctx->mt);
+    const int rc = mt_state_at(ctx, job->prm.seed, origin, job->mt_state.as<u32>(), ctx->mt);
+    tm.stop(ctx->mt);
+    if (rc) return rc;
+    job->mt_seeded = true;
+    job->mt_origin = origin;
+    job->mt_pairs_done = 0;
     return 0;
 }
 
@@ -860,8 +911,8 @@ static int finalize_slot(fastf_bam2db_job *job, u32 si)
     job->n_records = n_records;
     job->n_cand = n_cand;
     S.pending = false;
-    // let the MT19937 stream run ahead on its own stream (single-GPU case: ordinal base 0)
-    TRY(mt_extend(job, job->prm.d0 + n_cand));
+    // let the MT19937 stream run ahead on its own stream (ordinal base 0: a single GPU, or the first shard; later shards jump)
+    if (!job->prm.headerless) TRY(mt_extend(job, job->prm.d0 + n_cand));
     return 0;
 }
 
@@ -1086,6 +1137,13 @@ extern "C" int fastf_bam2db_sample(fastf_bam2db_job *job, uint64_t ordinal_base)
     job->n_sampled = job->n_valid = 0;
     if (n >= 0xffffffffull) return ctx_fail(ctx, "bam2db_sample: %llu CB-valid reads exceed the 2^32-1 limit of one device; shard over more GPUs", (unsigned long long)n);
     if (n) {
+        // a later shard of a multi-GPU job starts deep inside the stream: jump there instead of generating everything in front
+        const char *jm = getenv("FASTF_MT_JUMP_MIN");   // draws worth jumping over (tests set 0 to force the jump path)
+        const u64 jump_min = jm ? strtoull(jm, nullptr, 10) : (1ull << 22);
+        if (first_draw > job->mt_origin + job->mt_pairs_done * 1248ull + jump_min) {
+            CK(cudaStreamSynchronize(ctx->mt));
+            mt_jump_to(job, first_draw);   // on failure (tables unavailable) the sequential extension below still gives the right bits
+        }
         TRY(mt_extend(job, first_draw + n));
         CK(cudaEventRecord(job->ev_mt, ctx->mt));
         CK(cudaStreamWaitEvent(ctx->compute, job->ev_mt, 0));
@@ -1094,7 +1152,7 @@ extern "C" int fastf_bam2db_sample(fastf_bam2db_job *job, uint64_t ordinal_base)
         TRY(dev_reserve(ctx, job->tile_tot, sizeof(u32)));
         CK(cudaMemsetAsync(job->sample_counters.p, 0, 2 * sizeof(u64), ctx->compute));
         job->t_sample.start(ctx->compute);
-        FASTF_LAUNCH(fastf_sample_count_kernel, ntiles, FASTF_SAMPLE_THREADS, 0, ctx->compute, (const u64 *)job->cand.as<u64>(), n, (const u32 *)job->keepbits.as<u32>(), first_draw,
+        FASTF_LAUNCH(fastf_sample_count_kernel, ntiles, FASTF_SAMPLE_THREADS, 0, ctx->compute, (const u64 *)job->cand.as<u64>(), n, (const u32 *)job->keepbits.as<u32>(), first_draw - job->mt_origin,
                      job->tile_valid.as<u32>(), job->sample_counters.as<u64>());
         CKL("sample_count");
         TRY(launch_scan_rows(ctx, job->tile_valid.as<u32>(), ntiles, 1, job->tile_tot.as<u32>(), ctx->compute));
@@ -1103,7 +1161,7 @@ extern "C" int fastf_bam2db_sample(fastf_bam2db_job *job, uint64_t ordinal_base)
         job->n_sampled = job->small_host.as<u64>()[0];
         job->n_valid = job->small_host.as<u64>()[1];
         TRY(dev_reserve(ctx, job->kept, std::max<u64>(job->n_valid, 1) * sizeof(u64)));
-        FASTF_LAUNCH(fastf_sample_scatter_kernel, ntiles, FASTF_SAMPLE_THREADS, 0, ctx->compute, (const u64 *)job->cand.as<u64>(), n, (const u32 *)job->keepbits.as<u32>(), first_draw,
+        FASTF_LAUNCH(fastf_sample_scatter_kernel, ntiles, FASTF_SAMPLE_THREADS, 0, ctx->compute, (const u64 *)job->cand.as<u64>(), n, (const u32 *)job->keepbits.as<u32>(), first_draw - job->mt_origin,
                      (const u32 *)job->tile_valid.as<u32>(), job->kept.as<u64>());
         CKL("sample_scatter");
         job->t_sample.stop(ctx->compute);
@@ -1483,12 +1541,32 @@ static int mt_host_common(fastf_ctx *ctx, uint32_t seed, uint64_t n, uint64_t th
     const size_t out_bytes = out_words ? (size_t)pairs * 1248 * sizeof(u32) : (size_t)pairs * 39 * sizeof(u32);
     if (!rc) rc = dev_reserve(ctx, out, out_bytes);
     if (!rc) {
-        FASTF_LAUNCH(fastf_mt19937_kernel, 1, FASTF_MT_THREADS, 0, ctx->compute, seed, state.as<u32>(), (u64)0, pairs, threshold, out_words ? out.as<u32>() : (u32 *)nullptr,
+        FASTF_LAUNCH(fastf_mt19937_kernel, 1, FASTF_MT_THREADS, 0, ctx->compute, seed, state.as<u32>(), 1u, (u64)0, pairs, threshold, out_words ? out.as<u32>() : (u32 *)nullptr,
                      out_words ? (u32 *)nullptr : out.as<u32>());
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) rc = ctx_fail(ctx, "mt19937 launch failed");
     }
     if (!rc) rc = out_words ? fastf_memcpy_d2h(ctx, out_words, out.p, (size_t)n * sizeof(u32)) : fastf_memcpy_d2h(ctx, out_bits, out.p, (size_t)((n + 31) / 32) * sizeof(u32));
+    dev_release(ctx, state);
+    dev_release(ctx, out);
+    return rc;
+}
+extern "C" int fastf_mt19937_host_from(fastf_ctx *ctx, uint32_t seed, uint64_t first, uint64_t n, uint32_t *out_words)
+{
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return 0;
+    const u64 pairs = (n + 1247) / 1248;
+    DevBuf state, out;
+    int rc = dev_reserve(ctx, state, 624 * sizeof(u32));
+    if (!rc) rc = dev_reserve(ctx, out, (size_t)pairs * 1248 * sizeof(u32));
+    if (!rc) rc = mt_state_at(ctx, seed, first, state.as<u32>(), ctx->compute);
+    if (rc == 1 && !ctx->err[0]) ctx_fail(ctx, "mt19937_host_from: jump tables unavailable");
+    if (!rc) {
+        FASTF_LAUNCH(fastf_mt19937_kernel, 1, FASTF_MT_THREADS, 0, ctx->compute, seed, state.as<u32>(), 0u, (u64)0, pairs, (u64)0, out.as<u32>(), (u32 *)nullptr);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = ctx_fail(ctx, "mt19937 launch failed");
+    }
+    if (!rc) rc = fastf_memcpy_d2h(ctx, out_words, out.p, (size_t)n * sizeof(u32));
     dev_release(ctx, state);
     dev_release(ctx, out);
     return rc;

@@ -77,15 +77,16 @@ __device__ __forceinline__ u32 fastf_mt_temper(u32 y)
 }
 // Produces twist pairs [pair0, pair0 + n_pairs): stream indices [pair0*1248, (pair0+n_pairs)*1248).
 // state (624 words in global memory) carries the generator between launches so the stream can be
-// extended chunk by chunk while the inflate kernel runs on another stream: pair0 == 0 seeds it from
-// `seed`, otherwise it is loaded; it is always stored back.  Exactly one of out_words / out_bits is non-null.
-__global__ void __launch_bounds__(FASTF_MT_THREADS) fastf_mt19937_kernel(u32 seed, u32 *__restrict__ state, u64 pair0, u64 n_pairs, u64 threshold,
+// extended chunk by chunk while the inflate kernel runs on another stream; it is always stored back.  Exactly one of out_words / out_bits is non-null.
+// do_seed != 0: start from init_genrand(seed); otherwise continue from `state` (left by a previous launch or by the jump kernel).
+// pair0 only positions the output (pair p writes words [p*1248, ..) or bit words [p*39, ..)).
+__global__ void __launch_bounds__(FASTF_MT_THREADS) fastf_mt19937_kernel(u32 seed, u32 *__restrict__ state, u32 do_seed, u64 pair0, u64 n_pairs, u64 threshold,
                                                                         u32 *__restrict__ out_words, u32 *__restrict__ out_bits)
 {
     __shared__ u32 st[2][624];
     __shared__ u32 tmp[1248];
     const u32 tid = threadIdx.x;
-    if (pair0 == 0) {
+    if (do_seed) {
         if (tid == 0) {
             u32 x = seed;
             st[0][0] = x;
@@ -125,6 +126,36 @@ __global__ void __launch_bounds__(FASTF_MT_THREADS) fastf_mt19937_kernel(u32 see
         __syncthreads();
     }
     for (u32 i = tid; i < 624; i += FASTF_MT_THREADS) state[i] = st[a][i];
+}
+
+// Jump-ahead (mt_jump.h): state <- g(F) state for one polynomial g (FASTF_MT_POLY_WORDS 64-bit words, bit i = g_i):
+//     new[j] = XOR over set bits i of x_{i+j},   x_0.. = the raw recurrence words generated from the current window.
+// One CTA; scratch holds FASTF_MT_DEG + 624 words.
+#define FASTF_MTJ_THREADS 1024
+__global__ void __launch_bounds__(FASTF_MTJ_THREADS) fastf_mt_jump_kernel(u32 *__restrict__ state, const u64 *__restrict__ poly, u32 *__restrict__ scratch)
+{
+    const u32 tid = threadIdx.x;
+    for (u32 i = tid; i < 624; i += FASTF_MTJ_THREADS) scratch[i] = state[i];
+    __syncthreads();
+    // x_k = x_{k-227} ^ tw(x_{k-624}, x_{k-623}): 227 independent words per step
+    for (u32 base = 624; base < 19937u + 624u; base += 227u) {
+        const u32 k = base + tid;
+        if (tid < 227u && k < 19937u + 624u) scratch[k] = scratch[k - 227] ^ fastf_mt_tw(scratch[k - 624], scratch[k - 623]);
+        __syncthreads();
+    }
+    if (tid < 624u) {
+        u32 acc = 0;
+        for (u32 w = 0; w < 312u; w++) {
+            u64 bits = poly[w];
+            const u32 b0 = w * 64u + tid;
+            while (bits) {
+                const u32 b = (u32)__ffsll((long long)bits) - 1u;
+                bits &= bits - 1ull;
+                acc ^= scratch[b0 + b];
+            }
+        }
+        state[tid] = acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -143,6 +143,9 @@ void fastf_free(void *p);
 /* host-buffer wrappers around single kernels (tests, smoke) */
 int fastf_inflate_host(fastf_ctx *ctx, const void *bgzf_bytes, size_t n, int lanes, void **out, size_t *out_n, float *ms);
 int fastf_mt19937_host(fastf_ctx *ctx, uint32_t seed, uint64_t n, uint32_t *out_words);
+/* the n outputs starting at stream index `first` (GF(2) jump-ahead to `first`, then the normal twist): what a later shard of a
+ * multi-GPU job does instead of generating every draw in front of its own */
+int fastf_mt19937_host_from(fastf_ctx *ctx, uint32_t seed, uint64_t first, uint64_t n, uint32_t *out_words);
 int fastf_mt19937_keepbits_host(fastf_ctx *ctx, uint32_t seed, uint64_t n, uint64_t threshold, uint32_t *out_bits /* ceil(n/32) words */);
 int fastf_sort_u64_host(fastf_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t n, uint32_t key_bits);
 

@@ -318,6 +318,7 @@ inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 inline int __popcll(uint64_t v) { return __builtin_popcountll(v); }
 inline int __clz(int v) { return v ? __builtin_clz((uint32_t)v) : 32; }
 inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 inline uint32_t __brev(uint32_t v)
 {
     v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);

@@ -52,3 +52,19 @@ def test_emu_freq_ragged(emu_lib):
 def test_emu_c_host_cli(emu_lib):
     """the C host (fastf_b200/host: option parsing, list readers, sqlite + gz writers, -u) linked against the emulator build"""
     _run(emu_lib, ["synth4k-c0.5-r0.5-s926", "freq-ragged-l16-u0"], cli=True)
+
+
+def test_emu_mt19937_jump_ahead(emu_lib):
+    """jump-ahead tables (Berlekamp-Massey characteristic polynomial, x^(2^k) mod phi) + the jump kernel against the oracle's stream"""
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from fastf_b200 import _lib\nimport oracle_binding\n"
+        "O = oracle_binding.load(); ctx = _lib.Context(0)\n"
+        "for seed, first, n in ((926, 1, 1500), (926, 624, 1300), (5489, 1234567, 2000)):\n"
+        "    out = np.zeros(n, dtype=np.uint32)\n"
+        "    ctx.check(ctx.lib.fastf_mt19937_host_from(ctx.h, seed, first, n, out.ctypes.data_as(_lib.c_u32p)), 'from')\n"
+        "    assert np.array_equal(out, O.mt_stream(seed, first + n)[first:]), (seed, first)\n"
+    ) % (ROOT, os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FASTF_GPU_LIB=emu_lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]

@@ -26,7 +26,8 @@ def test_sharded_equals_reference(name, world, tmp_path):
     emu = build.build_emu()
     case = [c for c in json.load(open(os.path.join(GOLD, "manifest.json")))["cases"] if c["name"] == name][0]
     d = os.path.join(GOLD, case["dir"])
-    env = dict(os.environ, FASTF_GPU_LIB=emu, OMP_NUM_THREADS="1")
+    # FASTF_MT_JUMP_MIN=0: later ranks reach their first draw by GF(2) jump-ahead even on these tiny inputs
+    env = dict(os.environ, FASTF_GPU_LIB=emu, OMP_NUM_THREADS="1", FASTF_MT_JUMP_MIN="0")
     port = 29600 + (os.getpid() % 300)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "sharded_worker.py"), d, str(tmp_path), str(case["rate_cell"]), str(case["rate_depth"]), str(case["seed"])]
