@@ -212,6 +212,7 @@ extern "C" int fastf_ctx_create(int device, fastf_ctx **out)
 #else
     if (cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->n_sm <= 0) ctx->n_sm = 148;
 #endif
+    std::thread([] { fastf_mtj::tables(); }).detach();   // GF(2) jump tables (0.2 s of host work) while the first job streams
     ctx->dev_pool = new std::vector<PoolEntry>();
     ctx->pin_pool = new std::vector<PoolEntry>();
     *out = ctx;
@@ -705,7 +706,7 @@ struct fastf_bam2db_job {
     bool header_done = false;
     std::vector<u8> carry;    // partial BGZF block left over by fastf_bam2db_feed
     // MT19937 keep bits
-    DevBuf mt_state, keepbits;
+    DevBuf mt_state, keepbits, mt_states, mt_scratch;
     u64 mt_pairs_done = 0;     // twist pairs generated since mt_origin
     u64 mt_origin = 0;         // stream index of bit 0 of keepbits (0 unless the job jumped ahead)
     bool mt_seeded = false;
@@ -752,7 +753,7 @@ extern "C" void fastf_bam2db_job_free(fastf_bam2db_job *job)
     if (job->ev_first) cudaEventDestroy(job->ev_first);
     if (job->ev_last) cudaEventDestroy(job->ev_last);
     dev_release(ctx, job->cells.slots); dev_release(ctx, job->cells.pool); dev_release(ctx, job->genes.slots); dev_release(ctx, job->genes.pool);
-    dev_release(ctx, job->counters); dev_release(ctx, job->hdr_off); dev_release(ctx, job->cand); dev_release(ctx, job->mt_state); dev_release(ctx, job->keepbits);
+    dev_release(ctx, job->counters); dev_release(ctx, job->hdr_off); dev_release(ctx, job->cand); dev_release(ctx, job->mt_state); dev_release(ctx, job->keepbits); dev_release(ctx, job->mt_states); dev_release(ctx, job->mt_scratch);
     dev_release(ctx, job->tile_valid); dev_release(ctx, job->tile_tot); dev_release(ctx, job->sample_counters); dev_release(ctx, job->kept); dev_release(ctx, job->orand);
     pin_release(ctx, job->small_host);
     sort_scratch_release(ctx, job->sortS);
@@ -806,7 +807,7 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
     rc = rc || cudaEventCreate(&job->ev_first) != cudaSuccess || cudaEventCreate(&job->ev_last) != cudaSuccess;
     if (!rc) rc = cudaMemsetAsync(job->counters.p, 0, 4 * sizeof(u64), ctx->compute) != cudaSuccess;
     job->header_done = p->headerless != 0;
-    if (p->headerless) std::thread([] { fastf_mtj::tables(); }).detach();   // a later shard will jump: build the GF(2) tables while the GPU inflates
+
     if (rc) { if (!ctx->err[0]) ctx_fail(ctx, "bam2db_begin: resource setup failed"); fastf_bam2db_job_free(job); return 1; }
     *out = job;
     return 0;
@@ -877,6 +878,44 @@ static int mt_jump_to(fastf_bam2db_job *job, u64 origin)
     return 0;
 }
 
+// Keep bits for stream indices [first, first + n) generated by FASTF_MT_SEGMENTS CTAs at once: every CTA jumps to the start of
+// its own segment, then runs the normal twist.  Used once the number of draws is known (fastf_bam2db_sample); replaces whatever
+// the job had generated speculatively.  Returns 1 when the jump tables are unavailable (caller falls back to one sequential CTA).
+#define FASTF_MT_SEGMENTS 32
+static int mt_generate_parallel(fastf_bam2db_job *job, u64 first, u64 n, cudaStream_t s)
+{
+    fastf_ctx *ctx = job->ctx;
+    const fastf_mtj::Tables &T = fastf_mtj::tables();
+    if (!T.ok) return 1;
+    const u64 pairs = (n + 1247) / 1248;
+    const u32 K = (u32)std::min<u64>(FASTF_MT_SEGMENTS, std::max<u64>(1, pairs / 64));
+    const u64 ppc = (pairs + K - 1) / K;
+    if (((first + (u64)K * ppc * 1248ull) >> T.pow2.size()) != 0) return 1;
+    if (!ctx->mtj_polys) {
+        std::vector<uint64_t> flat(T.pow2.size() * FASTF_MT_POLY_WORDS);
+        for (size_t k = 0; k < T.pow2.size(); k++) memcpy(flat.data() + k * FASTF_MT_POLY_WORDS, T.pow2[k].data(), FASTF_MT_POLY_WORDS * sizeof(uint64_t));
+        CK(cudaMalloc(&ctx->mtj_polys, flat.size() * sizeof(uint64_t)));
+        CK(cudaMalloc(&ctx->mtj_scratch, (size_t)(FASTF_MT_DEG + 624 + 64) * sizeof(u32)));
+        CK(cudaMemcpy(ctx->mtj_polys, flat.data(), flat.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
+    TRY(dev_reserve(ctx, job->mt_states, (size_t)K * 624 * sizeof(u32)));
+    TRY(dev_reserve(ctx, job->mt_scratch, (size_t)K * FASTF_MTJ_SCRATCH * sizeof(u32)));
+    TRY(dev_reserve(ctx, job->keepbits, (size_t)K * ppc * 39 * sizeof(u32)));
+    Timer &tm = job->t_mt[job->mt_launches++ & 1u];
+    tm.collect(&job->ms_mt);
+    tm.start(s);
+    FASTF_LAUNCH(fastf_mt_jump_batch_kernel, K, FASTF_MTJ_THREADS, 0, s, job->prm.seed, (const u64 *)ctx->mtj_polys, (u32)T.pow2.size(), first, ppc * 1248ull, job->mt_states.as<u32>(),
+                 job->mt_scratch.as<u32>());
+    CKL("mt_jump_batch");
+    FASTF_LAUNCH(fastf_mt19937_kernel, K, FASTF_MT_THREADS, 0, s, job->prm.seed, job->mt_states.as<u32>(), 0u, (u64)0, ppc, job->prm.keep_threshold, (u32 *)nullptr, job->keepbits.as<u32>());
+    CKL("mt19937");
+    tm.stop(s);
+    job->mt_seeded = true;
+    job->mt_origin = first;
+    job->mt_pairs_done = (u64)K * ppc;
+    return 0;
+}
+
 // Wait for the slot's counters, size the candidate array, gather the slot's staged candidates.
 static int finalize_slot(fastf_bam2db_job *job, u32 si)
 {
@@ -911,8 +950,7 @@ static int finalize_slot(fastf_bam2db_job *job, u32 si)
     job->n_records = n_records;
     job->n_cand = n_cand;
     S.pending = false;
-    // let the MT19937 stream run ahead on its own stream (ordinal base 0: a single GPU, or the first shard; later shards jump)
-    if (!job->prm.headerless) TRY(mt_extend(job, job->prm.d0 + n_cand));
+
     return 0;
 }
 
@@ -1137,14 +1175,10 @@ extern "C" int fastf_bam2db_sample(fastf_bam2db_job *job, uint64_t ordinal_base)
     job->n_sampled = job->n_valid = 0;
     if (n >= 0xffffffffull) return ctx_fail(ctx, "bam2db_sample: %llu CB-valid reads exceed the 2^32-1 limit of one device; shard over more GPUs", (unsigned long long)n);
     if (n) {
-        // a later shard of a multi-GPU job starts deep inside the stream: jump there instead of generating everything in front
-        const char *jm = getenv("FASTF_MT_JUMP_MIN");   // draws worth jumping over (tests set 0 to force the jump path)
-        const u64 jump_min = jm ? strtoull(jm, nullptr, 10) : (1ull << 22);
-        if (first_draw > job->mt_origin + job->mt_pairs_done * 1248ull + jump_min) {
-            CK(cudaStreamSynchronize(ctx->mt));
-            mt_jump_to(job, first_draw);   // on failure (tables unavailable) the sequential extension below still gives the right bits
-        }
-        TRY(mt_extend(job, first_draw + n));
+        // the number of draws is known now: generate exactly the keep bits [first_draw, first_draw + n) with 32 CTAs that each
+        // jump (GF(2) jump-ahead) to their own segment of the reference's single stream.  Fallback without the jump tables: one
+        // CTA generates the stream sequentially from the seed.
+        if (mt_generate_parallel(job, first_draw, n, ctx->mt)) TRY(mt_extend(job, first_draw + n));
         CK(cudaEventRecord(job->ev_mt, ctx->mt));
         CK(cudaStreamWaitEvent(ctx->compute, job->ev_mt, 0));
         const u32 ntiles = (u32)((n + FASTF_SAMPLE_TILE - 1) / FASTF_SAMPLE_TILE);

@@ -108,8 +108,9 @@ static inline uint64_t spread32(uint32_t v)   // bit i -> bit 2i
 
 static inline const Tables &tables()
 {
-    static Tables T;
-    static std::mutex mu;
+    // heap objects that are never destroyed: a detached warm-up thread may still be in here when the process exits
+    static Tables &T = *new Tables();
+    static std::mutex &mu = *new std::mutex();
     std::lock_guard<std::mutex> lock(mu);
     if (T.ok) return T;
     // 1. characteristic polynomial from 2*19937 (+ slack) bits of the most significant bit of x_t

@@ -86,6 +86,10 @@ __global__ void __launch_bounds__(FASTF_MT_THREADS) fastf_mt19937_kernel(u32 see
     __shared__ u32 st[2][624];
     __shared__ u32 tmp[1248];
     const u32 tid = threadIdx.x;
+    // several CTAs = several independent segments of the stream: CTA b continues from state b (put there by the batched jump
+    // kernel) and writes pairs [pair0 + b*n_pairs, pair0 + (b+1)*n_pairs)
+    state += (size_t)blockIdx.x * 624;
+    pair0 += (u64)blockIdx.x * n_pairs;
     if (do_seed) {
         if (tid == 0) {
             u32 x = seed;
@@ -156,6 +160,50 @@ __global__ void __launch_bounds__(FASTF_MTJ_THREADS) fastf_mt_jump_kernel(u32 *_
         }
         state[tid] = acc;
     }
+}
+
+// Batched jump: CTA b leaves in states[b] the window at stream index origin0 + b * stride (seed, then one polynomial per set bit).
+// scratch: gridDim.x regions of FASTF_MTJ_SCRATCH words.
+#define FASTF_MTJ_SCRATCH (19937 + 624 + 63)
+__global__ void __launch_bounds__(FASTF_MTJ_THREADS) fastf_mt_jump_batch_kernel(u32 seed, const u64 *__restrict__ polys, u32 n_polys, u64 origin0, u64 stride, u32 *__restrict__ states,
+                                                                               u32 *__restrict__ scratch_all)
+{
+    __shared__ u32 win[624];
+    const u32 tid = threadIdx.x;
+    u32 *scratch = scratch_all + (size_t)blockIdx.x * FASTF_MTJ_SCRATCH;
+    const u64 origin = origin0 + (u64)blockIdx.x * stride;
+    if (tid == 0) {
+        u32 x = seed;
+        win[0] = x;
+        for (u32 i = 1; i < 624; i++) { x = 1812433253u * (x ^ (x >> 30)) + i; win[i] = x; }
+    }
+    __syncthreads();
+    for (u32 kbit = 0; kbit < n_polys; kbit++) {
+        if (!((origin >> kbit) & 1ull)) continue;   // uniform across the CTA
+        const u64 *poly = polys + (size_t)kbit * 312u;
+        for (u32 i = tid; i < 624; i += FASTF_MTJ_THREADS) scratch[i] = win[i];
+        __syncthreads();
+        for (u32 base = 624; base < 19937u + 624u; base += 227u) {
+            const u32 k = base + tid;
+            if (tid < 227u && k < 19937u + 624u) scratch[k] = scratch[k - 227] ^ fastf_mt_tw(scratch[k - 624], scratch[k - 623]);
+            __syncthreads();
+        }
+        if (tid < 624u) {
+            u32 acc = 0;
+            for (u32 w = 0; w < 312u; w++) {
+                u64 bits = poly[w];
+                const u32 b0 = w * 64u + tid;
+                while (bits) {
+                    const u32 b = (u32)__ffsll((long long)bits) - 1u;
+                    bits &= bits - 1ull;
+                    acc ^= scratch[b0 + b];
+                }
+            }
+            win[tid] = acc;
+        }
+        __syncthreads();
+    }
+    for (u32 i = tid; i < 624; i += FASTF_MTJ_THREADS) states[(size_t)blockIdx.x * 624 + i] = win[i];
 }
 
 // ------------------------------------------------------------------------------------------------
