@@ -272,7 +272,28 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.Context(local_rank)
     lib = ctx.lib
-    base = make_base(args.base_reads, max(1, threads // max(1, world)))
+    # the synthetic segment is generated once per node (local rank 0, all host threads) and shared through /dev/shm
+    share = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(), f"fastf_bench_base_{os.environ.get('MASTER_PORT', '0')}_{args.base_reads}")
+    if world > 1:
+        if local_rank == 0:
+            base = make_base(args.base_reads, threads)
+            os.makedirs(share, exist_ok=True)
+            with open(os.path.join(share, "base.bam"), "wb") as f:
+                f.write(base["bam"])
+            json.dump({k: base[k] for k in ("reads", "n_blocks", "inflated", "compressed")}, open(os.path.join(share, "meta.json"), "w"))
+            open(os.path.join(share, "barcodes.txt"), "wb").write(base["barcodes"])
+            open(os.path.join(share, "features.txt"), "wb").write(base["features"])
+        dist.barrier()
+        if local_rank != 0:
+            base = json.load(open(os.path.join(share, "meta.json")))
+            base["bam"] = open(os.path.join(share, "base.bam"), "rb").read()
+            base["barcodes"] = open(os.path.join(share, "barcodes.txt"), "rb").read()
+            base["features"] = open(os.path.join(share, "features.txt"), "rb").read()
+        dist.barrier()
+        if local_rank == 0:
+            shutil.rmtree(share, ignore_errors=True)
+    else:
+        base = make_base(args.base_reads, threads)
     tmp = tempfile.mkdtemp(prefix=f"fastf_bench_{rank}_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     try:
         paths, _ = write_inputs(base, tmp)
