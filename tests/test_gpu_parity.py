@@ -190,6 +190,13 @@ def test_bam2db_config1_shape(gpu_ctx, oracle, synth, tmp_path):
     assert stats["total"] == 1000000
 
 
+def test_bam2db_parallel_draw_segments(gpu_ctx, oracle, synth, tmp_path):
+    """enough CB-valid reads (~2.9 M) that the keep bits are generated by all 32 jump-ahead segments at once, and a non-zero D0"""
+    paths, _ = synth.write_bam_set(str(tmp_path), n_reads=3000000, n_cells=3000, n_genes=4000, seed=13, p_umi_n=0.001, p_cb_in_list=0.97, p_cb_not_in_list=0.02)
+    stats, _ = _check_against_oracle(gpu_ctx, oracle, paths, 0.999, 0.37, 20240, chunk_inflated_bytes=256 << 20)
+    assert stats["cb_valid"] > 2_700_000
+
+
 @pytest.mark.parametrize("lanes,chunk,piece", [(32, 1 << 20, 0), (16, 3 << 20, 1000003), (8, 0, 65536), (32, 1 << 20, 777), (1, 2 << 20, 0), (1, 0, 250000)])
 def test_bam2db_streaming_is_invariant(gpu_ctx, oracle, synth, tmp_path, lanes, chunk, piece):
     """any chunking of the inflated stream and any split of the compressed bytes (also inside BGZF blocks) gives the same result"""
