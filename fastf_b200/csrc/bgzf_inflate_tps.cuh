@@ -414,22 +414,26 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
 // decoder side (one thread = one stream)
 // ------------------------------------------------------------------------------------------------------------------
 struct FastfTpsReader {
-    const u32 *words;
+    const u32 *words;   // the 32-bit word of `comp` that holds the first bit handed to init()
+    u64 base_bits;      // its absolute bit offset inside comp (streams may sit anywhere in a buffer of many GB)
     u32 max_words;
-    u32 widx;      // next word to load into nextw
+    u32 widx;           // next word (relative to `words`) to load into nextw
     u32 nextw;
     u64 buf;
     u32 nbits;
     __device__ __forceinline__ u32 ldw(u32 i) const { return i < max_words ? __ldg(words + i) : 0u; }
     __device__ __forceinline__ void init(const u8 *comp, u64 comp_total, u64 bitpos)
     {
-        words = (const u32 *)comp;
-        const u64 mw = comp_total >> 2;
-        max_words = mw > 0xffffffffull ? 0xffffffffu : (u32)mw;
-        const u32 w0 = (u32)(bitpos >> 5), sh = (u32)(bitpos & 31u);
-        buf = (u64)(ldw(w0) >> sh);
+        const u64 w0 = bitpos >> 5;
+        const u32 sh = (u32)(bitpos & 31u);
+        words = (const u32 *)comp + w0;
+        base_bits = w0 << 5;
+        const u64 total_words = comp_total >> 2;
+        const u64 left = total_words > w0 ? total_words - w0 : 0;
+        max_words = left > 0xffffffffull ? 0xffffffffu : (u32)left;
+        buf = (u64)(ldw(0) >> sh);
         nbits = 32u - sh;
-        widx = w0 + 1;
+        widx = 1;
         nextw = ldw(widx);
         refill();
     }
@@ -444,7 +448,7 @@ struct FastfTpsReader {
     }
     __device__ __forceinline__ u32 take(u32 n) { u32 v = (u32)buf & ((1u << n) - 1u); buf >>= n; nbits -= n; return v; }
     __device__ __forceinline__ void drop(u32 n) { buf >>= n; nbits -= n; }
-    __device__ __forceinline__ u64 bitpos() const { return (u64)widx * 32u - nbits; }   // words [0, widx) are in buf or consumed
+    __device__ __forceinline__ u64 bitpos() const { return base_bits + (u64)widx * 32u - nbits; }   // words [0, widx) are in buf or consumed
 };
 
 // entry of a code longer than the primary table (canonical walk starting at length tbits + 1).  The per-length counts are
