@@ -434,10 +434,10 @@ def main():
                            "l2": "inputs larger than L2 (compressed segment >> 126 MB); no explicit flush", "timing": "CUDA events on the library's launching stream around the K timed jobs, barrier + synchronize on both sides; max over ranks",
                            "ms_per_step_wall": ms_step_wall, "ms_per_job_library_clock": ms_job_dev, "counters": {k: st.get(k) for k in ("total", "cb_valid", "sampled", "valid", "nnz", "n_blocks", "n_chunks", "exchanged_keys")},
                            "parallelism": ("single GPU" if world == 1 else f"{world} ranks: contiguous BGZF block shards, all-gather of counts, NCCL all-to-all of locally deduplicated keys by cell hash, gather of COO")},
-                "roofline": {"bound": "hbm", "kernel": "hardware decompression engine" if args.engine == "hw" else ("fastf_bgzf_inflate_tps_kernel<8,16>" if args.lanes == 0 else "inflate (--lanes %d)" % args.lanes),
+                "roofline": {"bound": "hbm", "kernel": "hardware decompression engine" if args.engine == "hw" else ("fastf_bgzf_inflate_tps_kernel<16,24>" if args.lanes == 0 else "inflate (--lanes %d)" % args.lanes),
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on a full 2 GiB chunk (ncu --set full, profiles/r01_v5_ncu_inflate_tps128.txt)
-                             "traffic": 11.379e9 if (args.engine == "sm" and args.lanes == 0 and chunk == 0) else None, "traffic_source": "profiles/r01_v5_ncu_inflate_tps128.txt (9.193 GB read + 2.186 GB written per 2 GiB-chunk launch)",
+                             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on a full 2 GiB chunk (ncu --set full, profiles/r01_v7_ncu_inflate_tps.txt)
+                             "traffic": 11.396e9 if (args.engine == "sm" and args.lanes == 0 and chunk == 0) else None, "traffic_source": "profiles/r01_v7_ncu_inflate_tps.txt (9.202 GB read + 2.194 GB written per 2 GiB-chunk launch)",
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_launch, "ms_per_launch": infl_ms_launch},
                 "stages": stages, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "inflate_engine": args.engine, "hw_decompress_engine": hw_extra}
         if not args.no_cpu_baseline:

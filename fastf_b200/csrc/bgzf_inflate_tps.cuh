@@ -4,39 +4,66 @@
 // ~50 instructions per symbol, and ncu shows it bound by instruction issue (77 % of issue slots, 1 % of DRAM).  This kernel
 // removes the redundancy by splitting the work by role inside one persistent CTA per SM:
 //
-//   decoder warps  (8 warps x 8 lanes)   lane = one BGZF block ("stream"); only 8 lanes of a decoder warp work, because the
-//                                        divergent paths of a warp execute one after the other (ncu: a 32-lane decoder warp
-//                                        needs ~1300 cycles per round of tokens) while different warps overlap.  Pure scalar Huffman decoding out of that stream's
-//                                        own shared-memory tables; emits 4-byte TOKENS (literal | match(len, dist) | end)
-//                                        into the stream's shared-memory ring.  No global stores, no warp collectives.
-//   service warps  (8 warps, lock step)  own 8 streams each.  (a) LZ77: take up to 32 tokens of one stream, prefix-sum their
-//                                        output lengths, store the literals and copy the matches with all 32 lanes
-//                                        (coalesced; source loads of several matches are issued before any is stored so the L2
-//                                        round trips overlap).  (b) stream set-up: fetch the next BGZF block from a global
-//                                        counter, parse deflate block headers, copy stored blocks, build the Huffman tables
-//                                        cooperatively -- decoders never run that code, so they never wait for one another.
+//   decoder warps  (8 warps x 16 lanes)  lane = one BGZF block ("stream").  Pure scalar Huffman decoding out of that stream's
+//                                        own shared-memory tables; emits 4-byte TOKENS (up to three literals | match(len, dist)
+//                                        | end) into the stream's shared-memory ring.  No global stores, no warp collectives.
+//                                        One ROUND of a lane = up to two literal tokens plus the match that ends the literal
+//                                        run: the divergent paths of a warp execute one after the other and some lane always
+//                                        needs each of them, so every lane walks through both (ncu: 14.4 M rounds per 2 GiB
+//                                        against 26 M with one token per round).
+//   service warps  (24 warps, lock step) own 5-6 streams each; one poll pass looks at all of them (lane k reads the k-th
+//                                        stream's control block, a ballot picks the streams with work).  (a) LZ77: take up to
+//                                        32 tokens of one stream, prefix-sum their output lengths, store the literals and copy
+//                                        the matches with all 32 lanes (the source loads of several matches are issued before
+//                                        any is stored so the L2 round trips overlap).  (b) stream set-up: fetch the next BGZF
+//                                        block from a global counter, parse deflate block headers, copy stored blocks, build
+//                                        the Huffman tables cooperatively -- decoders never run that code.
 //
 // Tables per stream: 9-bit literal/length table and 7-bit distance table with 16-bit entries (code length, kind, symbol) and the
 // per-length code counts in shared memory; the canonical walk for longer codes fetches its symbol from a per-stream list in global
-// memory (L2); length/distance base+extra bits sit in a CTA-wide table.  The decoders are latency-bound on their serial chains,
-// so throughput follows the number of streams in flight per SM: 128 streams x 1.6 KB fill the SM's shared memory (214 KB).
+// memory (L2); length/distance base+extra bits sit in a CTA-wide table.  128 streams x 1.6 KB fill the SM's shared memory.
+// What bounds it (profiles/README.md): every warp is a serial dependency chain issuing one instruction per ~9 cycles, so both
+// sides are latency-bound -- decoders at ~6.5 warp-instructions per symbol, service warps on the L2/DRAM round trips of match
+// sources (19 k streams x 32 KiB windows do not fit the 126 MB L2: 46 % hit rate).  More streams per SM made it slower
+// (8-bit tables, 160/192 streams: -10..-25 %), as did more loads in flight per service warp at the cost of registers.
 #pragma once
 #include "bgzf_inflate.cuh"
 
+#ifndef FASTF_TPS_LBITS
 #define FASTF_TPS_LBITS 9
+#endif
+#ifndef FASTF_TPS_DBITS
 #define FASTF_TPS_DBITS 7
+#endif
 // kernel shape (template parameters L = decoding lanes per decoder warp, SVC = service warps): 128 streams per CTA,
 // 128 / L decoder warps.  Divergent paths of a warp serialise, so few lanes and many warps decode faster.
+#ifndef FASTF_TPS_STREAMS
 #define FASTF_TPS_STREAMS 128
+#endif
+#ifndef FASTF_TPS_MAX_SVC
 #define FASTF_TPS_MAX_SVC 28
+#endif
 #define FASTF_TPS_THREADS_OF(L, SVC) ((FASTF_TPS_STREAMS / (L) + (SVC)) * 32)
 // defaults (used by the host launch and the emulator test)
-#define FASTF_TPS_LANES 8
-#define FASTF_TPS_SVC_WARPS 16
+#define FASTF_TPS_LANES 16
+#define FASTF_TPS_SVC_WARPS 24
 #define FASTF_TPS_SORTED_U16 320   // per stream in GLOBAL scratch: symbols sorted by code length (288 lit/len + 32 dist), read only for codes longer than the tables
 #define FASTF_TPS_THREADS FASTF_TPS_THREADS_OF(FASTF_TPS_LANES, FASTF_TPS_SVC_WARPS)
+#ifndef FASTF_TPS_RING
 #define FASTF_TPS_RING 64u
-#define FASTF_TPS_FAR 16             // far matches whose source loads are in flight together
+#endif
+#ifndef FASTF_TPS_TRIPLES
+#define FASTF_TPS_TRIPLES 2           // literal tokens (three literals each) a decoder round may produce in front of a match
+#endif
+#ifndef FASTF_TPS_BATCH_MIN
+#define FASTF_TPS_BATCH_MIN 32u       // tokens that make a stream worth a visit of its service warp
+#endif
+#ifndef FASTF_TPS_PREFETCH2
+#define FASTF_TPS_PREFETCH2 0
+#endif
+#ifndef FASTF_TPS_FAR
+#define FASTF_TPS_FAR 4              // far matches whose source loads are in flight together
+#endif
 
 // 16-bit table entry: bits 0-3 code length (0 = longer than the table), bits 4-5 kind, bits 6-15 payload
 #define FASTF_T16_LIT 0u     // payload = literal byte / code-length symbol
@@ -44,7 +71,7 @@
 #define FASTF_T16_EOB 2u
 #define FASTF_T16_BAD 3u
 // tokens
-#define FASTF_TOK_LIT 0u
+#define FASTF_TOK_LIT 0u             // bits 0-23 up to three literal bytes (first in bits 0-7), bits 24-25 their number
 #define FASTF_TOK_MATCH (1u << 30)   // bits 0-8 length, bits 9-24 distance
 #define FASTF_TOK_END (2u << 30)     // bits 0-15 status bits of the decoder
 // stream states
@@ -92,7 +119,14 @@ struct FastfTpsShared {
 #ifdef FASTF_EMU
 __device__ __forceinline__ u32 fastf_ld_sorted(const u16 *p) { return *p; }
 #else
+#ifndef FASTF_TPS_SORTED_L1
+#define FASTF_TPS_SORTED_L1 0
+#endif
+#if FASTF_TPS_SORTED_L1
+__device__ __forceinline__ u32 fastf_ld_sorted(const u16 *p) { return *p; }
+#else
 __device__ __forceinline__ u32 fastf_ld_sorted(const u16 *p) { return __ldcg(p); }
+#endif
 #endif
 __device__ __forceinline__ u32 fastf_ldv(const u32 *p) { return *(const volatile u32 *)p; }
 __device__ __forceinline__ void fastf_stv(u32 *p, u32 v) { *(volatile u32 *)p = v; }
@@ -321,7 +355,7 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
     if (endm) ntok = (u32)__ffs((int)endm) - 1u;
     const bool is_lit = lane < ntok && (tok >> 30) == 0u;
     const bool is_match = lane < ntok && (tok >> 30) == 1u;
-    const u32 mylen = is_lit ? 1u : (is_match ? (tok & 511u) : 0u);
+    const u32 mylen = is_lit ? ((tok >> 24) & 3u) : (is_match ? (tok & 511u) : 0u);
     // exclusive prefix sum of the output lengths
     u32 inc = mylen;
 #pragma unroll
@@ -331,12 +365,17 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
     }
     const u32 off = inc - mylen;
     const u32 total = __shfl_sync(FASTF_FULL_MASK, inc, 31);
-    if (is_lit) out[opos + off] = (u8)tok;
+    if (is_lit) {
+        out[opos + off] = (u8)tok;
+        if (mylen > 1u) out[opos + off + 1u] = (u8)(tok >> 8);
+        if (mylen > 2u) out[opos + off + 2u] = (u8)(tok >> 16);
+    }
     // Matches.  "Far" ones -- short (<= 32 bytes), non-overlapping (dist >= len) and reading only bytes written before this
     // batch -- depend on nothing in the batch: the source loads of up to FASTF_TPS_FAR of them are issued back to back (one L2
     // round trip for all), then stored.  The rest (long, overlapping, or reading this batch's own output) goes afterwards,
     // one at a time in token order behind a __syncwarp.  A far match never reads what a later-handled one writes, and the
     // bytes a slow match reads lie before its own position, so handling the far ones first preserves the result.
+    // (Synthetic 10x BAM: a batch of 32 tokens holds ~10 matches of 12 bytes on average, 9 % longer than 32, 14 % closer than 200.)
     u32 farm, slowm;
     {
         const u32 len = tok & 511u, dist = (tok >> 9) & 0xffffu;
@@ -417,9 +456,9 @@ struct FastfTpsReader {
     const u32 *words;   // the 32-bit word of `comp` that holds the first bit handed to init()
     u64 base_bits;      // its absolute bit offset inside comp (streams may sit anywhere in a buffer of many GB)
     u32 max_words;
-    u32 widx;           // next word (relative to `words`) to load into nextw
-    u32 nextw;
-    u64 buf;
+    u32 widx;           // words [0, widx) (relative to `words`) are in buf or consumed; nextw = word widx, nextw2 = word widx + 1
+    u32 nextw, nextw2;  // two words of prefetch: a second refill right behind the first (length + distance of a match) must not
+    u64 buf;            // wait for a load that was only just issued
     u32 nbits;
     __device__ __forceinline__ u32 ldw(u32 i) const { return i < max_words ? __ldg(words + i) : 0u; }
     __device__ __forceinline__ void init(const u8 *comp, u64 comp_total, u64 bitpos)
@@ -434,7 +473,8 @@ struct FastfTpsReader {
         buf = (u64)(ldw(0) >> sh);
         nbits = 32u - sh;
         widx = 1;
-        nextw = ldw(widx);
+        nextw = ldw(1);
+        nextw2 = FASTF_TPS_PREFETCH2 ? ldw(2) : 0u;
         refill();
     }
     __device__ __forceinline__ void refill()
@@ -443,12 +483,17 @@ struct FastfTpsReader {
             buf |= (u64)nextw << nbits;
             nbits += 32u;
             widx++;
+#if FASTF_TPS_PREFETCH2
+            nextw = nextw2;
+            nextw2 = ldw(widx + 1u);
+#else
             nextw = ldw(widx);
+#endif
         }
     }
     __device__ __forceinline__ u32 take(u32 n) { u32 v = (u32)buf & ((1u << n) - 1u); buf >>= n; nbits -= n; return v; }
     __device__ __forceinline__ void drop(u32 n) { buf >>= n; nbits -= n; }
-    __device__ __forceinline__ u64 bitpos() const { return base_bits + (u64)widx * 32u - nbits; }   // words [0, widx) are in buf or consumed
+    __device__ __forceinline__ u64 bitpos() const { return base_bits + (u64)widx * 32u - nbits; }
 };
 
 // entry of a code longer than the primary table (canonical walk starting at length tbits + 1).  The per-length counts are
@@ -518,51 +563,83 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
                 wr = S.wr;
                 have = true;
             }
-            if (wr - rd_cache >= FASTF_TPS_RING) {
+            // a round stores up to FASTF_TPS_TRIPLES + 1 tokens
+            if (wr - rd_cache > FASTF_TPS_RING - (FASTF_TPS_TRIPLES + 1u)) {
                 rd_cache = fastf_ldv(&S.rd);
-                if (wr - rd_cache >= FASTF_TPS_RING) { fastf_stv(&S.wr, wr); fastf_spin_poll(); continue; }
+                if (wr - rd_cache > FASTF_TPS_RING - (FASTF_TPS_TRIPLES + 1u)) { fastf_stv(&S.wr, wr); fastf_spin_poll(); continue; }
             }
-            // ---- one token ----
+            // ---- one round: up to two literal tokens (three literals each) and the match behind them ----
+            // Both the literal and the match path of a warp run in every round anyway (some lane always needs each), so a lane
+            // walks through both: literals first, then the match that ends the literal run.  Only the first symbol of a round may
+            // have a code longer than the primary table (canonical walk); behind it `e` is always a PEEK of the primary table
+            // ((e & 63) in 1..15 <=> literal inside the table) that the next step consumes or leaves to the next round.
+            // Bit budget: a refill leaves >= 33 bits; 15 + 9 + 9 for the first triple, 27 for the second, 9 + 5 for a length.
             br.refill();
             u32 e = S.lit[(u32)br.buf & ((1u << FASTF_TPS_LBITS) - 1u)];
             if ((e & 15u) == 0) e = fastf_tps_walk<FASTF_TPS_LBITS>(br.buf, lit_walk, S.lit_cnt, lit_sorted, FASTF_ALPHA_LITLEN);
-            const u32 kind = (e >> 4) & 3u;
-            u32 tok, err = 0;
+            u32 kind = (e >> 4) & 3u;
+            u32 err = 0;
+            const u32 wr0 = wr;
             bool end_stream = false, end_block = false;
-            br.drop(e & 15u);
             if (kind == FASTF_T16_LIT) {
-                tok = e >> 6;
-                if (pos >= isize) { err = FASTF_ST_OUT_OVERFLOW; }
-                pos++;
-            } else if (kind == FASTF_T16_SYM) {
+#pragma unroll
+                for (int triple = 0; triple < FASTF_TPS_TRIPLES; triple++) {
+                    br.drop(e & 15u);
+                    u32 tok = e >> 6, cnt = 1;
+                    e = S.lit[(u32)br.buf & ((1u << FASTF_TPS_LBITS) - 1u)];
+                    if ((e & 63u) - 1u < 15u) {
+                        br.drop(e & 15u);
+                        tok |= (e >> 6) << 8;
+                        cnt = 2;
+                        e = S.lit[(u32)br.buf & ((1u << FASTF_TPS_LBITS) - 1u)];
+                        if ((e & 63u) - 1u < 15u) {
+                            br.drop(e & 15u);
+                            tok |= (e >> 6) << 16;
+                            cnt = 3;
+                            br.refill();
+                            e = S.lit[(u32)br.buf & ((1u << FASTF_TPS_LBITS) - 1u)];
+                        }
+                    }
+                    if (pos + cnt > isize) { err = FASTF_ST_OUT_OVERFLOW; break; }   // never hand out bytes beyond the block
+                    fastf_stv(&S.ring[wr & (FASTF_TPS_RING - 1u)], tok | (cnt << 24));
+                    wr++;
+                    pos += cnt;
+                    if (cnt < 3u || (e & 63u) - 1u >= 15u) break;
+                }
+                // what follows the literals: a length code inside the table joins this round, anything else waits for the next
+                kind = ((e & 63u) >> 4 == FASTF_T16_SYM && (e & 15u) != 0 && !err) ? (u32)FASTF_T16_SYM : 4u;
+                if (kind == FASTF_T16_SYM) br.refill();
+            }
+            if (kind == FASTF_T16_SYM) {
+                br.drop(e & 15u);
                 const u32 K = G.lenK[e >> 6];
                 const u32 len = (K >> 8) + br.take(K & 255u);
                 br.refill();
                 u32 d = S.dist[(u32)br.buf & ((1u << FASTF_TPS_DBITS) - 1u)];
                 if ((d & 15u) == 0) d = fastf_tps_walk<FASTF_TPS_DBITS>(br.buf, dist_walk, S.dist_cnt, dist_sorted, FASTF_ALPHA_DIST);
-                if (((d >> 4) & 3u) != FASTF_T16_SYM) { err = FASTF_ST_BAD_SYMBOL; tok = 0; }
+                if (((d >> 4) & 3u) != FASTF_T16_SYM) err = FASTF_ST_BAD_SYMBOL;
                 else {
                     br.drop(d & 15u);
                     const u32 K2 = G.distK[d >> 6];
                     const u32 dist = (K2 >> 8) + br.take(K2 & 255u);
                     if (dist > pos) err = FASTF_ST_BAD_DISTANCE;
                     else if (pos + len > isize) err = FASTF_ST_OUT_OVERFLOW;
-                    tok = FASTF_TOK_MATCH | len | (dist << 9);
-                    pos += len;
+                    else {
+                        fastf_stv(&S.ring[wr & (FASTF_TPS_RING - 1u)], FASTF_TOK_MATCH | len | (dist << 9));
+                        wr++;
+                        pos += len;
+                    }
                 }
             } else if (kind == FASTF_T16_EOB) {
-                tok = 0;
+                br.drop(e & 15u);
                 end_block = true;
                 if (last) end_stream = true;
-            } else {
-                tok = 0;
+            } else if (kind == FASTF_T16_BAD) {
                 err = FASTF_ST_BAD_SYMBOL;
             }
             if (err) { end_stream = true; end_block = true; }
             if (!end_block) {
-                fastf_stv(&S.ring[wr & (FASTF_TPS_RING - 1u)], tok);
-                wr++;
-                if ((wr & 7u) == 0) { FASTF_SMEM_ORDER(); fastf_stv(&S.wr, wr); }
+                if ((wr ^ wr0) & ~7u) { FASTF_SMEM_ORDER(); fastf_stv(&S.wr, wr); }   // publish whenever a multiple of 8 is crossed
                 continue;
             }
             // ---- end of a deflate block: hand the stream to its service warp ----
@@ -582,24 +659,45 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
             have = false;
         }
     } else {
-        // ---------------- service: lock-step warp, owns FASTF_TPS_PER_SVC streams ----------------
+        // ---------------- service: lock-step warp, owns the streams sw, sw + SVC, sw + 2 SVC, ... ----------------
+        // One poll pass costs a handful of instructions: lane k looks at the control block of the k-th stream of this warp, a
+        // ballot collects the streams that need something, and only those are visited.  (A pass that walked the streams one
+        // after the other was half of all instructions the SM issued.)
         const u32 sw = warp;
+        constexpr u32 NPER = (FASTF_TPS_STREAMS + SVC - 1) / SVC;
+        static_assert(NPER <= 32, "one lane per owned stream");
+        const u32 my_sidx = sw + lane * (u32)SVC;
+        const bool mine = lane < NPER && my_sidx < FASTF_TPS_STREAMS;
+        FastfTpsStream &MS = streams[mine ? my_sidx : sw];
         for (;;) {
-            bool all_done = true, did = false;
-            for (u32 k = 0; k < (u32)((FASTF_TPS_STREAMS + SVC - 1) / SVC); k++) {
+            u32 st = FASTF_TPS_DONE, rd = 0, avail = 0;
+            if (mine) {
+                st = fastf_ldv(&MS.state);   // volatile shared-memory reads stay in program order: once the state says the
+                const u32 wr = fastf_ldv(&MS.wr);   // decoder handed the stream over, wr is final
+                rd = fastf_ldv(&MS.rd);
+                avail = wr - rd;
+            }
+            u32 work = 0;
+            if (st != FASTF_TPS_DONE) {
+                if (avail >= FASTF_TPS_BATCH_MIN || (avail > 0 && st != FASTF_TPS_RUN)) work = 1;
+                else if (avail == 0 && st == FASTF_TPS_NEXT) work = 2;
+                else if (avail == 0 && st == FASTF_TPS_BUILD) work = 3;
+            }
+            if (__ballot_sync(FASTF_FULL_MASK, st != FASTF_TPS_DONE) == 0) break;
+            u32 m = __ballot_sync(FASTF_FULL_MASK, work != 0);
+            if (!m) { fastf_spin_pause(); continue; }   // nothing to copy or set up: leave the issue slots to the decoders
+            while (m) {
+                const u32 k = (u32)__ffs((int)m) - 1u;
+                m &= m - 1u;
+                const u32 w = __shfl_sync(FASTF_FULL_MASK, work, (int)k);
+                const u32 krd = __shfl_sync(FASTF_FULL_MASK, rd, (int)k);
+                const u32 kav = __shfl_sync(FASTF_FULL_MASK, avail, (int)k);
                 const u32 sidx = sw + k * (u32)SVC;
-                if (sidx >= FASTF_TPS_STREAMS) break;   // SVC need not divide the stream count
                 FastfTpsStream &S = streams[sidx];
                 u16 *ssorted = sorted_base + (size_t)sidx * FASTF_TPS_SORTED_U16;
-                const u32 st = fastf_ldv(&S.state);
-                if (st == FASTF_TPS_DONE) continue;
-                all_done = false;
-                const u32 wr = fastf_ldv(&S.wr), rd = fastf_ldv(&S.rd);   // volatile shared-memory reads stay in program order
-                const u32 avail = wr - rd;
-                if (avail >= 32u || (avail > 0 && st != FASTF_TPS_RUN)) {
-                    fastf_tps_copy(A, S, rd, avail < 32u ? avail : 32u, lane);
-                    did = true;
-                } else if (avail == 0 && st == FASTF_TPS_NEXT) {
+                if (w == 1) {
+                    fastf_tps_copy(A, S, krd, kav < 32u ? kav : 32u, lane);
+                } else if (w == 2) {
                     // fetch the next BGZF block for this stream
                     u32 b = 0;
                     if (lane == 0) b = atomicAdd(A.next_block, 1u);
@@ -618,14 +716,10 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
                         __syncwarp();
                         fastf_tps_setup(A, S, ssorted, G, sw, lane);
                     }
-                    did = true;
-                } else if (avail == 0 && st == FASTF_TPS_BUILD) {
+                } else {
                     fastf_tps_setup(A, S, ssorted, G, sw, lane);
-                    did = true;
                 }
             }
-            if (all_done) break;
-            if (!did) fastf_spin_pause();   // nothing to copy or set up: leave the issue slots to the decoders
         }
     }
 }

@@ -385,7 +385,7 @@ struct DeScratch {   // per-launch state of the inflate engines
     DevBuf sorted;                                // its per-stream sorted-symbol lists (global scratch)
 };
 #define FASTF_INFLATE_TPS 1u   // inflate_lanes 1..4 select a shape of the thread-per-stream kernel; 8/16/32 the lock-step kernel
-#define FASTF_INFLATE_DEFAULT 1u   // 0 = default: thread-per-stream, 128 streams per SM: 8 decoding lanes x 16 decoder warps + 16 service warps
+#define FASTF_INFLATE_DEFAULT 2u   // 0 = default: thread-per-stream, 128 streams per SM: 16 decoding lanes x 8 decoder warps + 24 service warps
 
 // h_* = host copies of the block index (needed to build the engine's parameter array)
 static int launch_inflate(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_total, const u64 *in_off, const u32 *in_len, const u64 *out_off, const u32 *isize, u32 nblocks, u8 *out,
@@ -435,8 +435,8 @@ static int launch_inflate(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_to
 #endif
     }
     if (lanes >= 1 && lanes <= 4) {
-        // thread-per-stream kernel: persistent CTAs (one per SM), 64 streams each; blocks are handed out by a global counter.
-        // lanes selects the shape <decoding lanes per decoder warp, service warps>: 1 = <8, 16> (default), 2 = <16, 24>, 3 = <16, 16>, 4 = <32, 28>
+        // thread-per-stream kernel: persistent CTAs (one per SM), FASTF_TPS_STREAMS streams each; blocks are handed out by a global counter.
+        // lanes selects the shape <decoding lanes per decoder warp, service warps>: 1 = <8, 16>, 2 = <16, 24> (default), 3 = <16, 16>, 4 = <32, 28>
         const size_t smem = sizeof(FastfTpsStream) * FASTF_TPS_STREAMS + sizeof(FastfTpsShared);
         TRY(dev_reserve(ctx, de->counter, 64));
         CK(cudaMemsetAsync(de->counter.p, 0, sizeof(u32), s));
@@ -449,12 +449,20 @@ static int launch_inflate(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_to
         A.sorted = de->sorted.as<u16>();
 #ifndef FASTF_EMU
 #define FASTF_TPS_ATTR(L, SVC) CK(cudaFuncSetAttribute(fastf_bgzf_inflate_tps_kernel<L, SVC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
-        if (!ctx->tps_attr_set) { FASTF_TPS_ATTR(8, 16); FASTF_TPS_ATTR(16, 24); FASTF_TPS_ATTR(16, 16); FASTF_TPS_ATTR(32, 28); ctx->tps_attr_set = true; }
+#else
+#define FASTF_TPS_ATTR(L, SVC) ((void)0)
 #endif
+#ifdef FASTF_TPS_ALT_L
+        // experiment builds (-DFASTF_TPS_STREAMS=... -DFASTF_TPS_ALT_L=... -DFASTF_TPS_ALT_SVC=...): one shape only
+        if (!ctx->tps_attr_set) { FASTF_TPS_ATTR(FASTF_TPS_ALT_L, FASTF_TPS_ALT_SVC); ctx->tps_attr_set = true; }
+        FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<FASTF_TPS_ALT_L, FASTF_TPS_ALT_SVC>), grid, FASTF_TPS_THREADS_OF(FASTF_TPS_ALT_L, FASTF_TPS_ALT_SVC), smem, s, A);
+#else
+        if (!ctx->tps_attr_set) { FASTF_TPS_ATTR(8, 16); FASTF_TPS_ATTR(16, 24); FASTF_TPS_ATTR(16, 16); FASTF_TPS_ATTR(32, 28); ctx->tps_attr_set = true; }
         if (lanes == 1) { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<8, 16>), grid, FASTF_TPS_THREADS_OF(8, 16), smem, s, A); }
         else if (lanes == 2) { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<16, 24>), grid, FASTF_TPS_THREADS_OF(16, 24), smem, s, A); }
         else if (lanes == 3) { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<16, 16>), grid, FASTF_TPS_THREADS_OF(16, 16), smem, s, A); }
         else { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<32, 28>), grid, FASTF_TPS_THREADS_OF(32, 28), smem, s, A); }
+#endif
         CKL("bgzf_inflate_tps");
         return 0;
     }

@@ -50,7 +50,10 @@ enum : u32 {
 __device__ __forceinline__ void fastf_spin_pause() { emu::spin_yield(); }
 __device__ __forceinline__ void fastf_spin_poll() { emu::spin_yield(); }
 #else
-__device__ __forceinline__ void fastf_spin_pause() { __nanosleep(400); }
+#ifndef FASTF_PAUSE_NS
+#define FASTF_PAUSE_NS 400
+#endif
+__device__ __forceinline__ void fastf_spin_pause() { __nanosleep(FASTF_PAUSE_NS); }
 __device__ __forceinline__ void fastf_spin_poll() {}
 #endif
 
