@@ -422,7 +422,7 @@ def main():
         alg_bytes_launch = (st["compressed_bytes"] + st["inflated_bytes"]) / n_chunks
         achieved = alg_bytes_launch / (infl_ms_launch * 1e-3) / 1e9
         stages = {}
-        for k, bytes_ in (("inflate", st["compressed_bytes"] + st["inflated_bytes"]), ("parse", st["inflated_bytes"] + 8 * st["total"]), ("mt", st["cb_valid"] / 8.0 + 0),
+        for k, bytes_ in (("inflate", st["compressed_bytes"] + st["inflated_bytes"]), ("crc", st["inflated_bytes"]), ("parse", st["inflated_bytes"] + 8 * st["total"]), ("mt", st["cb_valid"] / 8.0 + 0),
                           ("sample", st["cb_valid"] * 8 * 2 + st["valid"] * 8), ("sort", st["valid"] * 16 * 7), ("count", st["valid"] * 8 + st["nnz"] * 12)):
             if world > 1 and k in ("sort", "count", "sample", "mt"):
                 continue   # rank 0's local clocks only cover the streaming stages in the sharded job

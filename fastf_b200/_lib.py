@@ -26,7 +26,7 @@ class Bam2dbResult(C.Structure):
                 ("n_blocks", C.c_uint64), ("compressed_bytes", C.c_uint64), ("inflated_bytes", C.c_uint64),
                 ("status", C.c_uint32), ("n_launches", C.c_uint32), ("n_chunks", C.c_uint32),
                 ("ms_inflate", C.c_float), ("ms_parse", C.c_float), ("ms_gather", C.c_float), ("ms_mt", C.c_float),
-                ("ms_sample", C.c_float), ("ms_sort", C.c_float), ("ms_count", C.c_float), ("ms_device_total", C.c_float)]
+                ("ms_sample", C.c_float), ("ms_sort", C.c_float), ("ms_count", C.c_float), ("ms_device_total", C.c_float), ("ms_crc", C.c_float)]
 
 
 class FreqResult(C.Structure):

@@ -15,6 +15,7 @@
 #include "bgzf_index.h"
 #include "bgzf_inflate.cuh"
 #include "bgzf_inflate_tps.cuh"
+#include "bgzf_crc32.cuh"
 #include "bam_parse.cuh"
 #include "scan_mt_sample.cuh"
 #include "radix_dedup.cuh"
@@ -77,9 +78,9 @@ static int ctx_fail(fastf_ctx *ctx, const char *fmt, ...)
 static const char *status_string(u32 st, char *buf, size_t n)
 {
     static const char *names[] = {"bad-btype", "bad-stored", "bad-codelens", "bad-symbol", "bad-distance", "out-overflow", "size-mismatch", "in-overrun",
-                                  "record-straddles-bgzf-block", "record-corrupt", "umi-too-long", "aux-corrupt", "bad-bam-header"};
+                                  "record-straddles-bgzf-block", "record-corrupt", "umi-too-long", "aux-corrupt", "bad-bam-header", "bgzf-crc32-mismatch"};
     buf[0] = 0;
-    for (u32 b = 0; b < 13; b++)
+    for (u32 b = 0; b < 14; b++)
         if (st & (1u << b)) { strncat(buf, names[b], n - strlen(buf) - 2); strncat(buf, " ", n - strlen(buf) - 1); }
     return buf;
 }
@@ -386,6 +387,19 @@ struct DeScratch {   // per-launch state of the inflate engines
 };
 #define FASTF_INFLATE_TPS 1u   // inflate_lanes 1..4 select a shape of the thread-per-stream kernel; 8/16/32 the lock-step kernel
 #define FASTF_INFLATE_DEFAULT 2u   // 0 = default: thread-per-stream, 128 streams per SM: 16 decoding lanes x 8 decoder warps + 24 service warps
+
+// CRC-32 of every inflated block against its BGZF trailer (htslib does this in bgzf_read_block); sets FASTF_ST_BAD_CRC in status[]
+static int launch_crc(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_total, const u64 *in_off, const u32 *in_len, const u8 *infl, const u64 *out_off, const u32 *isize, u32 nblocks,
+                      u32 *status, cudaStream_t s)
+{
+    if (nblocks == 0 || (lanes & FASTF_INFLATE_NO_CRC)) return 0;
+    u32 grid = (nblocks + FASTF_CRC_WARPS - 1) / FASTF_CRC_WARPS;
+    const u32 cap = (u32)ctx->n_sm * 8u;   // 64 warps per SM; the rest is a grid-stride loop (the tables are built once per CTA)
+    if (grid > cap) grid = cap;
+    FASTF_LAUNCH(fastf_bgzf_crc32_kernel, grid, FASTF_CRC_WARPS * 32, 0, s, comp, comp_total, in_off, in_len, infl, out_off, isize, nblocks, status);
+    CKL("bgzf_crc32");
+    return 0;
+}
 
 // h_* = host copies of the block index (needed to build the engine's parameter array)
 static int launch_inflate(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_total, const u64 *in_off, const u32 *in_len, const u64 *out_off, const u32 *isize, u32 nblocks, u8 *out,
@@ -729,11 +743,11 @@ struct fastf_bam2db_job {
     // stats
     u64 n_blocks = 0, comp_bytes = 0, infl_bytes = 0;
     u32 launches0 = 0, n_chunks = 0;
-    Timer t_infl[2], t_parse[2], t_gather[2], t_mt[2], t_sample, t_sort, t_count;
+    Timer t_infl[2], t_crc[2], t_parse[2], t_gather[2], t_mt[2], t_sample, t_sort, t_count;
     u32 mt_launches = 0;
     cudaEvent_t ev_first = nullptr, ev_last = nullptr;
     bool first_recorded = false;
-    float ms_inflate = 0, ms_parse = 0, ms_gather = 0, ms_mt = 0, ms_sample = 0, ms_sort = 0, ms_count = 0;
+    float ms_inflate = 0, ms_crc = 0, ms_parse = 0, ms_gather = 0, ms_mt = 0, ms_sample = 0, ms_sort = 0, ms_count = 0;
 };
 
 static u32 stage_cap_for(u32 isize) { return isize / 36u + 1u; }   // a record is >= 4 + 32 bytes
@@ -754,7 +768,7 @@ extern "C" void fastf_bam2db_job_free(fastf_bam2db_job *job)
         if (S.ev_infl) cudaEventDestroy(S.ev_infl);
         if (S.ev_gather) cudaEventDestroy(S.ev_gather);
         if (S.ev_done) cudaEventDestroy(S.ev_done);
-        job->t_infl[i].destroy(); job->t_parse[i].destroy(); job->t_gather[i].destroy();
+        job->t_infl[i].destroy(); job->t_crc[i].destroy(); job->t_parse[i].destroy(); job->t_gather[i].destroy();
     }
     job->t_mt[0].destroy(); job->t_mt[1].destroy(); job->t_sample.destroy(); job->t_sort.destroy(); job->t_count.destroy();
     if (job->ev_mt) cudaEventDestroy(job->ev_mt);
@@ -781,7 +795,7 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
     job->launches0 = ctx->launches;
     {
         const u32 l = p->inflate_lanes & 0xffu;
-        job->lanes = ((l == 8 || l == 16 || l == 32 || (l >= 1 && l <= 4)) ? l : FASTF_INFLATE_DEFAULT) | (p->inflate_lanes & FASTF_INFLATE_HW_ENGINE);
+        job->lanes = ((l == 8 || l == 16 || l == 32 || (l >= 1 && l <= 4)) ? l : FASTF_INFLATE_DEFAULT) | (p->inflate_lanes & (FASTF_INFLATE_HW_ENGINE | FASTF_INFLATE_NO_CRC));
     }
     job->chunk_bytes = p->chunk_inflated_bytes ? std::max<u64>(p->chunk_inflated_bytes, 1u << 20) : FASTF_DEFAULT_CHUNK;
     // the persistent thread-per-stream kernel keeps 64 streams per SM busy: give every launch several blocks per stream
@@ -808,7 +822,7 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
         rc = rc || cudaEventCreateWithFlags(&job->slot[i].ev_done, cudaEventDisableTiming) != cudaSuccess;
         rc = rc || cudaEventCreateWithFlags(&job->slot[i].ev_infl, cudaEventDisableTiming) != cudaSuccess;
         rc = rc || cudaEventCreateWithFlags(&job->slot[i].ev_gather, cudaEventDisableTiming) != cudaSuccess;
-        rc = rc || job->t_infl[i].init() || job->t_parse[i].init() || job->t_gather[i].init();
+        rc = rc || job->t_infl[i].init() || job->t_crc[i].init() || job->t_parse[i].init() || job->t_gather[i].init();
     }
     rc = rc || job->t_mt[0].init() || job->t_mt[1].init() || job->t_sample.init() || job->t_sort.init() || job->t_count.init();
     rc = rc || cudaEventCreateWithFlags(&job->ev_mt, cudaEventDisableTiming) != cudaSuccess;
@@ -1007,6 +1021,10 @@ static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb
     job->t_infl[si].stop(ctx->infl);
     CK(cudaEventRecord(S.ev_infl, ctx->infl));
     CK(cudaStreamWaitEvent(ctx->compute, S.ev_infl, 0));
+    job->t_crc[si].collect(&job->ms_crc);
+    job->t_crc[si].start(ctx->compute);
+    TRY(launch_crc(ctx, job->lanes, comp_dev, comp_total, S.idx.in_off, S.idx.in_len, S.infl.as<u8>(), S.idx.out_off, S.idx.isize, nb, S.idx.st_infl, ctx->compute));
+    job->t_crc[si].stop(ctx->compute);
     job->t_parse[si].collect(&job->ms_parse);
     job->t_parse[si].start(ctx->compute);
     if (!job->header_done) {
@@ -1055,7 +1073,7 @@ static int run_blocks(fastf_bam2db_job *job, const std::vector<FastfBgzfBlock> &
         }
         if (host_base) {
             // copy [start of first payload rounded down to 4, end of last payload) and rebase the offsets
-            const u64 lo = byte0 & ~3ull, hi = blocks[j - 1].in_off + blocks[j - 1].in_len;
+            const u64 lo = byte0 & ~3ull, hi = blocks[j - 1].in_off + blocks[j - 1].in_len + 8;   // + the last block's CRC32 / ISIZE trailer
             rel.assign(blocks.begin() + i, blocks.begin() + j);
             for (auto &b : rel) b.in_off -= lo;
             TRY(run_chunk(job, rel.data(), (u32)(j - i), nullptr, 0, host_base + lo, hi - lo));
@@ -1278,9 +1296,9 @@ static int fill_stats(fastf_bam2db_job *job, fastf_bam2db_result *res)
     res->bits_cell = L.bits_cell; res->bits_gene = L.bits_gene; res->bits_umi = L.bits_umi; res->umi_max_bytes = L.umi_max_bytes;
     res->n_blocks = job->n_blocks; res->compressed_bytes = job->comp_bytes; res->inflated_bytes = job->infl_bytes;
     res->status = job->status;
-    for (int i = 0; i < 2; i++) { job->t_infl[i].collect(&job->ms_inflate); job->t_parse[i].collect(&job->ms_parse); job->t_gather[i].collect(&job->ms_gather); }
+    for (int i = 0; i < 2; i++) { job->t_infl[i].collect(&job->ms_inflate); job->t_crc[i].collect(&job->ms_crc); job->t_parse[i].collect(&job->ms_parse); job->t_gather[i].collect(&job->ms_gather); }
     job->t_mt[0].collect(&job->ms_mt); job->t_mt[1].collect(&job->ms_mt); job->t_sample.collect(&job->ms_sample); job->t_sort.collect(&job->ms_sort); job->t_count.collect(&job->ms_count);
-    res->ms_inflate = job->ms_inflate; res->ms_parse = job->ms_parse; res->ms_gather = job->ms_gather; res->ms_mt = job->ms_mt;
+    res->ms_inflate = job->ms_inflate; res->ms_crc = job->ms_crc; res->ms_parse = job->ms_parse; res->ms_gather = job->ms_gather; res->ms_mt = job->ms_mt;
     res->ms_sample = job->ms_sample; res->ms_sort = job->ms_sort; res->ms_count = job->ms_count;
     if (job->first_recorded) {
         CK(cudaEventRecord(job->ev_last, ctx->compute));
@@ -1535,11 +1553,12 @@ static int inflate_whole(fastf_ctx *ctx, InflatedFile &F, const void *host_bytes
     if (ms) { CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); CK(cudaEventRecord(a, s)); }
     {
         const u32 l = lanes & 0xffu;
-        lanes = ((l == 8 || l == 16 || l == 32 || (l >= 1 && l <= 4)) ? l : FASTF_INFLATE_DEFAULT) | (lanes & FASTF_INFLATE_HW_ENGINE);
+        lanes = ((l == 8 || l == 16 || l == 32 || (l >= 1 && l <= 4)) ? l : FASTF_INFLATE_DEFAULT) | (lanes & (FASTF_INFLATE_HW_ENGINE | FASTF_INFLATE_NO_CRC));
     }
     TRY(launch_inflate(ctx, lanes, comp, comp_total, F.idx.in_off, F.idx.in_len, F.idx.out_off, F.idx.isize, (u32)nb, F.infl.as<u8>(), F.idx.st_infl, s, &F.de, F.idx.h_in_off, F.idx.h_in_len,
                        F.idx.h_out_off, F.idx.h_isize));
     if (ms) { CK(cudaEventRecord(b, s)); }
+    TRY(launch_crc(ctx, lanes, comp, dev_bytes ? (u64)n : comp_total, F.idx.in_off, F.idx.in_len, F.infl.as<u8>(), F.idx.out_off, F.idx.isize, (u32)nb, F.idx.st_infl, s));
     // OR of the per-block status words
     std::vector<u32> st(nb);
     if (nb) CK(cudaMemcpyAsync(st.data(), F.idx.st_infl, nb * sizeof(u32), cudaMemcpyDeviceToHost, s));

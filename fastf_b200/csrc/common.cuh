@@ -41,6 +41,7 @@ enum : u32 {
     FASTF_ST_UMI_TOO_LONG = 1u << 10,    // UB longer than the key layout allows
     FASTF_ST_AUX_CORRUPT = 1u << 11,     // malformed aux field (htslib: treated as "tag absent")
     FASTF_ST_BAD_HEADER = 1u << 12,      // BAM magic / header does not fit the first chunk
+    FASTF_ST_BAD_CRC = 1u << 13,         // CRC-32 of the inflated block differs from the BGZF trailer
 };
 
 // polite spin while another warp of the CTA makes progress.  fastf_spin_pause: the WHOLE warp has nothing to do (sleeps);

@@ -27,6 +27,9 @@ extern "C" {
 /* OR this into any `inflate_lanes` argument to inflate with the B200 hardware decompression engine (driver API
  * cuMemBatchDecompressAsync, DEFLATE) instead of the hand-written SM kernel.  Fails loudly where the engine is absent. */
 #define FASTF_INFLATE_HW_ENGINE 0x100u
+/* OR this in to skip the CRC-32 check of every inflated block against its BGZF trailer (htslib bgzf_read_block does the same check
+ * for the reference, src/bam2db_ds.c:360).  On by default: a mismatch fails the job with "bgzf-crc32-mismatch". */
+#define FASTF_INFLATE_NO_CRC 0x200u
 
 typedef struct fastf_ctx fastf_ctx;
 typedef struct fastf_bam2db_job fastf_bam2db_job;
@@ -99,6 +102,7 @@ typedef struct {
     uint32_t n_chunks;          /* inflate (= parse) launches: one per streamed chunk */
     /* device time, CUDA events on the launching stream, milliseconds */
     float ms_inflate, ms_parse, ms_gather, ms_mt, ms_sample, ms_sort, ms_count, ms_device_total;
+    float ms_crc;               /* CRC-32 verification of the inflated blocks */
 } fastf_bam2db_result;
 
 /* umi_code layout inside row_keys: bit (bits_umi-1) = non-NULL flag, then 8*umi_max_bytes content bits

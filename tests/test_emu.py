@@ -68,3 +68,30 @@ def test_emu_mt19937_jump_ahead(emu_lib):
     ) % (ROOT, os.path.join(ROOT, "tests"))
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FASTF_GPU_LIB=emu_lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_emu_bgzf_crc32_check(emu_lib):
+    """warp-parallel CRC-32 (32 lane segments folded by GF(2) shifts) against zlib's for ragged block sizes; a flipped payload byte in
+    a stored block (still valid deflate) and a wrong CRC field are reported as bgzf-crc32-mismatch"""
+    code = (
+        "import sys, zlib, ctypes as C, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from fastf_b200 import _lib\nimport bamgen\n"
+        "ctx = _lib.Context(0)\n"
+        "def inflate(img, lanes):\n"
+        "    buf = np.frombuffer(img, dtype=np.uint8); out, n, ms = C.c_void_p(), C.c_size_t(), C.c_float()\n"
+        "    if ctx.lib.fastf_inflate_host(ctx.h, C.c_void_p(buf.ctypes.data), buf.size, lanes, C.byref(out), C.byref(n), C.byref(ms)): return None\n"
+        "    d = C.string_at(out, n.value); ctx.lib.fastf_free(out); return d\n"
+        "rng = np.random.default_rng(5)\n"
+        "payloads = [bytes(rng.integers(0, 256, n, dtype=np.uint8)) for n in (1, 16, 17, 511, 513, 4099, 20001)] + [b'', b'ACGT' * 16384]\n"
+        "blocks = [bamgen.bgzf_block(p, 0) for p in payloads[:-1]] + [bamgen.bgzf_block(payloads[-1])]\n"
+        "img = b''.join(blocks) + bamgen.EOF_BLOCK\n"
+        "assert inflate(img, 0) == b''.join(payloads)\n"
+        "bad = bytearray(img); bad[len(blocks[0]) + len(blocks[1]) + len(blocks[2]) + 18 + 5 + 100] ^= 4\n"
+        "assert inflate(bytes(bad), 0) is None and b'crc32' in ctx.lib.fastf_last_error(ctx.h)\n"
+        "assert inflate(bytes(bad), 0x200) is not None\n"
+        "bad = bytearray(img); bad[len(img) - len(bamgen.EOF_BLOCK) - 8] ^= 1\n"
+        "assert inflate(bytes(bad), 32) is None and b'crc32' in ctx.lib.fastf_last_error(ctx.h)\n"
+    ) % (ROOT, os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FASTF_GPU_LIB=emu_lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:]

@@ -112,6 +112,32 @@ def test_inflate_flags_corrupt_streams(gpu_ctx):
         if want is None or len(want) != 3700:
             assert out is None, "corrupt stream at byte %d must be reported" % pos
             assert b"malformed" in gpu_ctx.lib.fastf_last_error(gpu_ctx.h)
+        elif want != bytes(b"hello world, hello world, hello world" * 100):
+            assert out is None and b"crc32" in gpu_ctx.lib.fastf_last_error(gpu_ctx.h)
+
+
+def test_inflate_checks_the_bgzf_crc32(gpu_ctx):
+    """htslib verifies the CRC32 of every BGZF block (bgzf_read_block, reached from sam_read1, reference src/bam2db_ds.c:360): a
+    payload that inflates cleanly to the wrong bytes, or a wrong CRC field, must fail; FASTF_INFLATE_NO_CRC skips the check."""
+    import bamgen
+    rng = np.random.default_rng(5)
+    payloads = [bytes(rng.integers(0, 256, n, dtype=np.uint8)) for n in (1, 15, 16, 17, 511, 512, 513, 4096, 40001, 65280)] + [b"", b"ACGT" * 16384]
+    blocks = [bamgen.bgzf_block(p, 0 if len(p) < 65000 else 1, zlib.Z_DEFAULT_STRATEGY) for p in payloads[:-1]] + [bamgen.bgzf_block(payloads[-1])]
+    img = b"".join(blocks) + bamgen.EOF_BLOCK
+    for lanes in (0, 32):
+        assert _inflate(gpu_ctx, img, lanes) == b"".join(payloads)          # every segment split of the warp-parallel CRC agrees with zlib's
+    off = 0
+    for k, b in enumerate(blocks):
+        if len(payloads[k]) and len(payloads[k]) < 65000 and k < len(blocks) - 1:
+            bad = bytearray(img)
+            bad[off + 18 + 5 + len(payloads[k]) // 2] ^= 0x20                      # inside the stored payload: still a valid deflate stream
+            assert _inflate(gpu_ctx, bytes(bad), 0) is None, "block %d" % k
+            assert b"crc32" in gpu_ctx.lib.fastf_last_error(gpu_ctx.h)
+            assert _inflate(gpu_ctx, bytes(bad), 0x200) is not None             # FASTF_INFLATE_NO_CRC
+        bad = bytearray(img)
+        bad[off + len(b) - 8] ^= 1                                               # the CRC32 field itself
+        assert _inflate(gpu_ctx, bytes(bad), 0) is None and b"crc32" in gpu_ctx.lib.fastf_last_error(gpu_ctx.h)
+        off += len(b)
 
 
 def test_inflate_synthetic_bam_vs_zlib(gpu_ctx, synth, oracle):
@@ -242,6 +268,21 @@ def test_bam2db_rejects_truncated_and_foreign_input(gpu_ctx, synth, tmp_path):
         B.run_device(gpu_ctx, bam[:-100].copy(), inputs, 1.0, 926)
     with pytest.raises(_lib.FastfError, match="not a BGZF"):
         B.run_device(gpu_ctx, np.frombuffer(gzip.compress(b"hello" * 100), dtype=np.uint8), inputs, 1.0, 926)
+    # one flipped quality byte inside a block whose deflate stream stays valid: the CRC32 of the trailer catches it
+    blocks_at = []
+    o = 0
+    raw = bytes(bam)
+    while o < len(raw):
+        bs = int.from_bytes(raw[o + 16:o + 18], "little") + 1
+        blocks_at.append((o, bs))
+        o += bs
+    o, bs = blocks_at[len(blocks_at) // 2]
+    rebuilt = bytearray(zlib.decompress(raw[o + 18:o + bs - 8], -15))
+    rebuilt[len(rebuilt) // 2] ^= 1
+    forged = bytearray(bamgen.bgzf_block(bytes(rebuilt)))
+    forged[-8:-4] = raw[o + bs - 8:o + bs - 4]                                   # keep the ORIGINAL crc: payload and trailer disagree
+    with pytest.raises(_lib.FastfError, match="crc32"):
+        B.run_device(gpu_ctx, np.frombuffer(raw[:o] + bytes(forged) + raw[o + bs:], dtype=np.uint8), inputs, 1.0, 926)
     # a record split across two BGZF blocks (foreign writer): reported, never silently mis-parsed
     raw = zlib.decompress(bytes(bam[18:]), -15) if False else None
     whole = gzip.decompress(bytes(bam))
