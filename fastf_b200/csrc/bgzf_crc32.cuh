@@ -5,7 +5,9 @@
 // there.  Here such a block raises FASTF_ST_BAD_CRC and the job fails loudly instead of producing a truncated result.
 //
 // One warp per block (grid-stride).  CRC-32 (IEEE 802.3, reflected, polynomial 0xEDB88320) is linear over GF(2), so the 32
-// lanes checksum 32 contiguous segments independently -- slice-by-4 table lookups out of shared memory, 16-byte loads -- and
+// lanes checksum 32 contiguous segments independently -- slice-by-4 table lookups out of shared memory (one private copy of
+// the tables per lane, entry i of lane l at word 32 i + l, so that the 32 data-dependent lookups of a warp never collide on a
+// bank), 16-byte loads -- and
 // the lane results are folded by a 5-level tree: crc(A || B) = crc(A) * x^(8 |B|) mod P  xor  crc(B).  All segments but the
 // first have the same length S, so level k needs one constant, x^(8 S 2^k) mod P, built from a per-CTA table of
 // x^(8 2^j) mod P.  Bound: HBM read of the inflated bytes (once); measured in profiles/README.md.
@@ -13,7 +15,7 @@
 #include "common.cuh"
 
 #define FASTF_CRC_POLY 0xEDB88320u
-#define FASTF_CRC_WARPS 8
+#define FASTF_CRC_WARPS 32            // one CTA per SM: the lane-replicated tables take 128 KB of shared memory
 
 // a * b mod P, polynomials in the reflected representation (bit 31 = x^0), as in zlib's multmodp
 __device__ __forceinline__ u32 fastf_crc_mulmod(u32 a, u32 b)
@@ -28,8 +30,8 @@ __device__ __forceinline__ u32 fastf_crc_mulmod(u32 a, u32 b)
 }
 
 struct FastfCrcTables {
-    u32 t[4][256];     // slice-by-4
-    u32 x8pow[24];     // x^(8 * 2^j) mod P
+    u32 t[4][256][32];   // slice-by-4, replicated per lane
+    u32 x8pow[24];       // x^(8 * 2^j) mod P
 };
 
 __device__ __forceinline__ void fastf_crc_tables_init(FastfCrcTables &T)
@@ -37,14 +39,14 @@ __device__ __forceinline__ void fastf_crc_tables_init(FastfCrcTables &T)
     for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
         u32 c = i;
         for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1u) ? FASTF_CRC_POLY : 0u);
-        T.t[0][i] = c;
+        T.t[0][i][0] = c;
     }
     __syncthreads();
     for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
-        u32 c = T.t[0][i];
+        u32 c = T.t[0][i][0];
         for (int k = 1; k < 4; k++) {
-            c = T.t[0][c & 0xffu] ^ (c >> 8);
-            T.t[k][i] = c;
+            c = T.t[0][c & 0xffu][0] ^ (c >> 8);
+            T.t[k][i][0] = c;
         }
     }
     if (threadIdx.x == 0) {
@@ -52,27 +54,30 @@ __device__ __forceinline__ void fastf_crc_tables_init(FastfCrcTables &T)
         for (int j = 0; j < 24; j++) { T.x8pow[j] = p; p = fastf_crc_mulmod(p, p); }
     }
     __syncthreads();
+    for (u32 i = threadIdx.x; i < 4u * 256u * 32u; i += blockDim.x)
+        if (i & 31u) (&T.t[0][0][0])[i] = (&T.t[0][0][0])[i & ~31u];
+    __syncthreads();
 }
 
-__device__ __forceinline__ u32 fastf_crc_byte(const FastfCrcTables &T, u32 c, u32 b) { return T.t[0][(c ^ b) & 0xffu] ^ (c >> 8); }
-__device__ __forceinline__ u32 fastf_crc_word(const FastfCrcTables &T, u32 c, u32 w)
+__device__ __forceinline__ u32 fastf_crc_byte(const FastfCrcTables &T, u32 lane, u32 c, u32 b) { return T.t[0][(c ^ b) & 0xffu][lane] ^ (c >> 8); }
+__device__ __forceinline__ u32 fastf_crc_word(const FastfCrcTables &T, u32 lane, u32 c, u32 w)
 {
     c ^= w;
-    return T.t[3][c & 0xffu] ^ T.t[2][(c >> 8) & 0xffu] ^ T.t[1][(c >> 16) & 0xffu] ^ T.t[0][c >> 24];
+    return T.t[3][c & 0xffu][lane] ^ T.t[2][(c >> 8) & 0xffu][lane] ^ T.t[1][(c >> 16) & 0xffu][lane] ^ T.t[0][c >> 24][lane];
 }
 
 // register state after running `n` bytes at p through the CRC starting from state c (no pre/post inversion)
-__device__ __forceinline__ u32 fastf_crc_run(const FastfCrcTables &T, u32 c, const u8 *p, u32 n)
+__device__ __forceinline__ u32 fastf_crc_run(const FastfCrcTables &T, u32 lane, u32 c, const u8 *p, u32 n)
 {
-    while (n && ((uintptr_t)p & 15u)) { c = fastf_crc_byte(T, c, *p++); n--; }
+    while (n && ((uintptr_t)p & 15u)) { c = fastf_crc_byte(T, lane, c, *p++); n--; }
     for (; n >= 16; n -= 16, p += 16) {
         const uint4 v = *reinterpret_cast<const uint4 *>(p);
-        c = fastf_crc_word(T, c, v.x);
-        c = fastf_crc_word(T, c, v.y);
-        c = fastf_crc_word(T, c, v.z);
-        c = fastf_crc_word(T, c, v.w);
+        c = fastf_crc_word(T, lane, c, v.x);
+        c = fastf_crc_word(T, lane, c, v.y);
+        c = fastf_crc_word(T, lane, c, v.z);
+        c = fastf_crc_word(T, lane, c, v.w);
     }
-    while (n) { c = fastf_crc_byte(T, c, *p++); n--; }
+    while (n) { c = fastf_crc_byte(T, lane, c, *p++); n--; }
     return c;
 }
 
@@ -81,7 +86,8 @@ __device__ __forceinline__ u32 fastf_crc_run(const FastfCrcTables &T, u32 c, con
 __global__ void __launch_bounds__(FASTF_CRC_WARPS * 32) fastf_bgzf_crc32_kernel(const u8 *comp, u64 comp_total, const u64 *in_off, const u32 *in_len, const u8 *infl, const u64 *out_off,
                                                                               const u32 *isize, u32 nblocks, u32 *status)
 {
-    __shared__ FastfCrcTables T;
+    FASTF_DYN_SMEM(smem);
+    FastfCrcTables &T = *reinterpret_cast<FastfCrcTables *>(smem);
     fastf_crc_tables_init(T);
     const u32 lane = threadIdx.x & 31u;
     const u32 warp0 = blockIdx.x * FASTF_CRC_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * FASTF_CRC_WARPS;
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(FASTF_CRC_WARPS * 32) fastf_bgzf_crc32_kernel(
         const u32 S = (n >> 5) & ~15u;
         const u32 first = n - 31u * S;
         const u32 beg = lane ? first + (lane - 1u) * S : 0u, len = lane ? S : first;
-        u32 c = fastf_crc_run(T, lane ? 0u : 0xffffffffu, src + beg, len);
+        u32 c = fastf_crc_run(T, lane, lane ? 0u : 0xffffffffu, src + beg, len);
         if (S) {
             // lane k < 5 builds x^(8 S 2^k): product of x8pow[j + k] over the set bits j of S
             u32 pw = 0x80000000u;   // x^0

@@ -13,15 +13,20 @@ struct FastfBgzfBlock {
     uint32_t crc32;     // trailer CRC32
 };
 
-enum { FASTF_BGZF_OK = 0, FASTF_BGZF_NEED_MORE = 1, FASTF_BGZF_BAD_MAGIC = 2, FASTF_BGZF_NO_BSIZE = 3, FASTF_BGZF_BAD_ISIZE = 4 };
+enum { FASTF_BGZF_OK = 0, FASTF_BGZF_NEED_MORE = 1, FASTF_BGZF_BAD_MAGIC = 2, FASTF_BGZF_NO_BSIZE = 3, FASTF_BGZF_BAD_ISIZE = 4, FASTF_BGZF_LIMIT = 5 };
 
 // Index whole blocks found in buf[0..n).  origin is added to every in_off.  *consumed = bytes covered by
 // complete blocks.  Returns FASTF_BGZF_OK when the range ends on a block boundary, FASTF_BGZF_NEED_MORE when
 // a trailing partial block remains, or an error code (blocks before the error are still appended).
-static inline int fastf_bgzf_index(const uint8_t *buf, size_t n, uint64_t origin, std::vector<FastfBgzfBlock> &out, size_t *consumed)
+// With max_bytes != 0 the walk stops (FASTF_BGZF_LIMIT) in front of the block that would take the run past max_bytes of
+// inflated or of compressed span, or past max_blocks blocks -- one streaming chunk's worth -- so that the caller can hand that
+// chunk to the device before touching the next block headers.
+static inline int fastf_bgzf_index(const uint8_t *buf, size_t n, uint64_t origin, std::vector<FastfBgzfBlock> &out, size_t *consumed, uint64_t max_bytes = 0, size_t max_blocks = 0)
 {
     size_t pos = 0;
     int rc = FASTF_BGZF_OK;
+    uint64_t infl = 0;
+    const size_t n0 = out.size();
     while (pos < n) {
         if (n - pos < 12) { rc = FASTF_BGZF_NEED_MORE; break; }
         const uint8_t *h = buf + pos;
@@ -44,6 +49,8 @@ static inline int fastf_bgzf_index(const uint8_t *buf, size_t n, uint64_t origin
         b.crc32 = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
         b.isize = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
         if (b.isize > 65536) { rc = FASTF_BGZF_BAD_ISIZE; break; }
+        if (max_bytes && out.size() > n0 && (infl + b.isize > max_bytes || b.in_off + b.in_len - out[n0].in_off > max_bytes || out.size() - n0 >= max_blocks)) { rc = FASTF_BGZF_LIMIT; break; }
+        infl += b.isize;
         out.push_back(b);
         pos += bsize;
     }

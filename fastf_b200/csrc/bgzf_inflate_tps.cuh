@@ -100,11 +100,6 @@ struct FastfTpsShared {
     u16 scratch[FASTF_TPS_MAX_SVC][32];   // first[16], start[16] while building
 };
 
-#ifdef FASTF_EMU
-#define FASTF_DYN_SMEM(ptr) u8 *ptr = emu::dyn_smem()
-#else
-#define FASTF_DYN_SMEM(ptr) extern __shared__ __align__(16) u8 fastf_dyn_smem_[]; u8 *ptr = fastf_dyn_smem_
-#endif
 
 // Hand-over between warps of the CTA goes through shared memory only.  One thread's shared-memory stores are performed in
 // program order and so are another thread's volatile loads, so publishing "data, then counter" needs no MEMBAR on the hot

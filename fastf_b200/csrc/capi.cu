@@ -42,6 +42,7 @@ struct fastf_ctx {
     u32 launches;   // kernels launched through this context (bench: gpu_launches)
     int n_sm;
     bool tps_attr_set;
+    bool crc_attr_set;
     void *mtj_polys;   // device copy of x^(2^k) mod phi, k = 0..44 (uploaded on first use)
     void *mtj_scratch;
     // size-bucketed caches of device / pinned allocations: a job's buffers are recycled by the next job on the same
@@ -394,9 +395,11 @@ static int launch_crc(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_total,
 {
     if (nblocks == 0 || (lanes & FASTF_INFLATE_NO_CRC)) return 0;
     u32 grid = (nblocks + FASTF_CRC_WARPS - 1) / FASTF_CRC_WARPS;
-    const u32 cap = (u32)ctx->n_sm * 8u;   // 64 warps per SM; the rest is a grid-stride loop (the tables are built once per CTA)
-    if (grid > cap) grid = cap;
-    FASTF_LAUNCH(fastf_bgzf_crc32_kernel, grid, FASTF_CRC_WARPS * 32, 0, s, comp, comp_total, in_off, in_len, infl, out_off, isize, nblocks, status);
+    if (grid > (u32)ctx->n_sm) grid = (u32)ctx->n_sm;   // one CTA per SM (the tables are built once per CTA); the rest is a grid-stride loop
+#ifndef FASTF_EMU
+    if (!ctx->crc_attr_set) { CK(cudaFuncSetAttribute(fastf_bgzf_crc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastfCrcTables))); ctx->crc_attr_set = true; }
+#endif
+    FASTF_LAUNCH(fastf_bgzf_crc32_kernel, grid, FASTF_CRC_WARPS * 32, sizeof(FastfCrcTables), s, comp, comp_total, in_off, in_len, infl, out_off, isize, nblocks, status);
     CKL("bgzf_crc32");
     return 0;
 }
@@ -699,7 +702,6 @@ static void index_release(fastf_ctx *ctx, BlockIndexDev &I) { dev_release(ctx, I
 
 struct ChunkSlot {
     BlockIndexDev idx;
-    DevBuf comp;          // compressed bytes of the chunk (host feeds only)
     DevBuf stage;         // per-block candidate staging
     DevBuf infl;          // inflated bytes of the chunk (double buffered: chunk i+1 inflates while chunk i is parsed)
     DeScratch de;
@@ -719,6 +721,10 @@ struct fastf_bam2db_job {
     u64 chunk_bytes;
     ChunkSlot slot[2];
     u32 next_slot = 0;
+    // compressed bytes of host-fed chunks: a ring of three, so that the copy of chunk i is issued before the host waits for
+    // anything and overlaps the inflate of chunks i-2 and i-1
+    struct CompRing { DevBuf buf; cudaEvent_t ev_copy = nullptr, ev_free = nullptr; bool used = false; } comp_ring[3];
+    u32 comp_seq = 0;
     DevBuf counters;          // u64[4]: n_records, n_candidates, status_or, (unused)
     DevBuf hdr_off;           // u64: offset of the first alignment record inside the current chunk
     DevBuf cand;              // all candidates (CB-valid reads) in file order
@@ -763,12 +769,17 @@ extern "C" void fastf_bam2db_job_free(fastf_bam2db_job *job)
     cudaStreamSynchronize(ctx->mt);
     for (int i = 0; i < 2; i++) {
         ChunkSlot &S = job->slot[i];
-        index_release(ctx, S.idx); dev_release(ctx, S.comp); dev_release(ctx, S.stage); dev_release(ctx, S.infl); dev_release(ctx, S.de.counter); dev_release(ctx, S.de.sorted); pin_release(ctx, S.snap);
+        index_release(ctx, S.idx); dev_release(ctx, S.stage); dev_release(ctx, S.infl); dev_release(ctx, S.de.counter); dev_release(ctx, S.de.sorted); pin_release(ctx, S.snap);
         if (S.ev_copy) cudaEventDestroy(S.ev_copy);
         if (S.ev_infl) cudaEventDestroy(S.ev_infl);
         if (S.ev_gather) cudaEventDestroy(S.ev_gather);
         if (S.ev_done) cudaEventDestroy(S.ev_done);
         job->t_infl[i].destroy(); job->t_crc[i].destroy(); job->t_parse[i].destroy(); job->t_gather[i].destroy();
+    }
+    for (auto &R : job->comp_ring) {
+        dev_release(ctx, R.buf);
+        if (R.ev_copy) cudaEventDestroy(R.ev_copy);
+        if (R.ev_free) cudaEventDestroy(R.ev_free);
     }
     job->t_mt[0].destroy(); job->t_mt[1].destroy(); job->t_sample.destroy(); job->t_sort.destroy(); job->t_count.destroy();
     if (job->ev_mt) cudaEventDestroy(job->ev_mt);
@@ -823,6 +834,10 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
         rc = rc || cudaEventCreateWithFlags(&job->slot[i].ev_infl, cudaEventDisableTiming) != cudaSuccess;
         rc = rc || cudaEventCreateWithFlags(&job->slot[i].ev_gather, cudaEventDisableTiming) != cudaSuccess;
         rc = rc || job->t_infl[i].init() || job->t_crc[i].init() || job->t_parse[i].init() || job->t_gather[i].init();
+    }
+    for (auto &R : job->comp_ring) {
+        rc = rc || cudaEventCreateWithFlags(&R.ev_copy, cudaEventDisableTiming) != cudaSuccess;
+        rc = rc || cudaEventCreateWithFlags(&R.ev_free, cudaEventDisableTiming) != cudaSuccess;
     }
     rc = rc || job->t_mt[0].init() || job->t_mt[1].init() || job->t_sample.init() || job->t_sort.init() || job->t_count.init();
     rc = rc || cudaEventCreateWithFlags(&job->ev_mt, cudaEventDisableTiming) != cudaSuccess;
@@ -983,6 +998,19 @@ static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb
     fastf_ctx *ctx = job->ctx;
     const u32 si = job->next_slot;
     ChunkSlot &S = job->slot[si];
+    // Host feed: the H2D copy goes out FIRST, before the host waits for anything.  The ring entry was last read by chunk i-3
+    // (inflate + CRC), which the copy stream waits for on the device.
+    fastf_bam2db_job::CompRing *ring = nullptr;
+    if (host_src) {
+        ring = &job->comp_ring[job->comp_seq++ % 3u];
+        const u64 padded = (host_bytes + 3) & ~3ull;
+        TRY(dev_reserve(ctx, ring->buf, padded + 16));
+        if (ring->used) CK(cudaStreamWaitEvent(ctx->copy, ring->ev_free, 0));
+        CK(cudaMemcpyAsync(ring->buf.p, host_src, host_bytes, cudaMemcpyHostToDevice, ctx->copy));
+        CK(cudaEventRecord(ring->ev_copy, ctx->copy));
+        comp_dev = ring->buf.as<u8>();
+        comp_total = padded;
+    }
     // the slot was used two chunks ago: its gather must have been issued (finalize) before we reuse its buffers
     TRY(finalize_slot(job, si));
     TRY(index_reserve(ctx, S.idx, nb));
@@ -996,16 +1024,7 @@ static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb
         out_total += blocks[i].isize;
         stage_total += stage_cap_for(blocks[i].isize);
     }
-    if (host_src) {
-        const u64 padded = (host_bytes + 3) & ~3ull;
-        TRY(dev_reserve(ctx, S.comp, padded + 16));
-        // the previous user of S.comp (chunk i-2) finished inflating: its ev_done was waited for in finalize_slot
-        CK(cudaMemcpyAsync(S.comp.p, host_src, host_bytes, cudaMemcpyHostToDevice, ctx->copy));
-        CK(cudaEventRecord(S.ev_copy, ctx->copy));
-        CK(cudaStreamWaitEvent(ctx->infl, S.ev_copy, 0));
-        comp_dev = S.comp.as<u8>();
-        comp_total = padded;
-    }
+    if (ring) CK(cudaStreamWaitEvent(ctx->infl, ring->ev_copy, 0));
     // S.infl / S.stage / S.idx were last used by chunk i-2, whose parse and gather have completed (finalize_slot above)
     TRY(dev_reserve(ctx, S.infl, out_total + 64));
     TRY(dev_reserve(ctx, S.stage, stage_total * sizeof(u64) + 64));
@@ -1025,6 +1044,7 @@ static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb
     job->t_crc[si].start(ctx->compute);
     TRY(launch_crc(ctx, job->lanes, comp_dev, comp_total, S.idx.in_off, S.idx.in_len, S.infl.as<u8>(), S.idx.out_off, S.idx.isize, nb, S.idx.st_infl, ctx->compute));
     job->t_crc[si].stop(ctx->compute);
+    if (ring) { CK(cudaEventRecord(ring->ev_free, ctx->compute)); ring->used = true; }   // compressed bytes no longer needed
     job->t_parse[si].collect(&job->ms_parse);
     job->t_parse[si].start(ctx->compute);
     if (!job->header_done) {
@@ -1052,8 +1072,8 @@ static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb
     job->n_chunks++;
     job->infl_bytes += out_total;
     job->next_slot ^= 1u;
-    // now that this chunk is queued, gather the previous one (its counters are long done)
-    TRY(finalize_slot(job, si ^ 1u));
+    // The previous chunk (slot si ^ 1) is gathered when its slot comes round again (top of the next run_chunk) or at the end of
+    // the job: waiting for it here would keep the host from queueing more than one chunk ahead of the device.
     return 0;
 }
 
@@ -1145,11 +1165,17 @@ extern "C" int fastf_bam2db_feed(fastf_bam2db_job *job, const void *host_bytes, 
     }
     if (!n) return 0;
     // 2. whole blocks straight out of the caller's buffer
-    blocks.clear();
+    // (one chunk's worth of block headers at a time: the device starts on chunk i while the host walks the headers of chunk i+1)
     size_t used = 0;
-    int rc = fastf_bgzf_index(p, n, 0, blocks, &used);
-    if (rc != FASTF_BGZF_OK && rc != FASTF_BGZF_NEED_MORE) return ctx_fail(ctx, "bam2db_feed: not a BGZF stream at byte %zu (index error %d)", used, rc);
-    if (!blocks.empty()) TRY(run_blocks(job, blocks, nullptr, 0, p));
+    for (;;) {
+        blocks.clear();
+        size_t step = 0;
+        int rc = fastf_bgzf_index(p + used, n - used, used, blocks, &step, job->chunk_bytes, FASTF_MAX_BLOCKS_PER_CHUNK);
+        if (rc != FASTF_BGZF_OK && rc != FASTF_BGZF_NEED_MORE && rc != FASTF_BGZF_LIMIT) return ctx_fail(ctx, "bam2db_feed: not a BGZF stream at byte %zu (index error %d)", used + step, rc);
+        used += step;
+        if (!blocks.empty()) TRY(run_blocks(job, blocks, nullptr, 0, p));
+        if (rc != FASTF_BGZF_LIMIT) break;
+    }
     // 3. keep the tail.  The caller may reuse its buffer after we return: wait for the copies.
     if (used < n) job->carry.assign(p + used, p + n);
     CK(cudaStreamSynchronize(ctx->copy));

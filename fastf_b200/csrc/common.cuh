@@ -44,6 +44,13 @@ enum : u32 {
     FASTF_ST_BAD_CRC = 1u << 13,         // CRC-32 of the inflated block differs from the BGZF trailer
 };
 
+// dynamic shared memory of the running CTA
+#ifdef FASTF_EMU
+#define FASTF_DYN_SMEM(ptr) u8 *ptr = emu::dyn_smem()
+#else
+#define FASTF_DYN_SMEM(ptr) extern __shared__ __align__(16) u8 fastf_dyn_smem_[]; u8 *ptr = fastf_dyn_smem_
+#endif
+
 // polite spin while another warp of the CTA makes progress.  fastf_spin_pause: the WHOLE warp has nothing to do (sleeps);
 // fastf_spin_poll: only some lanes of a warp wait while others work -- a sleep there would stall the working lanes at the next
 // reconvergence point, so on the GPU it is a no-op (the emulator still has to let the other fibers run).
