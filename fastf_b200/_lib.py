@@ -38,6 +38,15 @@ class FreqResult(C.Structure):
                 ("ms_inflate", C.c_float), ("ms_keys", C.c_float), ("ms_sort", C.c_float), ("ms_rle", C.c_float), ("ms_device_total", C.c_float)]
 
 
+class TaghistResult(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("n_hits", C.c_uint64), ("n_groups", C.c_uint64), ("mode", C.c_uint32),
+                ("first", c_u32p), ("count", c_u32p), ("ivalue", C.POINTER(C.c_int32)), ("a_off", c_u64p), ("a_len", c_u32p), ("b_len", c_u32p),
+                ("strings", C.POINTER(C.c_char)), ("strings_bytes", C.c_uint64),
+                ("n_blocks", C.c_uint64), ("compressed_bytes", C.c_uint64), ("inflated_bytes", C.c_uint64),
+                ("status", C.c_uint32), ("n_launches", C.c_uint32), ("hash_rounds", C.c_uint32),
+                ("ms_inflate", C.c_float), ("ms_tags", C.c_float), ("ms_sort", C.c_float), ("ms_rle", C.c_float), ("ms_device_total", C.c_float)]
+
+
 _SIGS = {
     "fastf_abi_version": (C.c_int, []),
     "fastf_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
@@ -82,6 +91,8 @@ _SIGS = {
     "fastf_freq_gpu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.POINTER(FreqResult)]),
     "fastf_freq_gpu_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, c_u64p, c_u32p, c_u32p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(FreqResult)]),
     "fastf_freq_result_free": (None, [C.POINTER(FreqResult)]),
+    "fastf_taghist_gpu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(TaghistResult)]),
+    "fastf_taghist_result_free": (None, [C.POINTER(TaghistResult)]),
 }
 EXPORTS = sorted(_SIGS)
 

@@ -21,6 +21,7 @@
 #include "radix_dedup.cuh"
 #include "mt_jump.h"
 #include "freq.cuh"
+#include "bam_tags.cuh"
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -79,9 +80,9 @@ static int ctx_fail(fastf_ctx *ctx, const char *fmt, ...)
 static const char *status_string(u32 st, char *buf, size_t n)
 {
     static const char *names[] = {"bad-btype", "bad-stored", "bad-codelens", "bad-symbol", "bad-distance", "out-overflow", "size-mismatch", "in-overrun",
-                                  "record-straddles-bgzf-block", "record-corrupt", "umi-too-long", "aux-corrupt", "bad-bam-header", "bgzf-crc32-mismatch"};
+                                  "record-straddles-bgzf-block", "record-corrupt", "umi-too-long", "aux-corrupt", "bad-bam-header", "bgzf-crc32-mismatch", "tag-not-a-string"};
     buf[0] = 0;
-    for (u32 b = 0; b < 14; b++)
+    for (u32 b = 0; b < 15; b++)
         if (st & (1u << b)) { strncat(buf, names[b], n - strlen(buf) - 2); strncat(buf, " ", n - strlen(buf) - 1); }
     return buf;
 }
@@ -1878,6 +1879,215 @@ extern "C" int fastf_freq_gpu_device(fastf_ctx *ctx, const void *dev_bytes, size
     }
     return freq_common(ctx, nullptr, nbytes, (const u8 *)dev_bytes, &blocks, key_len, inflate_lanes, res);
 }
+// ---------------------------------------------------------------------------------------------------
+// crb / extract: histogram of one aux tag (or of the pair of two) over all records of a BAM image
+// ---------------------------------------------------------------------------------------------------
+extern "C" void fastf_taghist_result_free(fastf_taghist_result *res)
+{
+    if (!res) return;
+    free(res->first); free(res->count); free(res->ivalue); free(res->a_off); free(res->a_len); free(res->b_len); free(res->strings);
+    res->first = nullptr; res->count = nullptr; res->ivalue = nullptr; res->a_off = nullptr; res->a_len = nullptr; res->b_len = nullptr; res->strings = nullptr;
+}
+
+extern "C" int fastf_taghist_gpu(fastf_ctx *ctx, const void *host_bytes, size_t n, const char *tag_a, uint32_t mode, const char *tag_b, uint32_t inflate_lanes, fastf_taghist_result *res)
+{
+    CK(cudaSetDevice(ctx->device));
+    memset(res, 0, sizeof *res);
+    if (!tag_a || !tag_a[0] || !tag_a[1]) return ctx_fail(ctx, "taghist: a tag is two characters");
+    if (tag_b && (!tag_b[0] || !tag_b[1])) return ctx_fail(ctx, "taghist: a tag is two characters");
+    if (mode > FASTF_TAG_MODE_INT || (mode == FASTF_TAG_MODE_INT && tag_b)) return ctx_fail(ctx, "taghist: mode 0 = string (optionally a pair), 1 = integer");
+    if (!looks_like_gzip((const u8 *)host_bytes, n)) return ctx_fail(ctx, "taghist: not a BGZF stream");
+    res->mode = mode;
+    const u32 l0 = ctx->launches;
+    cudaStream_t s = ctx->compute;
+    InflatedFile F;
+    DevBuf hdr_off, counters, stage_off, stage, keys, loc_a, loc_b, vals, kalt, valt, orand, coll, rep_a, rep_b, blob_off, blob;
+    PinBuf host;
+    SortScratch S;
+    RleScratch R;
+    Timer t_tags, t_sort, t_rle;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::vector<u64> h_stage_off, h_rep_a, h_rep_b, h_blob_off;
+    std::vector<u32> h_start;
+    std::vector<u64> h_key;
+    auto cleanup = [&]() {
+        for (DevBuf *b : {&hdr_off, &counters, &stage_off, &stage, &keys, &loc_a, &loc_b, &vals, &kalt, &valt, &orand, &coll, &rep_a, &rep_b, &blob_off, &blob}) dev_release(ctx, *b);
+        pin_release(ctx, host);
+        sort_scratch_release(ctx, S);
+        rle_scratch_release(ctx, R);
+        t_tags.destroy(); t_sort.destroy(); t_rle.destroy();
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        inflated_release(ctx, F);
+    };
+    auto body = [&]() -> int {
+        if (t_tags.init() || t_sort.init() || t_rle.init() || cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return ctx_fail(ctx, "taghist: event creation failed");
+        CK(cudaEventRecord(e0, s));
+        TRY(inflate_whole(ctx, F, host_bytes, n, nullptr, nullptr, inflate_lanes, &res->ms_inflate, s));
+        res->n_blocks = F.n_blocks; res->compressed_bytes = n; res->inflated_bytes = F.infl_bytes;
+        const u32 nb = (u32)F.n_blocks;
+        TRY(pin_reserve(ctx, host, 64));
+        TRY(dev_reserve(ctx, hdr_off, sizeof(u64)));
+        TRY(dev_reserve(ctx, counters, 4 * sizeof(u64)));
+        TRY(dev_reserve(ctx, orand, 2 * sizeof(u64)));
+        TRY(dev_reserve(ctx, coll, sizeof(u32)));
+        CK(cudaMemsetAsync(counters.p, 0, 4 * sizeof(u64), s));
+        CK(cudaMemsetAsync(hdr_off.p, 0, sizeof(u64), s));
+        // per-block staging slices (a record is >= 36 bytes)
+        h_stage_off.resize(std::max<u32>(nb, 1));
+        u64 plane = 0;
+        for (u32 i = 0; i < nb; i++) { h_stage_off[i] = plane; plane += stage_cap_for(F.idx.h_isize[i]); }
+        TRY(dev_reserve(ctx, stage_off, h_stage_off.size() * sizeof(u64)));
+        CK(cudaMemcpyAsync(stage_off.p, h_stage_off.data(), h_stage_off.size() * sizeof(u64), cudaMemcpyHostToDevice, s));
+        TRY(dev_reserve(ctx, stage, std::max<u64>(plane, 1) * 3 * sizeof(u64)));
+        FastfTagQuery Q;
+        Q.a0 = (u8)tag_a[0]; Q.a1 = (u8)tag_a[1];
+        Q.b0 = tag_b ? (u8)tag_b[0] : 0u; Q.b1 = tag_b ? (u8)tag_b[1] : 0u;
+        Q.mode = mode;
+        u64 n_hits = 0, ngroups = 0;
+        for (u32 round = 0;; round++) {
+            if (round == 4) return ctx_fail(ctx, "taghist: 64-bit hash collisions in four rounds with different seeds");
+            Q.seed = 0x9e3779b97f4a7c15ull * round;
+            res->hash_rounds = round + 1;
+            CK(cudaMemsetAsync(counters.p, 0, 4 * sizeof(u64), s));
+            t_tags.collect(&res->ms_tags);
+            t_tags.start(s);
+            FASTF_LAUNCH(fastf_bam_header_kernel, 1, 32, 0, s, (const u8 *)F.infl.as<u8>(), F.infl_bytes, hdr_off.as<u64>(), (u32 *)(counters.as<u64>() + 2));
+            CKL("bam_header");
+            if (nb) {
+                FASTF_LAUNCH(fastf_bam_tags_kernel, (nb + FASTF_PARSE_WARPS - 1) / FASTF_PARSE_WARPS, FASTF_PARSE_WARPS * 32, 0, s, (const u8 *)F.infl.as<u8>(), (u64)((F.infl_bytes + 15) & ~15ull),
+                             (const u64 *)F.idx.out_off, (const u32 *)F.idx.isize, nb, (const u64 *)hdr_off.as<u64>(), Q, (const u64 *)stage_off.as<u64>(), stage.as<u64>(), plane, F.idx.nrec,
+                             F.idx.ncbv, F.idx.st_parse);
+                CKL("bam_tags");
+            }
+            FASTF_LAUNCH(fastf_chunk_counts_kernel, 1, FASTF_SCAN_THREADS, 0, s, (const u32 *)F.idx.nrec, (const u32 *)F.idx.ncbv, (const u32 *)F.idx.st_infl, (const u32 *)F.idx.st_parse, nb,
+                         F.idx.dst_base, counters.as<u64>());
+            CKL("chunk_counts");
+            t_tags.stop(s);
+            CK(cudaMemcpyAsync(host.p, counters.p, 4 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            res->n_records = host.as<u64>()[0];
+            n_hits = host.as<u64>()[1];
+            res->n_hits = n_hits;
+            res->status = (u32)host.as<u64>()[2];
+            if (res->status) {
+                char buf[256];
+                if (res->status & FASTF_ST_TAG_TYPE)
+                    return ctx_fail(ctx, "taghist: tag-not-a-string: a record carries %c%c%s as a non-string value%s (the reference passes bam_aux2Z()'s NULL to strcmp/strcpy there)", tag_a[0],
+                                    tag_a[1], tag_b ? " or its partner tag" : "", tag_b ? ", or lacks the partner tag" : "");
+                return ctx_fail(ctx, "taghist: malformed input: %s", status_string(res->status, buf, sizeof buf));
+            }
+            if (n_hits >= 0xffffffffull) return ctx_fail(ctx, "taghist: more than 2^32-1 tagged records in one pass");
+            ngroups = 0;
+            if (!n_hits) break;
+            TRY(dev_reserve(ctx, keys, n_hits * sizeof(u64)));
+            TRY(dev_reserve(ctx, loc_a, n_hits * sizeof(u64)));
+            TRY(dev_reserve(ctx, loc_b, n_hits * sizeof(u64)));
+            TRY(dev_reserve(ctx, kalt, n_hits * sizeof(u64)));
+            TRY(dev_reserve(ctx, vals, n_hits * sizeof(u32)));
+            TRY(dev_reserve(ctx, valt, n_hits * sizeof(u32)));
+            t_sort.collect(&res->ms_sort);
+            t_sort.start(s);
+            u64 *planes[3] = {keys.as<u64>(), loc_a.as<u64>(), loc_b.as<u64>()};
+            for (int k = 0; k < 3; k++) {
+                FASTF_LAUNCH(fastf_stage_gather_kernel, (nb + 7) / 8, 256, 0, s, (const u64 *)(stage.as<u64>() + (u64)k * plane), (const u64 *)stage_off.as<u64>(), (const u32 *)F.idx.ncbv,
+                             (const u64 *)F.idx.dst_base, nb, planes[k]);
+                CKL("stage_gather");
+            }
+            FASTF_LAUNCH(fastf_iota_kernel, (u32)((n_hits + 255) / 256), 256, 0, s, vals.as<u32>(), n_hits);
+            CKL("iota");
+            u64 varying = 0;
+            TRY(varying_bits(ctx, orand, host, keys.as<u64>(), n_hits, &varying, s));
+            u32 shifts[8];
+            const int npass = plan_windows(varying, shifts);
+            bool in_alt = false;
+            TRY(sort_keys(ctx, S, keys.as<u64>(), kalt.as<u64>(), vals.as<u32>(), valt.as<u32>(), n_hits, shifts, npass, &in_alt, s));
+            t_sort.stop(s);
+            const u64 *sorted = in_alt ? kalt.as<u64>() : keys.as<u64>();
+            const u32 *perm = in_alt ? valt.as<u32>() : vals.as<u32>();
+            t_rle.collect(&res->ms_rle);
+            t_rle.start(s);
+            u64 nd = 0;
+            TRY(rle_groups(ctx, R, sorted, perm, n_hits, 0, 64, 0, &ngroups, &nd, s));
+            u32 collided = 0;
+            if (mode == FASTF_TAG_MODE_STRING) {
+                CK(cudaMemsetAsync(coll.p, 0, sizeof(u32), s));
+                FASTF_LAUNCH(fastf_taghist_verify_kernel, (u32)((n_hits + 255) / 256), 256, 0, s, (const u8 *)F.infl.as<u8>(), sorted, perm, (const u64 *)loc_a.as<u64>(), (const u64 *)loc_b.as<u64>(),
+                             n_hits, coll.as<u32>());
+                CKL("taghist_verify");
+                CK(cudaMemcpyAsync(host.p, coll.p, sizeof(u32), cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                collided = host.as<u32>()[0];
+            }
+            t_rle.stop(s);
+            if (!collided) break;   // every group holds one value: done.  Otherwise hash again with another seed.
+        }
+        // ---- groups to host ----
+        res->n_groups = ngroups;
+        const u64 ng1 = std::max<u64>(ngroups, 1);
+        res->first = (u32 *)malloc(ng1 * sizeof(u32));
+        res->count = (u32 *)malloc(ng1 * sizeof(u32));
+        res->ivalue = (int32_t *)malloc(ng1 * sizeof(int32_t));
+        res->a_off = (u64 *)malloc(ng1 * sizeof(u64));
+        res->a_len = (u32 *)malloc(ng1 * sizeof(u32));
+        res->b_len = (u32 *)malloc(ng1 * sizeof(u32));
+        if (!res->first || !res->count || !res->ivalue || !res->a_off || !res->a_len || !res->b_len) return ctx_fail(ctx, "taghist: out of host memory");
+        if (ngroups) {
+            h_start.resize(ngroups);
+            h_key.resize(ngroups);
+            CK(cudaMemcpyAsync(res->first, R.grp_val.p, ngroups * sizeof(u32), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(h_start.data(), R.grp_first.p, ngroups * sizeof(u32), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(h_key.data(), R.grp_key.p, ngroups * sizeof(u64), cudaMemcpyDeviceToHost, s));
+            if (mode == FASTF_TAG_MODE_STRING) {
+                TRY(dev_reserve(ctx, rep_a, ngroups * sizeof(u64)));
+                TRY(dev_reserve(ctx, rep_b, ngroups * sizeof(u64)));
+                FASTF_LAUNCH(fastf_taghist_reps_kernel, (u32)((ngroups + 255) / 256), 256, 0, s, (const u32 *)R.grp_val.as<u32>(), (const u64 *)loc_a.as<u64>(), (const u64 *)loc_b.as<u64>(), (u32)ngroups,
+                             rep_a.as<u64>(), rep_b.as<u64>());
+                CKL("taghist_reps");
+                h_rep_a.resize(ngroups); h_rep_b.resize(ngroups); h_blob_off.resize(ngroups);
+                CK(cudaMemcpyAsync(h_rep_a.data(), rep_a.p, ngroups * sizeof(u64), cudaMemcpyDeviceToHost, s));
+                CK(cudaMemcpyAsync(h_rep_b.data(), rep_b.p, ngroups * sizeof(u64), cudaMemcpyDeviceToHost, s));
+            }
+            CK(cudaStreamSynchronize(s));
+            for (u64 g = 0; g < ngroups; g++) {
+                res->count[g] = (u32)((g + 1 < ngroups ? h_start[g + 1] : (u32)n_hits) - h_start[g]);
+                res->ivalue[g] = (int32_t)(u32)h_key[g];
+                res->a_off[g] = 0; res->a_len[g] = 0; res->b_len[g] = 0;
+            }
+            if (mode == FASTF_TAG_MODE_STRING) {
+                u64 total = 0;
+                for (u64 g = 0; g < ngroups; g++) {
+                    h_blob_off[g] = total;
+                    res->a_off[g] = total;
+                    res->a_len[g] = (u32)(h_rep_a[g] & 0xffffu);
+                    res->b_len[g] = (u32)(h_rep_b[g] & 0xffffu);
+                    total += res->a_len[g] + res->b_len[g];
+                }
+                res->strings_bytes = total;
+                res->strings = (char *)malloc(std::max<u64>(total, 1));
+                if (!res->strings) return ctx_fail(ctx, "taghist: out of host memory");
+                TRY(dev_reserve(ctx, blob_off, ngroups * sizeof(u64)));
+                TRY(dev_reserve(ctx, blob, std::max<u64>(total, 1)));
+                CK(cudaMemcpyAsync(blob_off.p, h_blob_off.data(), ngroups * sizeof(u64), cudaMemcpyHostToDevice, s));
+                FASTF_LAUNCH(fastf_taghist_strings_kernel, (u32)((ngroups * 32 + 255) / 256), 256, 0, s, (const u8 *)F.infl.as<u8>(), (const u64 *)rep_a.as<u64>(), (const u64 *)rep_b.as<u64>(),
+                             (const u64 *)blob_off.as<u64>(), (u32)ngroups, blob.as<u8>());
+                CKL("taghist_strings");
+                if (total) CK(cudaMemcpyAsync(res->strings, blob.p, total, cudaMemcpyDeviceToHost, s));
+            }
+        }
+        CK(cudaEventRecord(e1, s));
+        CK(cudaEventSynchronize(e1));
+        t_tags.collect(&res->ms_tags); t_sort.collect(&res->ms_sort); t_rle.collect(&res->ms_rle);
+        cudaEventElapsedTime(&res->ms_device_total, e0, e1);
+        return 0;
+    };
+    int rc = body();
+    cleanup();
+    res->n_launches = ctx->launches - l0;
+    if (rc) fastf_taghist_result_free(res);
+    return rc;
+}
+
 extern "C" void fastf_freq_result_free(fastf_freq_result *res)
 {
     if (!res) return;

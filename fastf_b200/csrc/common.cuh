@@ -42,6 +42,7 @@ enum : u32 {
     FASTF_ST_AUX_CORRUPT = 1u << 11,     // malformed aux field (htslib: treated as "tag absent")
     FASTF_ST_BAD_HEADER = 1u << 12,      // BAM magic / header does not fit the first chunk
     FASTF_ST_BAD_CRC = 1u << 13,         // CRC-32 of the inflated block differs from the BGZF trailer
+    FASTF_ST_TAG_TYPE = 1u << 14,        // crb / extract: a tag the reference reads with bam_aux2Z() is not a string (or CR is absent): it dereferences NULL there
 };
 
 // dynamic shared memory of the running CTA

@@ -1,8 +1,10 @@
-/* fastF (B200 build): the reference's command line for the two GPU subcommands (reference src/main.c:30-92, 288-362, 404-443).
- *   fastF bam2db -b BAM -f FEATURES -a BARCODES -d DB -c RATE_CELL -r RATE_DEPTH [-o OUT] [-s SEED] [-u]
- *   fastF freq   -R R1 -o OUT [-l LEN] [-u UMI]
- * Long options (--bam --feature --barcode --dbname --cell --depth --out --seed --umicopies; --R1 --out --len --umi) as in the
- * reference.  filter / crb / extract are not part of this build (out of scope: see DESIGN.md). */
+/* fastF (B200 build): the reference's command line for the GPU subcommands (reference src/main.c:30-92, 231-402, 404-443).
+ *   fastF bam2db  -b BAM -f FEATURES -a BARCODES -d DB -c RATE_CELL -r RATE_DEPTH [-o OUT] [-s SEED] [-u]
+ *   fastF freq    -R R1 -o OUT [-l LEN] [-u UMI]
+ *   fastF crb     -b BAM -o OUT.gz
+ *   fastF extract -b BAM -t TAG [-T 0|1]
+ * Long options (--bam --feature --barcode --dbname --cell --depth --out --seed --umicopies; --R1 --out --len --umi; --tag --type) as
+ * in the reference.  filter is not part of this build (out of scope: see DESIGN.md). */
 #include "fastf_host.h"
 #include <stdlib.h>
 #include <string.h>
@@ -95,16 +97,58 @@ static int cmd_bam2db(int argc, const char **argv)
     return 0;
 }
 
+static int cmd_crb(int argc, const char **argv)
+{
+    const char *bam = NULL, *out = ".";   /* reference default (src/main.c:234): gzopen(".") fails */
+    static const optdef defs[] = {{'b', "bam", 1}, {'o', "out", 1}, {'h', "help", 0}};
+    for (int i = 1; i < argc; i++) {
+        const char *v;
+        switch (next_opt(argc, argv, &i, defs, 3, &v)) {
+        case 0: bam = v; break;
+        case 1: out = v; break;
+        default: printf("Usage: fastF crb -b BAM -o OUT.gz\n\nExtract CR and CB tags from bam file and summarize them with frequencies to a tsv file.\n"); exit(0);
+        }
+    }
+    if (!bam) { fprintf(stderr, "\x1b[31mError:\x1b[0m path to bam file can not been NULL while extracting .\n"); exit(1); }
+    gzFile fo = gzopen(out, "w");
+    if (!fo) { fprintf(stderr, "\x1b[31mError:\x1b[0m can not open file %s\n", out); exit(1); }
+    int rc = crb_write((char *)bam, fo);
+    gzclose(fo);
+    if (!rc) printf("Done.\n");
+    return rc;
+}
+
+static int cmd_extract(int argc, const char **argv)
+{
+    const char *bam = NULL, *tag = NULL;
+    int type = 0;
+    static const optdef defs[] = {{'b', "bam", 1}, {'t', "tag", 1}, {'T', "type", 1}, {'h', "help", 0}};
+    for (int i = 1; i < argc; i++) {
+        const char *v;
+        switch (next_opt(argc, argv, &i, defs, 4, &v)) {
+        case 0: bam = v; break;
+        case 1: tag = v; break;
+        case 2: type = (int)strtol(v, NULL, 0); break;
+        default: printf("Usage: fastF extract -b BAM -t TAG [-T 0|1]\n\nExtract the tag of bam file.\n"); exit(0);
+        }
+    }
+    if (!bam || access(bam, F_OK) == -1) { fprintf(stderr, "\x1b[31mError:\x1b[0m bam file: %s does not exist.\n", bam ? bam : "(null)"); exit(1); }
+    if (!tag) { fprintf(stderr, "\x1b[31mError:\x1b[0m --tag is required.\n"); exit(1); }
+    return extract_bam((char *)bam, tag, type);
+}
+
 int main(int argc, const char **argv)
 {
     const char *dev = getenv("FASTF_DEVICE");
     if (dev) fastf_device = atoi(dev);
     if (argc < 2 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) {
-        printf("Usage: fastF [-h] <command> [<args>]\n\nCommands (GPU build): freq, bam2db\n");
+        printf("Usage: fastF [-h] <command> [<args>]\n\nCommands (GPU build): freq, bam2db, crb, extract\n");
         return argc < 2 ? -1 : 0;
     }
     if (!strcmp(argv[1], "freq")) return cmd_freq(argc - 1, argv + 1);
     if (!strcmp(argv[1], "bam2db")) return cmd_bam2db(argc - 1, argv + 1);
-    if (!strcmp(argv[1], "filter") || !strcmp(argv[1], "crb") || !strcmp(argv[1], "extract")) { fprintf(stderr, "fastF (B200 build): `%s` is not part of this build; use the reference binary.\n", argv[1]); return 1; }
+    if (!strcmp(argv[1], "crb")) return cmd_crb(argc - 1, argv + 1);
+    if (!strcmp(argv[1], "extract")) return cmd_extract(argc - 1, argv + 1);
+    if (!strcmp(argv[1], "filter")) { fprintf(stderr, "fastF (B200 build): `%s` is not part of this build; use the reference binary.\n", argv[1]); return 1; }
     return 0;   /* the reference silently ignores unknown commands (src/main.c:437-442) */
 }

@@ -177,6 +177,35 @@ int fastf_freq_gpu_device(fastf_ctx *ctx, const void *dev_bytes, size_t nbytes, 
                           uint32_t key_len, uint32_t inflate_lanes, fastf_freq_result *res);
 void fastf_freq_result_free(fastf_freq_result *res);
 
+/* ---- crb / extract: the reference's other two per-record BAM histograms -----------------------------------------------------
+ * Replaces read_bam() (reference src/extract.c:64-133, called from cmd_crb src/main.c:272) and the record loop of extract_bam()
+ * (src/extract.c:135-199, called from cmd_extract src/main.c:399): for every record that carries tag A, count its value -- a string
+ * (bam_aux2Z), the pair (A, B) of two strings (crb: A = "CB", B = "CR"), or an integer (bam_aux2i printed with "%d").  The host
+ * turns (value, count, first occurrence) into the pre-order of the reference's BSTs (insert_tree / insert_CB_node).  Where the
+ * reference dereferences NULL (string mode on a non-string tag, CB present without CR) the call fails with "tag-not-a-string". */
+#define FASTF_TAG_STRING 0u
+#define FASTF_TAG_INT 1u
+typedef struct {
+    uint64_t n_records;         /* BAM records in the file (crb: read_count; extract: total_count / 2, src/extract.c:162,164) */
+    uint64_t n_hits;            /* records carrying tag A (extract: valid_count) */
+    uint64_t n_groups;          /* distinct values / pairs; the per-group arrays below are in no particular order */
+    uint32_t mode;
+    uint32_t *first;            /* ordinal among the hits (file order) of the group's first occurrence */
+    uint32_t *count;
+    int32_t *ivalue;            /* FASTF_TAG_INT: the value */
+    uint64_t *a_off;            /* FASTF_TAG_STRING: value A = strings[a_off, a_off + a_len), value B follows it (b_len bytes); no NULs */
+    uint32_t *a_len, *b_len;
+    char *strings;
+    uint64_t strings_bytes;
+    uint64_t n_blocks, compressed_bytes, inflated_bytes;
+    uint32_t status, n_launches;
+    uint32_t hash_rounds;       /* 1 unless two different values shared a 64-bit hash (detected byte for byte, re-run with another seed) */
+    float ms_inflate, ms_tags, ms_sort, ms_rle, ms_device_total;
+} fastf_taghist_result;
+/* bgzf_bytes: the whole BAM file in host memory; tag_b = NULL for a single tag */
+int fastf_taghist_gpu(fastf_ctx *ctx, const void *bgzf_bytes, size_t n, const char *tag_a, uint32_t mode, const char *tag_b, uint32_t inflate_lanes, fastf_taghist_result *res);
+void fastf_taghist_result_free(fastf_taghist_result *res);
+
 #ifdef __cplusplus
 }
 #endif

@@ -544,6 +544,152 @@ int oracle_freq(const char *r1_file, size_t len_cellbarcode, size_t len_umi, con
     return 0;
 }
 
+/* ====================================================================================== */
+/* crb / extract -- src/extract.c:4-216 (two more per-record histograms over the same BAM reader; */
+/* output order is again the pre-order of an unbalanced BST built in read order)                  */
+/* ====================================================================================== */
+typedef struct cbnode { char *cb; fnode *cr; struct cbnode *lo, *hi; } cbnode;
+static void fnode_insert(fnode **root, const char *key)             /* insert_tree, src/filter.c:105-124 */
+{
+    fnode **slot = root;
+    while (*slot) {
+        int c = strcmp(key, (*slot)->key);
+        if (c == 0) { (*slot)->count++; return; }
+        slot = c < 0 ? &(*slot)->lo : &(*slot)->hi;
+    }
+    fnode *nn = (fnode *)calloc(1, sizeof(fnode));
+    nn->key = strdup(key);
+    nn->count = 1;
+    *slot = nn;
+}
+static void fnode_print(fnode *nd, FILE *f, const char *fmt)        /* print_tree / print_tree_same_row: node, left, right */
+{
+    if (!nd) return;
+    fprintf(f, fmt, nd->key, nd->count);
+    fnode_print(nd->lo, f, fmt);
+    fnode_print(nd->hi, f, fmt);
+    free(nd->key);
+    free(nd);
+}
+static void cbnode_print(cbnode *nd, FILE *f)                        /* print_CB_node, src/extract.c:47-62 */
+{
+    if (!nd) return;
+    fprintf(f, "%s;", nd->cb);
+    fnode_print(nd->cr, f, "%s,%ld;");
+    fprintf(f, "\n");
+    cbnode_print(nd->lo, f);
+    cbnode_print(nd->hi, f);
+    free(nd->cb);
+    free(nd);
+}
+/* walks the records of an inflated BAM; returns the offset of the first record or 0 on a bad header */
+static size_t bam_first_record(const uint8_t *bam, size_t bn)
+{
+    if (bn < 12 || memcmp(bam, "BAM\1", 4)) return 0;
+    size_t p = 8 + (size_t)rd32(bam + 4);
+    uint32_t n_ref = rd32(bam + p);
+    p += 4;
+    for (uint32_t i = 0; i < n_ref; i++) p += 8 + (size_t)rd32(bam + p);
+    return p;
+}
+static const uint8_t *bam_next_aux(const uint8_t *bam, size_t bn, size_t *p, const uint8_t **end)   /* sam_read1 >= 0 */
+{
+    if (*p + 4 > bn) return NULL;
+    int32_t bs = (int32_t)rd32(bam + *p);
+    if (bs < 32 || *p + 4 + (size_t)bs > bn) return NULL;
+    const uint8_t *c = bam + *p + 4;
+    *end = c + bs;
+    *p += 4 + (size_t)bs;
+    int64_t aoff = 32 + (int64_t)c[8] + 4 * (int64_t)rd16(c + 12) + ((int64_t)(int32_t)rd32(c + 16) + 1) / 2 + (int32_t)rd32(c + 16);
+    if ((int32_t)rd32(c + 16) < 0 || aoff > bs) return NULL;
+    return c + aoff;
+}
+static int load_bam(const char *bam_file, uint8_t **bam, size_t *bn, size_t *first)
+{
+    uint8_t *file;
+    size_t fn;
+    if (read_whole_file(bam_file, &file, &fn)) return 1;
+    int irc = oracle_bgzf_inflate(file, fn, bam, bn, NULL, NULL, NULL, NULL);
+    free(file);
+    if (irc) return 10 + irc;
+    *first = bam_first_record(*bam, *bn);
+    if (!*first) { free(*bam); return 20; }
+    return 0;
+}
+
+/* read_bam + print_CB_node (src/extract.c:64-133, src/main.c:231-286): out_path receives the DECOMPRESSED bytes of the
+ * reference's gz output.  Returns 3 where the reference dereferences NULL (CB present but CR absent, or either not a string). */
+int oracle_crb(const char *bam_file, const char *out_path, uint64_t *n_reads)
+{
+    uint8_t *bam;
+    size_t bn, p;
+    int rc = load_bam(bam_file, &bam, &bn, &p);
+    if (rc) return rc;
+    cbnode *root = NULL;
+    uint64_t reads = 0;
+    const uint8_t *aux, *end;
+    while ((aux = bam_next_aux(bam, bn, &p, &end)) != NULL) {
+        const uint8_t *cbp = aux_find(aux, end, 'C', 'B'), *crp = aux_find(aux, end, 'C', 'R');
+        if (cbp) {                                                   /* src/extract.c:92-103 */
+            const char *cb = aux_as_Z(cbp), *cr = aux_as_Z(crp);
+            if (!cb || !cr) { free(bam); return 3; }
+            cbnode **slot = &root;                                   /* insert_CB_node, src/extract.c:4-31 */
+            while (*slot) {
+                int c = strcmp(cb, (*slot)->cb);
+                if (c == 0) break;
+                slot = c < 0 ? &(*slot)->lo : &(*slot)->hi;
+            }
+            if (!*slot) { cbnode *nn = (cbnode *)calloc(1, sizeof(cbnode)); nn->cb = strdup(cb); *slot = nn; }
+            fnode_insert(&(*slot)->cr, cr);
+        }
+        reads++;
+    }
+    free(bam);
+    FILE *f = fopen(out_path, "w");
+    if (!f) return 2;
+    cbnode_print(root, f);
+    fclose(f);
+    if (n_reads) *n_reads = reads;
+    return 0;
+}
+
+/* extract_bam (src/extract.c:135-216): histogram of one aux tag; type 0 = string (bam_aux2Z), 1 = integer printed with "%d".
+ * *total is the reference's total_count, which it increments TWICE per record (src/extract.c:162,164).  Returns 3 where the
+ * reference dereferences NULL (type 0 on a tag that is not Z/H). */
+int oracle_extract(const char *bam_file, const char *tag, int type, const char *out_path, uint64_t *total, uint64_t *valid)
+{
+    uint8_t *bam;
+    size_t bn, p;
+    int rc = load_bam(bam_file, &bam, &bn, &p);
+    if (rc) return rc;
+    fnode *root = NULL;
+    uint64_t tot = 0, val = 0;
+    const uint8_t *aux, *end;
+    while ((aux = bam_next_aux(bam, bn, &p, &end)) != NULL) {
+        tot += 2;
+        const uint8_t *tp = aux_find(aux, end, tag[0], tag[1]);
+        if (!tp) continue;
+        val++;
+        if (type == 0) {
+            const char *z = aux_as_Z(tp);
+            if (!z) { free(bam); return 3; }
+            fnode_insert(&root, z);
+        } else {
+            char buf[32];
+            snprintf(buf, sizeof buf, "%d", (int)aux_as_int(tp));     /* "%d" of the int64 bam_aux2i(): its low 32 bits */
+            fnode_insert(&root, buf);
+        }
+    }
+    free(bam);
+    FILE *f = fopen(out_path, "w");
+    if (!f) return 2;
+    fnode_print(root, f, "%s,%ld\n");
+    fclose(f);
+    if (total) *total = tot;
+    if (valid) *valid = val;
+    return 0;
+}
+
 #ifdef FASTF_ORACLE_MAIN
 int main(int argc, char **argv)
 {
@@ -561,6 +707,20 @@ int main(int argc, char **argv)
         int rc = oracle_freq(argv[2], strtoul(argv[3], 0, 10), strtoul(argv[4], 0, 10), argv[5], &nr, &nk);
         if (rc) { fprintf(stderr, "oracle freq failed: %d\n", rc); return 1; }
         printf("reads=%llu keys=%llu\n", (unsigned long long)nr, (unsigned long long)nk);
+        return 0;
+    }
+    if (argc >= 4 && !strcmp(argv[1], "crb")) {
+        uint64_t nr;
+        int rc = oracle_crb(argv[2], argv[3], &nr);
+        if (rc) { fprintf(stderr, "oracle crb failed: %d\n", rc); return 1; }
+        printf("reads=%llu\n", (unsigned long long)nr);
+        return 0;
+    }
+    if (argc >= 6 && !strcmp(argv[1], "extract")) {
+        uint64_t t, v;
+        int rc = oracle_extract(argv[2], argv[3], atoi(argv[4]), argv[5], &t, &v);
+        if (rc) { fprintf(stderr, "oracle extract failed: %d\n", rc); return 1; }
+        printf("total=%llu valid=%llu\n", (unsigned long long)t, (unsigned long long)v);
         return 0;
     }
     fprintf(stderr, "usage: oracle_cli bam2db BAM BARCODES FEATURES RATE_CELL RATE_DEPTH SEED OUTDIR | freq R1 L U OUT\n");

@@ -30,6 +30,8 @@ class Oracle:
         lib.oracle_bam2db.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_float, C.c_float, C.c_uint, C.c_char_p, C.POINTER(Bam2dbResult)]
         lib.oracle_bam2db_free.argtypes = [C.POINTER(Bam2dbResult)]
         lib.oracle_freq.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_char_p, u64p, u64p]
+        lib.oracle_crb.argtypes = [C.c_char_p, C.c_char_p, u64p]
+        lib.oracle_extract.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, u64p, u64p]
 
     def mt_stream(self, seed, n):
         out = np.zeros(n, dtype=np.uint32)
@@ -75,6 +77,23 @@ class Oracle:
         if rc:
             raise RuntimeError("oracle freq rc=%d" % rc)
         return nr.value, nk.value
+
+
+    def crb(self, bam, out_path):
+        """-> read_count; out_path gets the decompressed text of the reference's gz output; rc 3 = the reference would dereference NULL"""
+        nr = C.c_uint64()
+        rc = self.lib.oracle_crb(bam.encode(), out_path.encode(), C.byref(nr))
+        if rc:
+            raise RuntimeError("oracle crb rc=%d" % rc)
+        return nr.value
+
+    def extract(self, bam, tag, type_, out_path):
+        """-> (total_count as the reference prints it, valid_count)"""
+        t, v = C.c_uint64(), C.c_uint64()
+        rc = self.lib.oracle_extract(bam.encode(), tag.encode(), type_, out_path.encode(), C.byref(t), C.byref(v))
+        if rc:
+            raise RuntimeError("oracle extract rc=%d" % rc)
+        return t.value, v.value
 
 
 _o = None

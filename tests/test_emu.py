@@ -95,3 +95,26 @@ def test_emu_bgzf_crc32_check(emu_lib):
     ) % (ROOT, os.path.join(ROOT, "tests"))
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FASTF_GPU_LIB=emu_lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_emu_crb_extract_golden(emu_lib):
+    """`crb` and `extract` (fastf_taghist_gpu + host pre-order) against the outputs of the unmodified reference (tests/golden/tags)"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tags_cases.py")], env=dict(os.environ, FASTF_GPU_LIB=emu_lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.count("ok ") == 15, r.stdout[-2000:]
+
+
+def test_emu_c_host_cli_crb_extract(emu_lib, tmp_path):
+    """the C host's crb / extract subcommands (option parsing, BST pre-order, gz / csv writers, stdout lines) on the emulator build"""
+    import gzip
+    from fastf_b200 import build
+    cli = build.build_cli(emu=True)
+    g = os.path.join(ROOT, "tests", "golden", "tags")
+    r = subprocess.run([cli, "crb", "-b", os.path.join(g, "tags.bam"), "--out", "o.gz"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.splitlines() == ["Processed all 904 reads", "Writing to file...", "Done."], r.stdout
+    assert gzip.open(tmp_path / "o.gz", "rb").read() == gzip.open(os.path.join(g, "expect_tags_crb.txt.gz"), "rb").read()
+    r = subprocess.run([cli, "extract", "-b", os.path.join(g, "tags.bam"), "-t", "AS", "-T", "1"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.splitlines() == ["Processed all 1808 reads", "Valid reads: 900"], r.stdout
+    assert open(tmp_path / "tag_summary.csv", "rb").read() == gzip.open(os.path.join(g, "expect_tags_extract_AS_1.csv.gz"), "rb").read()
+    # where the reference dereferences NULL (string extraction of an integer tag) this build refuses
+    r = subprocess.run([cli, "extract", "-b", os.path.join(g, "tags.bam"), "-t", "NH"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 1 and "tag-not-a-string" in r.stdout

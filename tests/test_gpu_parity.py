@@ -434,3 +434,61 @@ def test_bam2db_two_gpus_equal_reference_and_one_gpu(gpu_ctx, synth, oracle, tmp
         assert a == open(str(ora / f[:-3]), "rb").read(), f
     d1, d2 = db_digest(str(one / "x.db")), db_digest(str(two / "x.db"))
     assert d1 == d2
+
+
+# ---- crb / extract ----
+def _tags_cases():
+    import tags_cases
+    return tags_cases.cases()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", _tags_cases(), ids=lambda c: c["name"])
+def test_crb_extract_golden_files(gpu_ctx, case, tmp_path):
+    """outputs recorded from the unmodified reference (scripts/make_golden_tags.py), byte for byte"""
+    import tags_cases
+    tags_cases.run_case(gpu_ctx, case, str(tmp_path))
+
+
+@pytest.mark.gpu
+def test_crb_extract_match_oracle_on_synthetic_bam(gpu_ctx, oracle, synth, tmp_path):
+    """300k reads, 2000 cells: crb (pairs), extract of a high-cardinality string tag (UB: nearly every read distinct), of GX and of two
+    integer tags, against the oracle; exercises the 64-bit hash grouping + byte-for-byte verification at scale"""
+    from fastf_b200 import tags_host as T
+    paths, _ = synth.write_bam_set(str(tmp_path), n_reads=300000, n_cells=2000, n_genes=3000, seed=8)
+    assert T.crb(gpu_ctx, paths["bam"], str(tmp_path / "crb.gz")) == oracle.crb(paths["bam"], str(tmp_path / "crb.txt"))
+    assert gzip.open(tmp_path / "crb.gz", "rb").read() == open(tmp_path / "crb.txt", "rb").read()
+    for tag, typ in (("UB", 0), ("GX", 0), ("CB", 0), ("xf", 1), ("NH", 1), ("ZZ", 0)):
+        got = T.extract_bam(gpu_ctx, paths["bam"], tag, typ, str(tmp_path))
+        assert got == oracle.extract(paths["bam"], tag, typ, str(tmp_path / "o.csv")), tag
+        assert open(tmp_path / "tag_summary.csv", "rb").read() == open(tmp_path / "o.csv", "rb").read(), tag
+
+
+@pytest.mark.gpu
+def test_crb_extract_refuse_what_crashes_the_reference(gpu_ctx, tmp_path):
+    """string extraction of a non-string tag and CB without CR make the reference dereference NULL (src/extract.c:97-100,186): refused loudly"""
+    from fastf_b200 import tags_host as T, _lib
+    import bamgen
+    recs = [bamgen.record("a", [bamgen.aux_Z("CB", "ACGT-1"), bamgen.aux_Z("CR", "ACGT"), bamgen.aux_int("NH", "C", 1)]),
+            bamgen.record("b", [bamgen.aux_Z("CB", "ACGT-1"), bamgen.aux_int("NH", "C", 1)])]
+    p = str(tmp_path / "x.bam")
+    open(p, "wb").write(bamgen.bgzf_file(bamgen.pack_records(bamgen.bam_header(), recs)))
+    with pytest.raises(_lib.FastfError, match="tag-not-a-string"):
+        T.crb(gpu_ctx, p, str(tmp_path / "o.gz"))
+    with pytest.raises(_lib.FastfError, match="tag-not-a-string"):
+        T.extract_bam(gpu_ctx, p, "NH", 0, str(tmp_path))
+    assert T.extract_bam(gpu_ctx, p, "NH", 1, str(tmp_path)) == (4, 2)
+
+
+@pytest.mark.gpu
+def test_c_cli_crb_extract_golden(gpu_ctx, tmp_path):
+    import subprocess
+    from fastf_b200 import build
+    cli = build.build_cli()
+    g = os.path.join(os.path.dirname(__file__), "golden", "tags")
+    r = subprocess.run([cli, "crb", "-b", os.path.join(g, "tags.bam"), "-o", "o.gz"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.splitlines() == ["Processed all 904 reads", "Writing to file...", "Done."], r.stdout
+    assert gzip.open(tmp_path / "o.gz", "rb").read() == gzip.open(os.path.join(g, "expect_tags_crb.txt.gz"), "rb").read()
+    r = subprocess.run([cli, "extract", "-b", os.path.join(g, "tags.bam"), "-t", "GX"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.splitlines() == ["Processed all 1808 reads", "Valid reads: 902"], r.stdout
+    assert open(tmp_path / "tag_summary.csv", "rb").read() == gzip.open(os.path.join(g, "expect_tags_extract_GX_0.csv.gz"), "rb").read()
