@@ -187,7 +187,8 @@ def main():
     ap.add_argument("--chunk-mb", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="bam2db", choices=["bam2db", "freq"], help="bam2db = BASELINE.json configs[2] (the headline); freq = configs[1] (use --reads 100000000)")
+    ap.add_argument("--depth-sweep", action="store_true", help="after the main line: -r 0.1..1.0 over the same resident input (BASELINE.json configs[4])")
+    ap.add_argument("--workload", default="bam2db", choices=["bam2db", "freq", "crb", "extract"], help="bam2db = BASELINE.json configs[2] (the headline); freq = configs[1] (use --reads 100000000)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -227,6 +228,25 @@ def main():
                           "cpu_baseline": {"value": v, "unit": "reads/s", "cores": 1, "kind": kind, "sample": sample, "cpu": cpu_model(), "host_cores": threads},
                           "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
+    if args.impl == "reference" and args.workload in ("crb", "extract"):
+        if rank != 0:
+            return 0
+        base = make_base(min(args.base_reads, args.ref_sample_reads), threads)
+        tmp = tempfile.mkdtemp(prefix="fastf_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            paths, _ = write_inputs(base, tmp)
+            times = [tags_reference_cli(args.workload, paths["bam"], tmp)[0] for _ in range(args.warmup + args.steps)][args.warmup:]
+            kind = tags_reference_cli(args.workload, paths["bam"], tmp, dry=True)[1]
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        ms = 1e3 * sum(times) / len(times)
+        v = base["reads"] / (ms / 1e3)
+        sample = f"{base['reads']}-read synthetic BAM per step (whole run of the reference CLI `{TAGS_CMD[args.workload]}`; wall clock)"
+        print(json.dumps({"impl": "reference", "metric": args.workload + " reads/sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": {"workload": args.workload + " (SURVEY 8f)", "sample": sample},
+                          "cpu_baseline": {"value": v, "unit": "reads/s", "cores": 1, "kind": kind, "sample": sample, "cpu": cpu_model(), "host_cores": threads},
+                          "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
     if args.impl == "reference":
         if rank != 0:
             return 0
@@ -258,6 +278,10 @@ def main():
         if args.reads == 500_000_000:
             args.reads = 100_000_000
         return bench_freq(args)
+    if args.workload in ("crb", "extract"):
+        if args.reads == 500_000_000:
+            args.reads = 32_000_000
+        return bench_tags(args)
 
     # ------------------------------------------------------------------ our arm
     import torch
@@ -327,8 +351,10 @@ def main():
         HW = 0x100   # FASTF_INFLATE_HW_ENGINE
         engine = {"lanes": args.lanes | (HW if args.engine == "hw" else 0)}
 
+        rate = {"depth": RATE_DEPTH}
+
         def one_job(device_resident, want_copy=False):
-            with B.Bam2dbJob(ctx, inputs, RATE_DEPTH, SEED, want_rows=False, inflate_lanes=engine["lanes"], chunk_inflated_bytes=chunk, headerless=(rank != 0)) as job:
+            with B.Bam2dbJob(ctx, inputs, rate["depth"], SEED, want_rows=False, inflate_lanes=engine["lanes"], chunk_inflated_bytes=chunk, headerless=(rank != 0)) as job:
                 for t in range(tiles):
                     if device_resident:
                         lo = 0 if (t == 0 and rank == 0) else rec_lo
@@ -390,6 +416,27 @@ def main():
             d2h = int(estats[-1].get("nnz") or 0) * 12 + 64
             e2e = {"value": world * reads_per_step / (e_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(tiles * comp_rec_bytes + hdr_end), "d2h_bytes_per_step": d2h,
                    "ms_per_step": e_ms, "steps": args.e2e_steps, "timing": "host wall clock around begin..finish (pinned host BGZF bytes in, COO out)"}
+        sweep = None
+        if args.depth_sweep:
+            # BASELINE.json configs[4]: -r 0.1 .. 1.0 at a fixed seed over the same resident input; per rate one warm-up and one timed job
+            sweep = []
+            for r10 in range(1, 11):
+                rate["depth"] = r10 / 10.0
+                _, sst, _, _, sdev = timed(True, 1, 1)
+                sms = sdev
+                if dist:
+                    tt = torch.tensor([sms], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    sms = float(tt[0])
+                q = sst[-1]
+                row = {"rate_depth": rate["depth"], "reads_per_s": world * reads_per_step / (sms / 1e3), "ms_per_job": sms, "sampled": q.get("sampled"), "valid": q.get("valid"), "nnz": q.get("nnz")}
+                if world == 1:
+                    row.update({"ms_sample": round(q["ms_sample"], 3), "ms_sort": round(q["ms_sort"], 3), "ms_count": round(q["ms_count"], 3),
+                                "sample_dedup_keys_per_s": (q["valid"] / ((q["ms_sample"] + q["ms_sort"] + q["ms_count"]) * 1e-3)) if q["valid"] else None})
+                else:
+                    row["exchanged_keys"] = q.get("exchanged_keys")
+                sweep.append(row)
+            rate["depth"] = RATE_DEPTH
         hw_extra = None
         if args.engine == "sm" and not args.no_hw_extra:
             # the same job with BGZF inflate on the B200 hardware decompression engine instead of the SM kernel (reported beside the main line)
@@ -440,6 +487,8 @@ def main():
                              "traffic": 11.396e9 if (args.engine == "sm" and args.lanes == 0 and chunk == 0) else None, "traffic_source": "profiles/r01_v7_ncu_inflate_tps.txt (9.202 GB read + 2.194 GB written per 2 GiB-chunk launch)",
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_launch, "ms_per_launch": infl_ms_launch},
                 "stages": stages, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "inflate_engine": args.engine, "hw_decompress_engine": hw_extra}
+        if sweep is not None:
+            line["depth_sweep"] = sweep
         if not args.no_cpu_baseline:
             d2 = os.path.join(tmp, "refin")
             os.makedirs(d2, exist_ok=True)
@@ -549,6 +598,87 @@ def bench_freq(args):
             dt = time.time() - t0
             line["cpu_baseline"] = {"value": sub.n_reads / dt, "unit": "reads/s", "cores": 1, "kind": kind, "cpu": cpu_model(), "host_cores": threads,
                                     "sample": f"one run of the reference CLI `freq -l 16 -u 12` on {sub.n_reads} reads of the same shape ({dt:.1f}s wall)"}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    print(json.dumps(line))
+    return 0
+
+
+TAGS_CMD = {"crb": "crb -b BAM -o out.gz", "extract": "extract -b BAM -t GX -T 0"}
+
+
+def tags_reference_cli(workload, bam, tmp, dry=False):
+    """one run of the reference's crb / extract (oracle/_ref/fastF_ref, else the oracle port) on bam -> (seconds, kind)"""
+    ref = os.path.join(ROOT, "oracle", "_ref", "fastF_ref")
+    kind = "reference" if os.path.exists(ref) else "port"
+    if dry:
+        return 0.0, kind
+    if kind == "reference":
+        cmd = [ref, "crb", "-b", bam, "-o", os.path.join(tmp, "ref_crb.gz")] if workload == "crb" else [ref, "extract", "-b", bam, "-t", "GX", "-T", "0"]
+    else:
+        cli = os.path.join(ROOT, "oracle", "_build", "oracle_cli")
+        cmd = [cli, "crb", bam, os.path.join(tmp, "ref_crb.txt")] if workload == "crb" else [cli, "extract", bam, "GX", "0", os.path.join(tmp, "ref_extract.csv")]
+    t0 = time.time()
+    subprocess.run(cmd, check=True, cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return time.time() - t0, kind
+
+
+def bench_tags(args):
+    """`fastF crb` / `fastF extract -t GX` on the synthetic 10x-v3 BAM: one step = one fastf_taghist_gpu call over the whole
+    BGZF image in pinned host memory.  value = reads / sum of the device stage clocks (inflate, tag kernel, sort, RLE + verification;
+    the H2D copy is outside); e2e = reads / wall clock of the call (H2D of the file, groups + value strings back)."""
+    from fastf_b200 import _lib
+    threads = os.cpu_count() or 1
+    ctx = _lib.Context(0)
+    lib = ctx.lib
+    base = make_base(min(args.base_reads, args.reads), threads)
+    bam = np.frombuffer(base["bam"], dtype=np.uint8)
+    hptr = C.c_void_p()
+    ctx.check(lib.fastf_host_alloc(ctx.h, bam.size, C.byref(hptr)), "host_alloc")
+    C.memmove(hptr, bam.ctypes.data, bam.size)
+    tag_a, tag_b = (b"CB", b"CR") if args.workload == "crb" else (b"GX", None)
+
+    def one():
+        res = _lib.TaghistResult()
+        ctx.check(lib.fastf_taghist_gpu(ctx.h, hptr, bam.size, tag_a, 0, tag_b, args.lanes, C.byref(res)), "taghist")
+        st_ = {f: getattr(res, f) for f, t_ in _lib.TaghistResult._fields_ if t_ in (C.c_uint64, C.c_uint32, C.c_float)}
+        lib.fastf_taghist_result_free(C.byref(res))
+        return st_
+
+    for _ in range(max(args.warmup, 1)):
+        one()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = ctx.launches
+    t0 = time.time()
+    sts = [one() for _ in range(args.steps)]
+    wall = time.time() - t0
+    clocks = sampler.stop()
+    launches = ctx.launches - l0
+    st = sts[-1]
+    dev_ms = sum(sum(x["ms_" + k] for k in ("inflate", "tags", "sort", "rle")) for x in sts) / args.steps
+    n_reads = int(st["n_records"])
+    peak, peak_src = measured_peak()
+    alg = st["compressed_bytes"] + st["inflated_bytes"]
+    ach = alg / (st["ms_inflate"] * 1e-3) / 1e9
+    line = {"metric": args.workload + " reads/sec (device-timed)", "value": n_reads / (dev_ms / 1e3), "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{args.workload} ({TAGS_CMD[args.workload]}) on the synthetic 10x-v3 BAM: {n_reads} reads, {N_CELLS} cells, {N_GENES} genes (SURVEY 8f)",
+                       "l2": "inputs larger than L2", "counters": {k: st[k] for k in ("n_records", "n_hits", "n_groups", "n_blocks", "hash_rounds")}},
+            "roofline": {"bound": "hbm", "kernel": "fastf_bgzf_inflate_tps_kernel<16,24>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg, "ms_per_launch": st["ms_inflate"]},
+            "stages": {k: {"ms": round(st["ms_" + k], 3)} for k in ("inflate", "tags", "sort", "rle")}, "gpu_launches": launches, "clocks": clocks,
+            "e2e": {"value": n_reads / (wall / args.steps), "unit": "reads/s", "h2d_bytes_per_step": int(bam.size), "d2h_bytes_per_step": int(st["n_groups"] * 40 + st["strings_bytes"]),
+                    "ms_per_step": 1e3 * wall / args.steps, "steps": args.steps, "timing": "host wall clock around fastf_taghist_gpu (pinned host BAM bytes in, groups + value strings out)"}}
+    line["stages"]["tags"]["alg_GBps"] = round(st["inflated_bytes"] / (st["ms_tags"] * 1e-3) / 1e9, 1) if st["ms_tags"] > 0 else None
+    if not args.no_cpu_baseline:
+        tmp = tempfile.mkdtemp(prefix="fastf_tags_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            sub = make_base(min(base["reads"], 2_000_000), threads) if base["reads"] > 2_000_000 else base
+            paths, _ = write_inputs(sub, tmp)
+            dt, kind = tags_reference_cli(args.workload, paths["bam"], tmp)
+            line["cpu_baseline"] = {"value": sub["reads"] / dt, "unit": "reads/s", "cores": 1, "kind": kind, "cpu": cpu_model(), "host_cores": threads,
+                                    "sample": f"one run of the reference CLI `{TAGS_CMD[args.workload]}` on {sub['reads']} reads of the same shape ({dt:.1f}s wall)"}
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
     print(json.dumps(line))
