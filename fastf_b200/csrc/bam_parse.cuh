@@ -63,6 +63,14 @@ template <class Acc> __device__ __forceinline__ u64 fastf_find_nul(const Acc &A,
     }
     return rend;
 }
+// the four bytes at off .. off+3 (any alignment), all of which must be readable: two aligned word loads instead of four byte loads
+template <class Acc> __device__ __forceinline__ u32 fastf_acc_4bytes(const Acc &A, u64 off)
+{
+    const u32 sh = 8u * (u32)(off & 3ull);
+    const u32 lo = A.word(off);
+    if (sh == 0) return lo;
+    return (lo >> sh) | (A.word(off + 3) << (32u - sh));
+}
 template <class Acc> __device__ __forceinline__ u32 fastf_acc_u16(const Acc &A, u64 off) { return A.byte(off) | (A.byte(off + 1) << 8); }
 template <class Acc> __device__ __forceinline__ u32 fastf_acc_u32(const Acc &A, u64 off) { return A.byte(off) | (A.byte(off + 1) << 8) | (A.byte(off + 2) << 16) | (A.byte(off + 3) << 24); }
 
@@ -258,10 +266,11 @@ __device__ __forceinline__ u32 fastf_table_lookup_lane(const FastfStrTableView &
             // pool strings start on 4-byte boundaries (FastfStrTableHost::insert): compare word-wise
             const u32 *pw = reinterpret_cast<const u32 *>(T.pool + raw.y);
             bool same = true;
-            for (u32 i = 0; i < len && same; i += 4) {
+            u32 i = 0;
+            for (; i + 4 <= len && same; i += 4) same = pw[i >> 2] == fastf_acc_4bytes(A, s + i);
+            if (same && i < len) {
                 const u32 w = pw[i >> 2];
-                const u32 m = len - i < 4u ? len - i : 4u;
-                for (u32 b = 0; b < m; b++) same = same && (((w >> (8u * b)) & 255u) == A.byte(s + i + b));
+                for (u32 b = 0; i + b < len; b++) same = same && (((w >> (8u * b)) & 255u) == A.byte(s + i + b));
             }
             if (same) return raw.w;
         }
