@@ -291,8 +291,13 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dist = None
+    saved_stdout = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL prints its version banner on stdout when NCCL_DEBUG asks for it: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.Context(local_rank)
     lib = ctx.lib
@@ -496,6 +501,9 @@ def main():
             dt, total, kind = run_reference_cli(p2, os.path.join(tmp, "refout"), RATE_CELL, RATE_DEPTH, SEED)
             line["cpu_baseline"] = {"value": total / dt, "unit": "reads/s", "cores": 1, "kind": kind, "cpu": cpu_model(), "host_cores": threads,
                                     "sample": f"one run of the unmodified reference CLI on a {total}-read prefix of the same synthetic BAM ({dt:.1f}s wall; inflate via zlib shim, sqlite on /dev/shm)"}
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line))
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
