@@ -61,6 +61,9 @@
 #ifndef FASTF_TPS_PREFETCH2
 #define FASTF_TPS_PREFETCH2 0
 #endif
+#ifndef FASTF_TPS_FAR_LEN
+#define FASTF_TPS_FAR_LEN 32u         // longest match handled in the far group (32 or 64: one or two bytes per lane)
+#endif
 #ifndef FASTF_TPS_FAR
 #define FASTF_TPS_FAR 4              // far matches whose source loads are in flight together
 #endif
@@ -374,7 +377,7 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
     u32 farm, slowm;
     {
         const u32 len = tok & 511u, dist = (tok >> 9) & 0xffffu;
-        const bool far = is_match && len <= 32u && off + len <= dist;   // source ends before the batch starts (implies dist >= len)
+        const bool far = is_match && len <= FASTF_TPS_FAR_LEN && off + len <= dist;   // source ends before the batch starts (implies dist >= len)
         farm = __ballot_sync(FASTF_FULL_MASK, far);
         slowm = __ballot_sync(FASTF_FULL_MASK, is_match && !far);
     }
@@ -392,11 +395,18 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
                 const u32 len = t & 511u, dist = (t >> 9) & 0xffffu;
                 dpos[u] = opos + o; dlen[u] = len;
                 if (lane < len) dbyte[u] = out[opos + o - dist + lane];
+#if FASTF_TPS_FAR_LEN > 32
+                if (lane + 32u < len) dbyte[u] |= (u32)out[opos + o - dist + lane + 32u] << 8;
+#endif
             }
         }
 #pragma unroll
-        for (int u = 0; u < FASTF_TPS_FAR; u++)
+        for (int u = 0; u < FASTF_TPS_FAR; u++) {
             if (lane < dlen[u]) out[dpos[u] + lane] = (u8)dbyte[u];
+#if FASTF_TPS_FAR_LEN > 32
+            if (lane + 32u < dlen[u]) out[dpos[u] + lane + 32u] = (u8)(dbyte[u] >> 8);
+#endif
+        }
     }
     while (slowm) {
         const u32 m = (u32)__ffs((int)slowm) - 1u;
