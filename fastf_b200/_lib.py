@@ -93,6 +93,7 @@ _SIGS = {
     "fastf_freq_result_free": (None, [C.POINTER(FreqResult)]),
     "fastf_taghist_gpu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(TaghistResult)]),
     "fastf_taghist_result_free": (None, [C.POINTER(TaghistResult)]),
+    "fastf_taghist_test_hooks": (None, [C.c_void_p, C.c_uint64, C.c_uint64]),
 }
 EXPORTS = sorted(_SIGS)
 

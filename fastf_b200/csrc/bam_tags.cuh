@@ -20,6 +20,7 @@ struct FastfTagQuery {
     u32 b0, b1;        // tag B (pair mode), b0 = 0: none
     u32 mode;          // FASTF_TAG_MODE_*
     u64 seed;          // hash seed
+    u64 key_mask;      // ~0; tests AND the keys with less to force collisions
 };
 
 __device__ __forceinline__ u64 fastf_hash_mix(u64 h)
@@ -103,7 +104,7 @@ __device__ __forceinline__ u32 fastf_tag_record(const Acc &A, u64 rec, u64 rend,
     if (ha.len > 0xffffu || hb.len > 0xffffu) return 3;
     u64 h = fastf_hash_bytes(A, ha.off, ha.len, 14695981039346656037ull ^ Q.seed);
     if (Q.b0) h = fastf_hash_bytes(A, hb.off, hb.len, h);
-    *key = h;
+    *key = h & Q.key_mask;
     *loc_a = (ha.off << 16) | ha.len;
     *loc_b = Q.b0 ? ((hb.off << 16) | hb.len) : 0;
     return 1;

@@ -202,9 +202,12 @@ typedef struct {
     uint32_t hash_rounds;       /* 1 unless two different values shared a 64-bit hash (detected byte for byte, re-run with another seed) */
     float ms_inflate, ms_tags, ms_sort, ms_rle, ms_device_total;
 } fastf_taghist_result;
-/* bgzf_bytes: the whole BAM file in host memory; tag_b = NULL for a single tag */
+/* bgzf_bytes: the whole BAM file in host memory; tag_b = NULL for a single tag.  The file streams through HBM in chunks of whole
+ * blocks; each chunk is grouped on the device and the per-chunk groups are merged on the host. */
 int fastf_taghist_gpu(fastf_ctx *ctx, const void *bgzf_bytes, size_t n, const char *tag_a, uint32_t mode, const char *tag_b, uint32_t inflate_lanes, fastf_taghist_result *res);
 void fastf_taghist_result_free(fastf_taghist_result *res);
+/* test hooks (0, 0 = production): blocks per streaming chunk, and a mask ANDed onto the first round's hash keys to force collisions */
+void fastf_taghist_test_hooks(fastf_ctx *ctx, uint64_t chunk_blocks, uint64_t round0_key_mask);
 
 #ifdef __cplusplus
 }

@@ -39,3 +39,14 @@ if __name__ == "__main__":   # emulator entry: FASTF_GPU_LIB points at the SIMT-
                 continue
             run_case(ctx, c, tmp)
             print("ok", c["name"])
+        # streaming: three blocks per chunk (cross-chunk merge of counts and first occurrences); forced hash collisions in round 0
+        ctx.lib.fastf_taghist_test_hooks(ctx.h, 3, 0xff)
+        for c in cases():
+            if c["input"] == "tags.bam":
+                run_case(ctx, c, tmp)
+                print("ok-streamed-collided", c["name"])
+        from fastf_b200 import tags_host as T
+        import numpy as np
+        st, _ = T.taghist(ctx, np.fromfile(os.path.join(D, "tags.bam"), dtype=np.uint8), "CB", 0, "CR")
+        assert st["hash_rounds"] == 2, st
+        ctx.lib.fastf_taghist_test_hooks(ctx.h, 0, 0)

@@ -100,7 +100,7 @@ def test_emu_bgzf_crc32_check(emu_lib):
 def test_emu_crb_extract_golden(emu_lib):
     """`crb` and `extract` (fastf_taghist_gpu + host pre-order) against the outputs of the unmodified reference (tests/golden/tags)"""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tags_cases.py")], env=dict(os.environ, FASTF_GPU_LIB=emu_lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
-    assert r.returncode == 0 and r.stdout.count("ok ") == 15, r.stdout[-2000:]
+    assert r.returncode == 0 and r.stdout.count("ok ") == 15 and r.stdout.count("ok-streamed-collided") == 9, r.stdout[-2000:]
 
 
 def test_emu_c_host_cli_crb_extract(emu_lib, tmp_path):

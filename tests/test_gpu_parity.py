@@ -492,3 +492,27 @@ def test_c_cli_crb_extract_golden(gpu_ctx, tmp_path):
     r = subprocess.run([cli, "extract", "-b", os.path.join(g, "tags.bam"), "-t", "GX"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.splitlines() == ["Processed all 1808 reads", "Valid reads: 902"], r.stdout
     assert open(tmp_path / "tag_summary.csv", "rb").read() == gzip.open(os.path.join(g, "expect_tags_extract_GX_0.csv.gz"), "rb").read()
+
+
+@pytest.mark.gpu
+def test_crb_extract_streamed_chunks_and_forced_collisions(gpu_ctx, oracle, synth, tmp_path):
+    """the file streams through HBM in chunks (test hook: 5 blocks per chunk) whose groups are merged on the host; a mask on the first
+    round's hash keys forces collisions, which the byte-for-byte verification must catch (second round wins)"""
+    import numpy as np
+    import tags_cases
+    from fastf_b200 import tags_host as T
+    paths, _ = synth.write_bam_set(str(tmp_path), n_reads=60000, n_cells=300, n_genes=500, seed=12)
+    try:
+        gpu_ctx.lib.fastf_taghist_test_hooks(gpu_ctx.h, 5, 0x3ff)
+        for case in tags_cases.cases():
+            if case["input"] == "tags.bam":
+                tags_cases.run_case(gpu_ctx, case, str(tmp_path))
+        st, _ = T.taghist(gpu_ctx, np.fromfile(paths["bam"], dtype=np.uint8), "CB", 0, "CR")
+        assert st["hash_rounds"] == 2 and st["n_blocks"] > 20
+        assert T.crb(gpu_ctx, paths["bam"], str(tmp_path / "crb.gz")) == oracle.crb(paths["bam"], str(tmp_path / "crb.txt"))
+        assert gzip.open(tmp_path / "crb.gz", "rb").read() == open(tmp_path / "crb.txt", "rb").read()
+        for tag, typ in (("UB", 0), ("xf", 1)):
+            assert T.extract_bam(gpu_ctx, paths["bam"], tag, typ, str(tmp_path)) == oracle.extract(paths["bam"], tag, typ, str(tmp_path / "o.csv"))
+            assert open(tmp_path / "tag_summary.csv", "rb").read() == open(tmp_path / "o.csv", "rb").read(), tag
+    finally:
+        gpu_ctx.lib.fastf_taghist_test_hooks(gpu_ctx.h, 0, 0)
