@@ -1999,10 +1999,19 @@ extern "C" int fastf_taghist_gpu(fastf_ctx *ctx, const void *host_bytes, size_t 
         Q.mode = mode;
         // The file streams through HBM in chunks of whole blocks (two full rounds of the persistent inflate kernel each); every chunk
         // is grouped on the device, the per-chunk groups are merged here.
-        const size_t chunk_blocks = std::max<size_t>(1, ctx->taghist_chunk_blocks ? ctx->taghist_chunk_blocks : 2ull * (size_t)ctx->n_sm * FASTF_TPS_STREAMS);
+        size_t chunk_blocks = std::max<size_t>(1, ctx->taghist_chunk_blocks ? ctx->taghist_chunk_blocks : 2ull * (size_t)ctx->n_sm * FASTF_TPS_STREAMS);
+        if (!ctx->taghist_chunk_blocks) {
+            // a file whose inflated bytes, staging planes (worst case 2/3 of them) and key arrays fit HBM comfortably goes through in ONE
+            // chunk: no host-side merge at all
+            u64 infl_total = 0;
+            for (auto &b : all) infl_total += b.isize;
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (double)infl_total * 2.6 + (double)n < 0.7 * (double)free_b && all.size() < 0xffffffffull) chunk_blocks = all.size();
+        }
         u64 hit_base = 0;
         bool first_chunk = true;
         res->hash_rounds = 1;
+        smap.reserve(1u << 16);
         for (size_t c0 = 0; c0 < all.size() || first_chunk; c0 += chunk_blocks) {
             const size_t c1 = std::min(all.size(), c0 + chunk_blocks);
             part.assign(all.begin() + c0, all.begin() + c1);
