@@ -68,11 +68,15 @@
 #define FASTF_TPS_FAR 4              // far matches whose source loads are in flight together
 #endif
 
-// 16-bit table entry: bits 0-3 code length (0 = longer than the table), bits 4-5 kind, bits 6-15 payload
+// 16-bit table entry: bits 0-3 code length (0 = longer than the table), bits 4-5 kind, bits 8-15 payload.  A slot whose code is
+// longer than the table holds FASTF_T16_LONG (length 0, kind BAD), so that "literal resolved by the table" is the single test
+// (e & 0x30) == 0, and a literal byte moves into its token with one masked OR (e & 0xff00).
 #define FASTF_T16_LIT 0u     // payload = literal byte / code-length symbol
 #define FASTF_T16_SYM 1u     // payload = length symbol - 257, or distance symbol
 #define FASTF_T16_EOB 2u
 #define FASTF_T16_BAD 3u
+#define FASTF_T16_LONG (FASTF_T16_BAD << 4)
+#define FASTF_T16_IS_TABLE_LIT(e) (((e) & 0x30u) == 0u)
 // tokens
 #define FASTF_TOK_LIT 0u             // bits 0-23 up to three literal bytes (first in bits 0-7), bits 24-25 their number
 #define FASTF_TOK_MATCH (1u << 30)   // bits 0-8 length, bits 9-24 distance
@@ -83,14 +87,14 @@ enum { FASTF_TPS_NEXT = 0, FASTF_TPS_RUN = 1, FASTF_TPS_BUILD = 2, FASTF_TPS_DON
 struct FastfTpsStream {
     u16 lit[1 << FASTF_TPS_LBITS];
     u16 dist[1 << FASTF_TPS_DBITS];
-    u16 lit_cnt[16];
-    u16 dist_cnt[16];
+    alignas(16) u16 lit_cnt[16];    // codes longer than the table: range limits [0, 8) and index offsets [8, 16) (fastf_tps_build)
+    alignas(16) u16 dist_cnt[16];
     u32 ring[FASTF_TPS_RING];
     // control block (volatile accesses; every hand-over is fenced)
     u32 state, wr, rd, last;
     u32 bitpos_lo, bitpos_hi;        // absolute bit offset of the next unread bit inside `comp`
     u32 pos, isize;                  // decoder's output position / block size
-    u32 lit_walk, dist_walk;         // canonical-walk start for codes longer than the table: first code << 16 | index
+    u32 spare0, spare1;
     u32 blk, opos;                   // service side: block index, bytes written
     u32 inend_lo, inend_hi;          // absolute bit offset of the end of the payload
     u32 obase_lo, obase_hi;          // offset of the block in the inflated buffer
@@ -131,22 +135,22 @@ __device__ __forceinline__ void fastf_stv(u32 *p, u32 v) { *(volatile u32 *)p = 
 
 __device__ __forceinline__ u32 fastf_make16(u32 alpha, u32 sym)
 {
-    if (alpha == FASTF_ALPHA_PLAIN) return (FASTF_T16_LIT << 4) | (sym << 6);
+    if (alpha == FASTF_ALPHA_PLAIN) return (FASTF_T16_LIT << 4) | (sym << 8);
     if (alpha == FASTF_ALPHA_LITLEN) {
-        if (sym < 256) return (FASTF_T16_LIT << 4) | (sym << 6);
+        if (sym < 256) return (FASTF_T16_LIT << 4) | (sym << 8);
         if (sym == 256) return FASTF_T16_EOB << 4;
         if (sym > 285) return FASTF_T16_BAD << 4;
-        return (FASTF_T16_SYM << 4) | ((sym - 257) << 6);
+        return (FASTF_T16_SYM << 4) | ((sym - 257) << 8);
     }
     if (sym >= 30) return FASTF_T16_BAD << 4;
-    return (FASTF_T16_SYM << 4) | (sym << 6);
+    return (FASTF_T16_SYM << 4) | (sym << 8);
 }
 
 // Cooperative (32 lanes, lock step) construction of one 16-bit decode table.  Returns non-zero for an invalid code.
 // *walk = (first canonical code of length tbits+1) << 16 | (index of its first symbol in sorted[]).
 __device__ __forceinline__ u32 fastf_tps_build(u32 alpha, const u8 *lens, u32 n, u16 *cnt, u16 *sorted, u16 *lut, u32 tbits, u16 *first, u16 *start, u32 *walk, u32 lane)
 {
-    for (u32 i = lane; i < (1u << tbits); i += 32) lut[i] = 0;
+    for (u32 i = lane; i < (1u << tbits); i += 32) lut[i] = FASTF_T16_LONG;
     u32 bad = 0, wk = 0;
     if (lane == 0) {
         for (u32 l = 0; l < 16; l++) cnt[l] = 0;
@@ -176,6 +180,16 @@ __device__ __forceinline__ u32 fastf_tps_build(u32 alpha, const u8 *lens, u32 n,
             }
         }
         first[0] = (u16)used;
+        // For the codes longer than the table the decoder needs, per length l = tbits+1+k: the left-aligned (15-bit) end of the
+        // length's code range (ranges of a canonical code follow one another in length order) and start[l] - first[l], the offset
+        // that turns a code into its index in sorted[].  They replace the counts in cnt[]: limits in [0, 8), offsets in [8, 16).
+        u16 lim[8], off[8];
+        for (u32 k = 0; k < 8; k++) {
+            const u32 l = tbits + 1 + k;
+            lim[k] = l <= 15 ? (u16)(((u32)first[l] + cnt[l]) << (15 - l)) : (u16)0xffff;
+            off[k] = l <= 15 ? (u16)((u32)start[l] - (u32)first[l]) : (u16)0;
+        }
+        for (u32 k = 0; k < 8; k++) { cnt[k] = lim[k]; cnt[8 + k] = off[k]; }
     }
     bad = __shfl_sync(FASTF_FULL_MASK, bad, 0);
     wk = __shfl_sync(FASTF_FULL_MASK, wk, 0);
@@ -197,23 +211,11 @@ __device__ __forceinline__ u32 fastf_tps_build(u32 alpha, const u8 *lens, u32 n,
     return 0;
 }
 
-// lock-step lookup used by the service warp while it reads the code-length code (7-bit table in the distance table's storage)
-__device__ __forceinline__ u32 fastf_tps_decode16(const FastfBitReader<32> &br, const u16 *lut, u32 tbits, const u16 *cnt, const u16 *sorted, u32 alpha)
+// lock-step lookup used by the service warp while it reads the code-length code (7-bit table in the distance table's storage;
+// code-length codes are at most 7 bits long, so every valid one is resolved by the table)
+__device__ __forceinline__ u32 fastf_tps_decode16(const FastfBitReader<32> &br, const u16 *lut, u32 tbits)
 {
-    u32 e = lut[(u32)br.buf & ((1u << tbits) - 1u)];
-    if (e & 15u) return e;
-    u32 code = 0, first = 0, index = 0;
-    u32 bits = (u32)br.buf;
-    for (u32 len = 1; len < 16; len++) {
-        code |= bits & 1u;
-        bits >>= 1;
-        u32 c = cnt[len];
-        if (code < first + c) return fastf_make16(alpha, fastf_ld_sorted(sorted + index + (code - first))) | len;
-        index += c;
-        first = (first + c) << 1;
-        code <<= 1;
-    }
-    return FASTF_T16_BAD << 4;
+    return lut[(u32)br.buf & ((1u << tbits) - 1u)];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -297,10 +299,10 @@ __device__ __forceinline__ void fastf_tps_setup(const FastfTpsArgs &A, FastfTpsS
             u32 i = 0, prev = 0;
             while (i < n) {
                 br.refill();
-                const u32 e = fastf_tps_decode16(br, S.dist, 7, S.dist_cnt, dist_sorted, FASTF_ALPHA_PLAIN);
+                const u32 e = fastf_tps_decode16(br, S.dist, 7);
                 if ((e & 15u) == 0) { err |= FASTF_ST_BAD_CODELENS; break; }
                 br.drop(e & 15u);
-                const u32 sym = e >> 6;
+                const u32 sym = e >> 8;
                 u32 rep, val;
                 if (sym < 16) { rep = 1; val = sym; prev = sym; }
                 else if (sym == 16) { if (i == 0) { err |= FASTF_ST_BAD_CODELENS; break; } rep = 3 + br.take(2); val = prev; }
@@ -322,7 +324,6 @@ __device__ __forceinline__ void fastf_tps_setup(const FastfTpsArgs &A, FastfTpsS
         bitpos = origin + consumed;
         if (lane == 0) {
             S.bitpos_lo = (u32)bitpos; S.bitpos_hi = (u32)(bitpos >> 32);
-            S.lit_walk = wl; S.dist_walk = wd;
             S.last = last; S.pos = opos; S.opos = opos;
             __threadfence_block();
             fastf_stv(&S.state, FASTF_TPS_RUN);
@@ -501,27 +502,21 @@ struct FastfTpsReader {
     __device__ __forceinline__ u64 bitpos() const { return base_bits + (u64)widx * 32u - nbits; }
 };
 
-// entry of a code longer than the primary table (canonical walk starting at length tbits + 1).  The per-length counts are
-// fetched up front (independent shared-memory loads) so that the walk itself is register arithmetic.
+// Entry of a code longer than the primary table.  lb = the stream's limit / offset array written by fastf_tps_build: the code's
+// length is TBITS + 1 + the number of length ranges that end at or below the next 15 stream bits.
 template <int TBITS>
-__device__ __forceinline__ u32 fastf_tps_walk(u64 buf, u32 walk, const u16 *cnt, const u16 *sorted, u32 alpha)
+__device__ __forceinline__ u32 fastf_tps_walk(u64 buf, const u16 *lb, const u16 *sorted, u32 alpha)
 {
     const u32 code15 = __brev((u32)buf) >> 17;   // the next 15 stream bits, first bit most significant
-    u32 c[15 - TBITS];
+    const uint4 L4 = *reinterpret_cast<const uint4 *>(lb);
+    const u32 w[4] = {L4.x, L4.y, L4.z, L4.w};
+    u32 k = 0;
 #pragma unroll
-    for (int k = 0; k < 15 - TBITS; k++) c[k] = cnt[TBITS + 1 + k];
-    u32 first = walk >> 16, index = walk & 0xffffu;
-    u32 found_len = 0, found_idx = 0;
-#pragma unroll
-    for (int k = 0; k < 15 - TBITS; k++) {
-        const u32 len = TBITS + 1 + k;
-        const u32 v = code15 >> (15u - len);
-        if (!found_len && v - first < c[k]) { found_len = len; found_idx = index + (v - first); }
-        index += c[k];
-        first = (first + c[k]) << 1;
-    }
-    if (!found_len) return FASTF_T16_BAD << 4;
-    return fastf_make16(alpha, fastf_ld_sorted(sorted + found_idx)) | found_len;
+    for (int i = 0; i < 15 - TBITS; i++) k += code15 >= ((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu));
+    if (k >= (u32)(15 - TBITS)) return FASTF_T16_BAD << 4;
+    const u32 len = (u32)TBITS + 1u + k;
+    const u32 idx = ((code15 >> (15u - len)) + (u32)lb[8 + k]) & 0xffffu;
+    return fastf_make16(alpha, fastf_ld_sorted(sorted + idx)) | len;
 }
 
 template <int L, int SVC>
@@ -554,7 +549,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
         const u16 *lit_sorted = sorted_base + (size_t)sidx * FASTF_TPS_SORTED_U16, *dist_sorted = lit_sorted + 288;
         FastfTpsReader br;
         bool have = false;
-        u32 wr = 0, rd_cache = 0, pos = 0, isize = 0, last = 0, lit_walk = 0, dist_walk = 0;
+        u32 wr = 0, rd_cache = 0, pos = 0, isize = 0, last = 0;
         u64 in_end = 0;
         for (;;) {
             if (!have) {
@@ -563,7 +558,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
                 if (st != FASTF_TPS_RUN) { fastf_spin_poll(); continue; }
                 __threadfence_block();
                 br.init(A.comp, A.comp_total, ((u64)S.bitpos_hi << 32) | S.bitpos_lo);
-                pos = S.pos; isize = S.isize; last = S.last; lit_walk = S.lit_walk; dist_walk = S.dist_walk;
+                pos = S.pos; isize = S.isize; last = S.last;
                 in_end = ((u64)S.inend_hi << 32) | S.inend_lo;
                 wr = S.wr;
                 have = true;
@@ -581,7 +576,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
             // Bit budget: a refill leaves >= 33 bits; 15 + 9 + 9 for the first triple, 27 for the second, 9 + 5 for a length.
             br.refill();
             u32 e = S.lit[(u32)br.buf & ((1u << FASTF_TPS_LBITS) - 1u)];
-            if ((e & 15u) == 0) e = fastf_tps_walk<FASTF_TPS_LBITS>(br.buf, lit_walk, S.lit_cnt, lit_sorted, FASTF_ALPHA_LITLEN);
+            if ((e & 15u) == 0) e = fastf_tps_walk<FASTF_TPS_LBITS>(br.buf, S.lit_cnt, lit_sorted, FASTF_ALPHA_LITLEN);
             u32 kind = (e >> 4) & 3u;
             u32 err = 0;
             const u32 wr0 = wr;
@@ -590,16 +585,16 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
 #pragma unroll
                 for (int triple = 0; triple < FASTF_TPS_TRIPLES; triple++) {
                     br.drop(e & 15u);
-                    u32 tok = e >> 6, cnt = 1;
+                    u32 tok = e >> 8, cnt = 1;
                     e = S.lit[(u32)br.buf & ((1u << FASTF_TPS_LBITS) - 1u)];
-                    if ((e & 63u) - 1u < 15u) {
+                    if (FASTF_T16_IS_TABLE_LIT(e)) {
                         br.drop(e & 15u);
-                        tok |= (e >> 6) << 8;
+                        tok |= e & 0xff00u;
                         cnt = 2;
                         e = S.lit[(u32)br.buf & ((1u << FASTF_TPS_LBITS) - 1u)];
-                        if ((e & 63u) - 1u < 15u) {
+                        if (FASTF_T16_IS_TABLE_LIT(e)) {
                             br.drop(e & 15u);
-                            tok |= (e >> 6) << 16;
+                            tok |= (e & 0xff00u) << 8;
                             cnt = 3;
                             br.refill();
                             e = S.lit[(u32)br.buf & ((1u << FASTF_TPS_LBITS) - 1u)];
@@ -609,23 +604,23 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
                     fastf_stv(&S.ring[wr & (FASTF_TPS_RING - 1u)], tok | (cnt << 24));
                     wr++;
                     pos += cnt;
-                    if (cnt < 3u || (e & 63u) - 1u >= 15u) break;
+                    if (cnt < 3u || !FASTF_T16_IS_TABLE_LIT(e)) break;
                 }
                 // what follows the literals: a length code inside the table joins this round, anything else waits for the next
-                kind = ((e & 63u) >> 4 == FASTF_T16_SYM && (e & 15u) != 0 && !err) ? (u32)FASTF_T16_SYM : 4u;
+                kind = (((e >> 4) & 3u) == FASTF_T16_SYM && !err) ? (u32)FASTF_T16_SYM : 4u;
                 if (kind == FASTF_T16_SYM) br.refill();
             }
             if (kind == FASTF_T16_SYM) {
                 br.drop(e & 15u);
-                const u32 K = G.lenK[e >> 6];
+                const u32 K = G.lenK[e >> 8];
                 const u32 len = (K >> 8) + br.take(K & 255u);
                 br.refill();
                 u32 d = S.dist[(u32)br.buf & ((1u << FASTF_TPS_DBITS) - 1u)];
-                if ((d & 15u) == 0) d = fastf_tps_walk<FASTF_TPS_DBITS>(br.buf, dist_walk, S.dist_cnt, dist_sorted, FASTF_ALPHA_DIST);
+                if ((d & 15u) == 0) d = fastf_tps_walk<FASTF_TPS_DBITS>(br.buf, S.dist_cnt, dist_sorted, FASTF_ALPHA_DIST);
                 if (((d >> 4) & 3u) != FASTF_T16_SYM) err = FASTF_ST_BAD_SYMBOL;
                 else {
                     br.drop(d & 15u);
-                    const u32 K2 = G.distK[d >> 6];
+                    const u32 K2 = G.distK[d >> 8];
                     const u32 dist = (K2 >> 8) + br.take(K2 & 255u);
                     if (dist > pos) err = FASTF_ST_BAD_DISTANCE;
                     else if (pos + len > isize) err = FASTF_ST_OUT_OVERFLOW;
