@@ -187,14 +187,18 @@ def main():
     ap.add_argument("--chunk-mb", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3], help="BASELINE.json configs[N] shape: 2 = 10k cells, -c 1.0 -r 0.3 (the headline); 3 = 50k cells, -c 0.2 -r 0.5 (the sharded 2 B-read case: --gpus 8 --reads 250000000)")
     ap.add_argument("--depth-sweep", action="store_true", help="after the main line: -r 0.1..1.0 over the same resident input (BASELINE.json configs[4])")
     ap.add_argument("--workload", default="bam2db", choices=["bam2db", "freq", "crb", "extract"], help="bam2db = BASELINE.json configs[2] (the headline); freq = configs[1] (use --reads 100000000)")
     args = ap.parse_args()
+    global N_CELLS, RATE_CELL, RATE_DEPTH
+    if args.config == 3:
+        N_CELLS, RATE_CELL, RATE_DEPTH = 50000, 0.2, 0.5
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     threads = os.cpu_count() or 1
-    workload = f"bam2db synthetic 10x-v3 BAM: {args.reads} reads/GPU, {N_CELLS} cells, {N_GENES} genes, -c {RATE_CELL} -r {RATE_DEPTH} -s {SEED} (BASELINE.json configs[2])"
+    workload = f"bam2db synthetic 10x-v3 BAM: {args.reads} reads/GPU, {N_CELLS} cells, {N_GENES} genes, -c {RATE_CELL} -r {RATE_DEPTH} -s {SEED} (BASELINE.json configs[{args.config}])"
 
     # ------------------------------------------------------------------ reference arm: the reference's own CPU path
     if args.impl == "reference" and args.workload == "freq":
@@ -302,7 +306,7 @@ def main():
     ctx = _lib.Context(local_rank)
     lib = ctx.lib
     # the synthetic segment is generated once per node (local rank 0, all host threads) and shared through /dev/shm
-    share = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(), f"fastf_bench_base_{os.environ.get('MASTER_PORT', '0')}_{args.base_reads}")
+    share = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(), f"fastf_bench_base_{os.environ.get('MASTER_PORT', '0')}_{args.base_reads}_{args.config}")
     if world > 1:
         if local_rank == 0:
             base = make_base(args.base_reads, threads)
