@@ -492,8 +492,8 @@ def main():
                            "parallelism": ("single GPU" if world == 1 else f"{world} ranks: contiguous BGZF block shards, all-gather of counts, NCCL all-to-all of locally deduplicated keys by cell hash, gather of COO")},
                 "roofline": {"bound": "hbm", "kernel": "hardware decompression engine" if args.engine == "hw" else ("fastf_bgzf_inflate_tps_kernel<16,24>" if args.lanes == 0 else "inflate (--lanes %d)" % args.lanes),
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on a full chunk of 37888 blocks (ncu --set full, profiles/r01_v8_ncu_inflate_crc_parse.txt)
-                             "traffic": 13.735e9 if (args.engine == "sm" and args.lanes == 0 and chunk == 0) else None, "traffic_source": "profiles/r01_v8_ncu_inflate_crc_parse.txt (11.211 GB read + 2.524 GB written per launch over one 37888-block chunk, 2.46 GB inflated)",
+                             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on a full chunk of 37888 blocks (ncu --set full, profiles/r01_v9_ncu_inflate_tps.txt)
+                             "traffic": 13.780e9 if (args.engine == "sm" and args.lanes == 0 and chunk == 0) else None, "traffic_source": "profiles/r01_v9_ncu_inflate_tps.txt (11.257 GB read + 2.523 GB written per launch over one 37888-block chunk, 2.46 GB inflated)",
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_launch, "ms_per_launch": infl_ms_launch},
                 "stages": stages, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "inflate_engine": args.engine, "hw_decompress_engine": hw_extra}
         if sweep is not None:
