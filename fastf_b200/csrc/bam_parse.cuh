@@ -71,8 +71,14 @@ template <class Acc> __device__ __forceinline__ u32 fastf_acc_4bytes(const Acc &
     if (sh == 0) return lo;
     return (lo >> sh) | (A.word(off + 3) << (32u - sh));
 }
-template <class Acc> __device__ __forceinline__ u32 fastf_acc_u16(const Acc &A, u64 off) { return A.byte(off) | (A.byte(off + 1) << 8); }
-template <class Acc> __device__ __forceinline__ u32 fastf_acc_u32(const Acc &A, u64 off) { return A.byte(off) | (A.byte(off + 1) << 8) | (A.byte(off + 2) << 16) | (A.byte(off + 3) << 24); }
+// little-endian 16 / 32-bit values at any alignment out of aligned word loads (the words that hold the bytes asked for, nothing beyond)
+template <class Acc> __device__ __forceinline__ u32 fastf_acc_u16(const Acc &A, u64 off)
+{
+    const u32 sh = 8u * (u32)(off & 3ull);
+    const u32 lo = A.word(off) >> sh;
+    return (sh == 24u ? (lo | (A.word(off + 1) << 8)) : lo) & 0xffffu;
+}
+template <class Acc> __device__ __forceinline__ u32 fastf_acc_u32(const Acc &A, u64 off) { return fastf_acc_4bytes(A, off); }
 
 // warp-cooperative lookup of the len bytes at offset s in a string table; every lane gets the value (0 = absent)
 template <class Acc>
@@ -147,7 +153,9 @@ __device__ __forceinline__ u32 fastf_parse_record(const Acc &A, u64 rec, u64 ren
     u32 found = 0;
     u64 q = rec + (u64)aoff;
     while (rend - q >= 3 && found != 15u) {
-        const u32 t0 = A.byte(q), t1 = A.byte(q + 1), ty = A.byte(q + 2);
+        u32 t0, t1, ty;
+        if (rend - q >= 4) { const u32 hd = fastf_acc_4bytes(A, q); t0 = hd & 255u; t1 = (hd >> 8) & 255u; ty = (hd >> 16) & 255u; }
+        else { t0 = A.byte(q); t1 = A.byte(q + 1); ty = A.byte(q + 2); }
         const u64 v = q + 3;
         u64 next;
         u32 vlen = 0;
@@ -292,7 +300,9 @@ __device__ __forceinline__ u32 fastf_parse_record_lane(const Acc &A, u64 rec, u6
     u32 found = 0;
     u64 q = rec + (u64)aoff;
     while (rend - q >= 3 && found != 15u) {
-        const u32 t0 = A.byte(q), t1 = A.byte(q + 1), ty = A.byte(q + 2);
+        u32 t0, t1, ty;
+        if (rend - q >= 4) { const u32 hd = fastf_acc_4bytes(A, q); t0 = hd & 255u; t1 = (hd >> 8) & 255u; ty = (hd >> 16) & 255u; }
+        else { t0 = A.byte(q); t1 = A.byte(q + 1); ty = A.byte(q + 2); }
         const u64 v = q + 3;
         u64 next;
         u32 vlen = 0;

@@ -48,7 +48,9 @@ __device__ __forceinline__ u32 fastf_tag_record(const Acc &A, u64 rec, u64 rend,
     u32 found = 0;
     u64 q = rec + (u64)aoff;
     while (rend - q >= 3 && found != want) {
-        const u32 t0 = A.byte(q), t1 = A.byte(q + 1), ty = A.byte(q + 2);
+        u32 t0, t1, ty;
+        if (rend - q >= 4) { const u32 hd = fastf_acc_4bytes(A, q); t0 = hd & 255u; t1 = (hd >> 8) & 255u; ty = (hd >> 16) & 255u; }
+        else { t0 = A.byte(q); t1 = A.byte(q + 1); ty = A.byte(q + 2); }
         const u64 v = q + 3;
         u64 next;
         u32 vlen = 0;
