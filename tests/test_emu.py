@@ -118,3 +118,28 @@ def test_emu_c_host_cli_crb_extract(emu_lib, tmp_path):
     # where the reference dereferences NULL (string extraction of an integer tag) this build refuses
     r = subprocess.run([cli, "extract", "-b", os.path.join(g, "tags.bam"), "-t", "NH"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 1 and "tag-not-a-string" in r.stdout
+
+
+def test_emu_bam2db_streaming_is_invariant(emu_lib):
+    """feeding the BAM in odd pieces and cutting chunks of different sizes (pending blocks carried across feed calls, host bytes
+    staged into the ring of compressed buffers piece by piece, partial BGZF blocks carried over) never changes the result"""
+    code = (
+        "import sys, os, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from fastf_b200 import _lib, bam2db_host as B\n"
+        "ctx = _lib.Context(0)\n"
+        "for d in ('edge', 'synth4k'):\n"
+        "    g = os.path.join(%r, 'tests', 'golden', d)\n"
+        "    inputs = B.Bam2dbInputs(ctx.lib, os.path.join(g, 'barcodes.tsv.gz'), os.path.join(g, 'features.tsv.gz'), 0.5, 926)\n"
+        "    bam = np.fromfile(os.path.join(g, 'in.bam'), dtype=np.uint8)\n"
+        "    ref = None\n"
+        "    for chunk, piece in ((0, 0), (1 << 20, 0), (1 << 20, 777), (3 << 20, 50001), (0, 4099), (70000, 13)):\n"
+        "        if piece == 13 and d == 'synth4k': continue\n"
+        "        st, out = B.run_device(ctx, bam, inputs, 0.5, 926, want_rows=True, chunk_inflated_bytes=chunk, feed_piece=piece)\n"
+        "        key = (st['total'], st['cb_valid'], st['sampled'], st['valid'], st['nnz'], out['m_gene'].tobytes(), out['m_cell'].tobytes(), out['m_count'].tobytes(), out['row_keys'].tobytes())\n"
+        "        if ref is None: ref = key\n"
+        "        assert key == ref, (d, chunk, piece, st)\n"
+        "    print('ok', d, ref[:5])\n"
+    ) % (ROOT, os.path.join(ROOT, "tests"), ROOT)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FASTF_GPU_LIB=emu_lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
+    assert r.returncode == 0 and r.stdout.count("ok ") == 2, r.stdout[-3000:]
