@@ -827,7 +827,9 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
     job->chunk_bytes = p->chunk_inflated_bytes ? std::max<u64>(p->chunk_inflated_bytes, 1u << 20) : FASTF_DEFAULT_CHUNK;
     // the persistent thread-per-stream kernel keeps 64 streams per SM busy: give every launch several blocks per stream
     if (!p->chunk_inflated_bytes && (job->lanes & 0xffu) >= 1 && (job->lanes & 0xffu) <= 4) {
-        job->chunk_blocks = 2ull * (u64)ctx->n_sm * FASTF_TPS_STREAMS;   // two full rounds of the persistent kernel (37888 blocks, <= 2.4 GiB on 148 SMs)
+        u64 rounds = 2;   // full rounds of the persistent kernel per chunk (2 -> 37888 blocks, <= 2.4 GiB on 148 SMs)
+        if (const char *e = getenv("FASTF_CHUNK_ROUNDS")) { const long v = atol(e); if (v >= 1 && v <= 16) rounds = (u64)v; }
+        job->chunk_blocks = rounds * (u64)ctx->n_sm * FASTF_TPS_STREAMS;
         job->chunk_bytes = job->chunk_blocks * 65536ull;
     }
     FastfKeyLayout &L = job->L;
@@ -1619,30 +1621,58 @@ static int inflate_whole(fastf_ctx *ctx, InflatedFile &F, const void *host_bytes
     }
     const u8 *comp = dev_bytes;
     u64 comp_total = n & ~(u64)3;
+    const u64 span = hi > lo ? hi - lo : 0;
     if (!dev_bytes) {
-        const u64 span = hi > lo ? hi - lo : 0, padded = (span + 3) & ~3ull;
+        const u64 padded = (span + 3) & ~3ull;
         TRY(dev_reserve(ctx, F.comp, padded + 16));
-        if (span) CK(cudaMemcpyAsync(F.comp.p, (const u8 *)host_bytes + lo, span, cudaMemcpyHostToDevice, s));
         comp = F.comp.as<u8>();
         comp_total = padded;
     }
     TRY(dev_reserve(ctx, F.infl, total + 64));
     TRY(index_upload(ctx, F.idx, s));
-    cudaEvent_t a = nullptr, b = nullptr;
-    if (ms) { CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); CK(cudaEventRecord(a, s)); }
     {
         const u32 l = lanes & 0xffu;
         lanes = ((l == 8 || l == 16 || l == 32 || (l >= 1 && l <= 4)) ? l : FASTF_INFLATE_DEFAULT) | (lanes & (FASTF_INFLATE_HW_ENGINE | FASTF_INFLATE_NO_CRC));
     }
-    TRY(launch_inflate(ctx, lanes, comp, comp_total, F.idx.in_off, F.idx.in_len, F.idx.out_off, F.idx.isize, (u32)nb, F.infl.as<u8>(), F.idx.st_infl, s, &F.de, F.idx.h_in_off, F.idx.h_in_len,
-                       F.idx.h_out_off, F.idx.h_isize));
-    if (ms) { CK(cudaEventRecord(b, s)); }
-    TRY(launch_crc(ctx, lanes, comp, dev_bytes ? (u64)n : comp_total, F.idx.in_off, F.idx.in_len, F.infl.as<u8>(), F.idx.out_off, F.idx.isize, (u32)nb, F.idx.st_infl, s));
+    // One launch over all blocks.  (Measured on freq, 117 k blocks: sending the host bytes in groups of two kernel rounds on the copy
+    // stream while the previous group inflates is SLOWER end to end, 491 vs 514 M reads/s, and four launches instead of one cost the
+    // device-resident path 7 %: every launch pays for building 128 tables per SM before its decoders start, and for its tail.
+    // FASTF_INFLATE_GROUP=<blocks> re-enables the grouping for experiments.)  The inflate clock is the sum of the launches.
+    size_t group = std::max<size_t>(nb, 1);
+    if (const char *e = getenv("FASTF_INFLATE_GROUP")) { const long v = atol(e); group = v > 0 ? (size_t)v : std::max<size_t>(nb, 1); }   // A/B knob: 0 = one launch
+    std::vector<cudaEvent_t> ev;
+    cudaEvent_t ev_copy = nullptr;
+    if (!dev_bytes) CK(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
+    int rc_l = 0;
+    for (size_t g0 = 0; g0 < nb && !rc_l; g0 += group) {
+        const size_t g1 = std::min(nb, g0 + group);
+        if (!dev_bytes) {
+            // bytes of this group: from its first payload (the very first group: from lo) to the end of its last block's trailer
+            const u64 b0 = g0 == 0 ? 0 : (F.idx.h_in_off[g0] & ~3ull);
+            const u64 b1 = std::min<u64>(F.idx.h_in_off[g1 - 1] + F.idx.h_in_len[g1 - 1] + 8, span);
+            if (b1 > b0) CK(cudaMemcpyAsync(F.comp.as<u8>() + b0, (const u8 *)host_bytes + lo + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->copy));
+            CK(cudaEventRecord(ev_copy, ctx->copy));
+            CK(cudaStreamWaitEvent(s, ev_copy, 0));
+        }
+        if (ms) { cudaEvent_t a = nullptr, b = nullptr; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); ev.push_back(a); ev.push_back(b); CK(cudaEventRecord(a, s)); }
+        rc_l = launch_inflate(ctx, lanes, comp, comp_total, F.idx.in_off + g0, F.idx.in_len + g0, F.idx.out_off + g0, F.idx.isize + g0, (u32)(g1 - g0), F.infl.as<u8>(), F.idx.st_infl + g0, s, &F.de,
+                              F.idx.h_in_off + g0, F.idx.h_in_len + g0, F.idx.h_out_off + g0, F.idx.h_isize + g0);
+        if (ms) CK(cudaEventRecord(ev.back(), s));
+        if (!rc_l) rc_l = launch_crc(ctx, lanes, comp, dev_bytes ? (u64)n : comp_total, F.idx.in_off + g0, F.idx.in_len + g0, F.infl.as<u8>(), F.idx.out_off + g0, F.idx.isize + g0, (u32)(g1 - g0),
+                                     F.idx.st_infl + g0, s);
+    }
+    if (rc_l) { for (auto e : ev) cudaEventDestroy(e); if (ev_copy) cudaEventDestroy(ev_copy); return rc_l; }
     // OR of the per-block status words
     std::vector<u32> st(nb);
     if (nb) CK(cudaMemcpyAsync(st.data(), F.idx.st_infl, nb * sizeof(u32), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (ms) { CK(cudaEventElapsedTime(ms, a, b)); cudaEventDestroy(a); cudaEventDestroy(b); }
+    if (!dev_bytes) CK(cudaStreamSynchronize(ctx->copy));
+    if (ms) {
+        *ms = 0;
+        for (size_t i = 0; i + 1 < ev.size(); i += 2) { float t = 0; cudaEventElapsedTime(&t, ev[i], ev[i + 1]); *ms += t; }
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+    if (ev_copy) cudaEventDestroy(ev_copy);
     F.status = 0;
     for (size_t i = 0; i < nb; i++) F.status |= st[i];
     F.n_blocks = nb;
@@ -2009,7 +2039,8 @@ extern "C" int fastf_taghist_gpu(fastf_ctx *ctx, const void *host_bytes, size_t 
             if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (double)infl_total * 2.6 + (double)n < 0.7 * (double)free_b && all.size() < 0xffffffffull) chunk_blocks = all.size();
         }
         u64 hit_base = 0;
-        bool first_chunk = true;
+        bool first_chunk = true, single = false;
+        u64 single_groups = 0, single_hits = 0;
         res->hash_rounds = 1;
         smap.reserve(1u << 16);
         for (size_t c0 = 0; c0 < all.size() || first_chunk; c0 += chunk_blocks) {
@@ -2140,6 +2171,13 @@ extern "C" int fastf_taghist_gpu(fastf_ctx *ctx, const void *host_bytes, size_t 
                     if (total) CK(cudaMemcpyAsync(h_blob.data(), blob.p, total, cudaMemcpyDeviceToHost, s));
                     CK(cudaStreamSynchronize(s));
                 }
+                if (c0 == 0 && c1 == all.size()) {
+                    // the whole file was one chunk: its groups are the result, no merge
+                    single = true;
+                    single_groups = ngroups;
+                    single_hits = n_hits;
+                    break;
+                }
                 std::string k;
                 for (u64 g = 0; g < ngroups; g++) {
                     const u64 cnt = (g + 1 < ngroups ? h_start[g + 1] : (u32)n_hits) - h_start[g], fst = hit_base + h_first[g];
@@ -2161,11 +2199,12 @@ extern "C" int fastf_taghist_gpu(fastf_ctx *ctx, const void *host_bytes, size_t 
             if (all.empty()) break;
         }
         // ---- merged groups -> result arrays ----
-        const u64 ngroups = mode == FASTF_TAG_MODE_INT ? imap.size() : smap.size();
+        const u64 ngroups = single ? single_groups : (mode == FASTF_TAG_MODE_INT ? imap.size() : smap.size());
         res->n_groups = ngroups;
         const u64 ng1 = std::max<u64>(ngroups, 1);
         u64 sbytes = 0;
         for (auto &kv : smap) sbytes += kv.first.size() - 1;
+        if (single && mode == FASTF_TAG_MODE_STRING) for (u64 g = 0; g < ngroups; g++) sbytes += (h_rep_a[g] & 0xffffu) + (h_rep_b[g] & 0xffffu);
         res->first = (u32 *)malloc(ng1 * sizeof(u32));
         res->count = (u32 *)malloc(ng1 * sizeof(u32));
         res->ivalue = (int32_t *)malloc(ng1 * sizeof(int32_t));
@@ -2176,6 +2215,17 @@ extern "C" int fastf_taghist_gpu(fastf_ctx *ctx, const void *host_bytes, size_t 
         res->strings_bytes = sbytes;
         if (!res->first || !res->count || !res->ivalue || !res->a_off || !res->a_len || !res->b_len || !res->strings) return ctx_fail(ctx, "taghist: out of host memory");
         u64 g = 0, at = 0;
+        if (single) {
+            for (; g < ngroups; g++) {
+                res->count[g] = (u32)((g + 1 < ngroups ? h_start[g + 1] : (u32)single_hits) - h_start[g]);
+                res->first[g] = h_first[g];
+                res->ivalue[g] = (int32_t)(u32)h_key[g];
+                res->a_off[g] = mode == FASTF_TAG_MODE_STRING ? h_blob_off[g] : 0;
+                res->a_len[g] = mode == FASTF_TAG_MODE_STRING ? (u32)(h_rep_a[g] & 0xffffu) : 0;
+                res->b_len[g] = mode == FASTF_TAG_MODE_STRING ? (u32)(h_rep_b[g] & 0xffffu) : 0;
+            }
+            if (mode == FASTF_TAG_MODE_STRING && sbytes) memcpy(res->strings, h_blob.data(), sbytes);
+        }
         for (auto &kv : imap) { res->ivalue[g] = kv.first; res->first[g] = (u32)kv.second.first; res->count[g] = (u32)kv.second.count; res->a_off[g] = 0; res->a_len[g] = 0; res->b_len[g] = 0; g++; }
         for (auto &kv : smap) {
             const std::string &k = kv.first;
