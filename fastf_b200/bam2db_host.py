@@ -130,6 +130,9 @@ def decode_rows(row_keys, bits_gene, bits_umi, umi_max_bytes):
     return cell, gene, nbytes, content
 
 
+BAM_STRADDLE = 0x400   # FASTF_BAM_STRADDLE (include/fastf_gpu.h)
+
+
 class Bam2dbJob:
     """One streaming bam2db job on one GPU: begin -> feed*/feed_device* -> (counts -> sample(base)) -> finish."""
 
@@ -365,12 +368,18 @@ def bam2db(bam_file, db_file, path_out, barcodes_file, features_file, rate_cell,
         print("Start to convert bam file to sqlite3 database...")
         sys.stdout.flush()
         bam_bytes = np.fromfile(bam_file, dtype=np.uint8)
-        try:
-            stats, out = run_device(ctx, bam_bytes, inputs, rate_depth, seed, want_rows=True, umi_max_bytes=3)   # 10x UMIs: 10 or 12 bases
-        except _lib.FastfError as e:
-            if "umi-too-long" not in str(e):
-                raise
-            stats, out = run_device(ctx, bam_bytes, inputs, rate_depth, seed, want_rows=True, umi_max_bytes=4)   # up to 16 bases
+        flags, umi_bytes = 0, 3   # 10x UMIs: 10 or 12 bases; room for 16 on demand
+        while True:
+            try:
+                stats, out = run_device(ctx, bam_bytes, inputs, rate_depth, seed, want_rows=True, umi_max_bytes=umi_bytes, inflate_lanes=flags)
+                break
+            except _lib.FastfError as e:
+                if "umi-too-long" in str(e) and umi_bytes == 3:
+                    umi_bytes = 4
+                elif "record-straddles-bgzf-block" in str(e) and not flags:
+                    flags = BAM_STRADDLE   # not an htslib-written file: guess and verify the record starts per block (one chunk)
+                else:
+                    raise
         rc = write_outputs(db, bam_file, path_out, inputs, rate_cell, rate_depth, stats, out)
         db.close()
         return rc

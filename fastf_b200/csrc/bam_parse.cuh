@@ -405,6 +405,7 @@ fastf_bam_parse_kernel(const u8 *__restrict__ infl, u64 infl_total, const u64 *_
     const u64 first_record_off = *first_record_off_ptr;   // end of the BAM header (chunk 0) or 0
     u64 p = bstart > first_record_off ? bstart : first_record_off;
     u64 *out = stage + stage_off[b];
+    const u64 cap = stage_off[b + 1] - stage_off[b];   // stage_off has nblocks + 1 entries; only a wrong record-start guess (FASTF_BAM_STRADDLE) can exceed it
     u32 nrec = 0, ncbv = 0, status = 0;
 
     while (p < bend) {
@@ -446,7 +447,11 @@ fastf_bam_parse_kernel(const u8 *__restrict__ infl, u64 infl_total, const u64 *_
             if (r == 2) break;
             p += 4 + (u64)bs;
             nrec++;
-            if (r == 1) { if (lane == 0) out[ncbv] = key; ncbv++; }
+            if (r == 1) {
+                if (ncbv >= cap) { status |= FASTF_ST_REC_CORRUPT; break; }
+                if (lane == 0) out[ncbv] = key;
+                ncbv++;
+            }
             continue;
         }
         // (3) one record per lane
@@ -458,6 +463,7 @@ fastf_bam_parse_kernel(const u8 *__restrict__ infl, u64 infl_total, const u64 *_
         u32 good = nb;
         if (badm) good = (u32)__ffs((int)badm) - 1u;
         const u32 cm = __ballot_sync(FASTF_FULL_MASK, r == 1 && lane < good);
+        if (ncbv + (u32)__popc(cm) > cap) { status |= FASTF_ST_REC_CORRUPT; break; }
         if (r == 1 && lane < good) out[ncbv + (u32)__popc(cm & fastf_lanemask_lt())] = key;
         ncbv += (u32)__popc(cm);
         nrec += good;

@@ -127,6 +127,7 @@ fastf_bam_tags_kernel(const u8 *__restrict__ infl, u64 infl_total, const u64 *__
     const u64 first_record_off = *first_record_off_ptr;
     u64 p = bstart > first_record_off ? bstart : first_record_off;
     u64 *out = stage + stage_off[b];
+    const u64 cap = stage_off[b + 1] - stage_off[b];   // stage_off has nblocks + 1 entries; only a wrong record-start guess (FASTF_BAM_STRADDLE) can exceed it
     u32 nrec = 0, nhit = 0, status = 0;
 
     while (p < bend) {
@@ -174,6 +175,7 @@ fastf_bam_tags_kernel(const u8 *__restrict__ infl, u64 infl_total, const u64 *__
         if (badm) good = (u32)__ffs((int)badm) - 1u;
         if (__ballot_sync(FASTF_FULL_MASK, r == 3 && lane < good)) status |= FASTF_ST_TAG_TYPE;
         const u32 cm = __ballot_sync(FASTF_FULL_MASK, r == 1 && lane < good);
+        if (nhit + (u32)__popc(cm) > cap) { status |= FASTF_ST_REC_CORRUPT; break; }
         if (r == 1 && lane < good) {
             const u32 at = nhit + (u32)__popc(cm & fastf_lanemask_lt());
             out[at] = key;

@@ -22,6 +22,7 @@
 #include "mt_jump.h"
 #include "freq.cuh"
 #include "bam_tags.cuh"
+#include "bam_straddle.cuh"
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -707,6 +708,7 @@ static void index_release(fastf_ctx *ctx, BlockIndexDev &I) { dev_release(ctx, I
 struct ChunkSlot {
     BlockIndexDev idx;
     DevBuf stage;         // per-block candidate staging
+    DevBuf virt;          // FASTF_BAM_STRADDLE: record-start guesses and virtual blocks
     DevBuf infl;          // inflated bytes of the chunk (double buffered: chunk i+1 inflates while chunk i is parsed)
     DeScratch de;
     cudaEvent_t ev_infl = nullptr, ev_gather = nullptr;
@@ -785,7 +787,7 @@ extern "C" void fastf_bam2db_job_free(fastf_bam2db_job *job)
     cudaStreamSynchronize(ctx->mt);
     for (int i = 0; i < 2; i++) {
         ChunkSlot &S = job->slot[i];
-        index_release(ctx, S.idx); dev_release(ctx, S.stage); dev_release(ctx, S.infl); dev_release(ctx, S.de.counter); dev_release(ctx, S.de.sorted); pin_release(ctx, S.snap);
+        index_release(ctx, S.idx); dev_release(ctx, S.stage); dev_release(ctx, S.virt); dev_release(ctx, S.infl); dev_release(ctx, S.de.counter); dev_release(ctx, S.de.sorted); pin_release(ctx, S.snap);
         if (S.ev_copy) cudaEventDestroy(S.ev_copy);
         if (S.ev_infl) cudaEventDestroy(S.ev_infl);
         if (S.ev_gather) cudaEventDestroy(S.ev_gather);
@@ -822,7 +824,7 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
     job->launches0 = ctx->launches;
     {
         const u32 l = p->inflate_lanes & 0xffu;
-        job->lanes = ((l == 8 || l == 16 || l == 32 || (l >= 1 && l <= 4)) ? l : FASTF_INFLATE_DEFAULT) | (p->inflate_lanes & (FASTF_INFLATE_HW_ENGINE | FASTF_INFLATE_NO_CRC));
+        job->lanes = ((l == 8 || l == 16 || l == 32 || (l >= 1 && l <= 4)) ? l : FASTF_INFLATE_DEFAULT) | (p->inflate_lanes & (FASTF_INFLATE_HW_ENGINE | FASTF_INFLATE_NO_CRC | FASTF_BAM_STRADDLE));
     }
     job->chunk_bytes = p->chunk_inflated_bytes ? std::max<u64>(p->chunk_inflated_bytes, 1u << 20) : FASTF_DEFAULT_CHUNK;
     // the persistent thread-per-stream kernel keeps 64 streams per SM busy: give every launch several blocks per stream
@@ -831,6 +833,12 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
         if (const char *e = getenv("FASTF_CHUNK_ROUNDS")) { const long v = atol(e); if (v >= 1 && v <= 16) rounds = (u64)v; }
         job->chunk_blocks = rounds * (u64)ctx->n_sm * FASTF_TPS_STREAMS;
         job->chunk_bytes = job->chunk_blocks * 65536ull;
+    }
+    if (job->lanes & FASTF_BAM_STRADDLE) {
+        // records may run across block boundaries: keep the whole file in one chunk so that none is cut by a chunk boundary
+        if (p->headerless) { delete job; return ctx_fail(ctx, "bam2db_begin: FASTF_BAM_STRADDLE needs the whole file in one job (a later shard does not know where its first record starts)"); }
+        job->chunk_blocks = FASTF_MAX_BLOCKS_PER_CHUNK;
+        job->chunk_bytes = ~0ull >> 2;
     }
     FastfKeyLayout &L = job->L;
     L.umi_max_bytes = p->umi_max_bytes ? p->umi_max_bytes : 3;
@@ -1012,6 +1020,25 @@ static int finalize_slot(fastf_bam2db_job *job, u32 si)
     return 0;
 }
 
+// FASTF_BAM_STRADDLE: record-start guesses per BGZF block -> virtual blocks [v_k, v_next) for the per-block kernels (bam_straddle.cuh).
+// scratch holds guess u64[nb] | virt_off u64[nb] | virt_size u32[nb]; status_word collects impossible layouts.
+static int launch_virtual_blocks(fastf_ctx *ctx, DevBuf &scratch, const u8 *infl, u64 infl_bytes, const u64 *blk_off, const u32 *blk_isize, u32 nb, const u64 *hdr_off, u32 *status_word,
+                                 const u64 **virt_off, const u32 **virt_size, cudaStream_t s)
+{
+    TRY(dev_reserve(ctx, scratch, (size_t)std::max<u32>(nb, 1) * 20 + 64));
+    u64 *guess = scratch.as<u64>(), *voff = guess + nb;
+    u32 *vsize = (u32 *)(voff + nb);
+    if (nb) {
+        FASTF_LAUNCH(fastf_bam_guess_kernel, (nb + 7) / 8, 256, 0, s, infl, infl_bytes, blk_off, blk_isize, nb, hdr_off, guess);
+        CKL("bam_guess");
+        FASTF_LAUNCH(fastf_bam_virtual_blocks_kernel, (nb + 255) / 256, 256, 0, s, (const u64 *)guess, nb, infl_bytes, voff, vsize, status_word);
+        CKL("bam_virtual_blocks");
+    }
+    *virt_off = voff;
+    *virt_size = vsize;
+    return 0;
+}
+
 // One chunk: blocks with payload offsets relative to `comp_dev` (the caller's device buffer, or the ring entry the host bytes were
 // staged into by stage_host_bytes: their H2D copies are already queued on the copy stream).
 static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb, const u8 *comp_dev, u64 comp_total, fastf_bam2db_job::CompRing *ring)
@@ -1022,7 +1049,8 @@ static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb
     if (ring) CK(cudaEventRecord(ring->ev_copy, ctx->copy));
     // the slot was used two chunks ago: its gather must have been issued (finalize) before we reuse its buffers
     TRY(finalize_slot(job, si));
-    TRY(index_reserve(ctx, S.idx, nb));
+    TRY(index_reserve(ctx, S.idx, nb + 1));
+    const bool straddle = (job->lanes & FASTF_BAM_STRADDLE) != 0;
     u64 out_total = 0, stage_total = 0;
     for (u32 i = 0; i < nb; i++) {
         S.idx.h_in_off[i] = blocks[i].in_off;
@@ -1031,8 +1059,10 @@ static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb
         S.idx.h_out_off[i] = out_total;
         S.idx.h_stage_off[i] = stage_total;
         out_total += blocks[i].isize;
-        stage_total += stage_cap_for(blocks[i].isize);
+        // straddle mode: a virtual block holds the records that START between this block's guess and the next one's
+        stage_total += straddle ? stage_cap_for(blocks[i].isize + (i + 1 < nb ? blocks[i + 1].isize : 0)) + 1u : stage_cap_for(blocks[i].isize);
     }
+    S.idx.h_stage_off[nb] = stage_total;   // the kernels read the slice capacity as stage_off[b + 1] - stage_off[b]
     if (ring) CK(cudaStreamWaitEvent(ctx->infl, ring->ev_copy, 0));
     // S.infl / S.stage / S.idx were last used by chunk i-2, whose parse and gather have completed (finalize_slot above)
     TRY(dev_reserve(ctx, S.infl, out_total + 64));
@@ -1063,9 +1093,13 @@ static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb
     } else {
         CK(cudaMemsetAsync(job->hdr_off.p, 0, sizeof(u64), ctx->compute));
     }
+    const u64 *p_off = S.idx.out_off;
+    const u32 *p_size = S.idx.isize;
+    if (straddle) TRY(launch_virtual_blocks(ctx, S.virt, (const u8 *)S.infl.as<u8>(), out_total, S.idx.out_off, S.idx.isize, nb, job->hdr_off.as<u64>(), (u32 *)(job->counters.as<u64>() + 2), &p_off, &p_size,
+                                            ctx->compute));
     if (nb) {
         FASTF_LAUNCH(fastf_bam_parse_kernel, (nb + FASTF_PARSE_WARPS - 1) / FASTF_PARSE_WARPS, FASTF_PARSE_WARPS * 32, 0, ctx->compute, (const u8 *)S.infl.as<u8>(), (u64)((out_total + 15) & ~15ull),
-                     (const u64 *)S.idx.out_off, (const u32 *)S.idx.isize, nb, (const u64 *)job->hdr_off.as<u64>(), job->cells.view, job->genes.view, job->L, (const u64 *)S.idx.stage_off,
+                     p_off, p_size, nb, (const u64 *)job->hdr_off.as<u64>(), job->cells.view, job->genes.view, job->L, (const u64 *)S.idx.stage_off,
                      S.stage.as<u64>(), S.idx.nrec, S.idx.ncbv, S.idx.st_parse);
         CKL("bam_parse");
     }
@@ -1632,7 +1666,7 @@ static int inflate_whole(fastf_ctx *ctx, InflatedFile &F, const void *host_bytes
     TRY(index_upload(ctx, F.idx, s));
     {
         const u32 l = lanes & 0xffu;
-        lanes = ((l == 8 || l == 16 || l == 32 || (l >= 1 && l <= 4)) ? l : FASTF_INFLATE_DEFAULT) | (lanes & (FASTF_INFLATE_HW_ENGINE | FASTF_INFLATE_NO_CRC));
+        lanes = ((l == 8 || l == 16 || l == 32 || (l >= 1 && l <= 4)) ? l : FASTF_INFLATE_DEFAULT) | (lanes & (FASTF_INFLATE_HW_ENGINE | FASTF_INFLATE_NO_CRC | FASTF_BAM_STRADDLE));
     }
     // One launch over all blocks.  (Measured on freq, 117 k blocks: sending the host bytes in groups of two kernel rounds on the copy
     // stream while the previous group inflates is SLOWER end to end, 491 vs 514 M reads/s, and four launches instead of one cost the
@@ -1986,7 +2020,8 @@ extern "C" int fastf_taghist_gpu(fastf_ctx *ctx, const void *host_bytes, size_t 
     const u32 l0 = ctx->launches;
     cudaStream_t s = ctx->compute;
     InflatedFile F;
-    DevBuf hdr_off, counters, stage_off, stage, keys, loc_a, loc_b, vals, kalt, valt, orand, coll, rep_a, rep_b, blob_off, blob;
+    DevBuf hdr_off, counters, stage_off, stage, keys, loc_a, loc_b, vals, kalt, valt, orand, coll, rep_a, rep_b, blob_off, blob, virt;
+    const bool straddle = (inflate_lanes & FASTF_BAM_STRADDLE) != 0;   // records may cross BGZF block boundaries (bam_straddle.cuh): one chunk
     PinBuf host;
     SortScratch S;
     RleScratch R;
@@ -2000,7 +2035,7 @@ extern "C" int fastf_taghist_gpu(fastf_ctx *ctx, const void *host_bytes, size_t 
     std::unordered_map<std::string, TagAgg> smap;
     std::unordered_map<int32_t, TagAgg> imap;
     auto cleanup = [&]() {
-        for (DevBuf *b : {&hdr_off, &counters, &stage_off, &stage, &keys, &loc_a, &loc_b, &vals, &kalt, &valt, &orand, &coll, &rep_a, &rep_b, &blob_off, &blob}) dev_release(ctx, *b);
+        for (DevBuf *b : {&hdr_off, &counters, &stage_off, &stage, &keys, &loc_a, &loc_b, &vals, &kalt, &valt, &orand, &coll, &rep_a, &rep_b, &blob_off, &blob, &virt}) dev_release(ctx, *b);
         pin_release(ctx, host);
         sort_scratch_release(ctx, S);
         rle_scratch_release(ctx, R);
@@ -2030,7 +2065,8 @@ extern "C" int fastf_taghist_gpu(fastf_ctx *ctx, const void *host_bytes, size_t 
         // The file streams through HBM in chunks of whole blocks (two full rounds of the persistent inflate kernel each); every chunk
         // is grouped on the device, the per-chunk groups are merged here.
         size_t chunk_blocks = std::max<size_t>(1, ctx->taghist_chunk_blocks ? ctx->taghist_chunk_blocks : 2ull * (size_t)ctx->n_sm * FASTF_TPS_STREAMS);
-        if (!ctx->taghist_chunk_blocks) {
+        if (straddle) chunk_blocks = std::max<size_t>(all.size(), 1);
+        else if (!ctx->taghist_chunk_blocks) {
             // a file whose inflated bytes, staging planes (worst case 2/3 of them) and key arrays fit HBM comfortably goes through in ONE
             // chunk: no host-side merge at all
             u64 infl_total = 0;
@@ -2052,9 +2088,13 @@ extern "C" int fastf_taghist_gpu(fastf_ctx *ctx, const void *host_bytes, size_t 
             res->inflated_bytes += F.infl_bytes;
             const u32 nb = (u32)F.n_blocks;
             // per-block staging slices (a record is >= 36 bytes)
-            h_stage_off.resize(std::max<u32>(nb, 1));
+            h_stage_off.resize((size_t)nb + 1);
             u64 plane = 0;
-            for (u32 i = 0; i < nb; i++) { h_stage_off[i] = plane; plane += stage_cap_for(F.idx.h_isize[i]); }
+            for (u32 i = 0; i < nb; i++) {
+                h_stage_off[i] = plane;
+                plane += straddle ? stage_cap_for(F.idx.h_isize[i] + (i + 1 < nb ? F.idx.h_isize[i + 1] : 0)) + 1u : stage_cap_for(F.idx.h_isize[i]);
+            }
+            h_stage_off[nb] = plane;   // the kernel reads the slice capacity as stage_off[b + 1] - stage_off[b]
             TRY(dev_reserve(ctx, stage_off, h_stage_off.size() * sizeof(u64)));
             CK(cudaMemcpyAsync(stage_off.p, h_stage_off.data(), h_stage_off.size() * sizeof(u64), cudaMemcpyHostToDevice, s));
             TRY(dev_reserve(ctx, stage, std::max<u64>(plane, 1) * 3 * sizeof(u64)));
@@ -2072,9 +2112,12 @@ extern "C" int fastf_taghist_gpu(fastf_ctx *ctx, const void *host_bytes, size_t 
                     FASTF_LAUNCH(fastf_bam_header_kernel, 1, 32, 0, s, (const u8 *)F.infl.as<u8>(), F.infl_bytes, hdr_off.as<u64>(), (u32 *)(counters.as<u64>() + 2));
                     CKL("bam_header");
                 }
+                const u64 *p_off = F.idx.out_off;
+                const u32 *p_size = F.idx.isize;
+                if (straddle) TRY(launch_virtual_blocks(ctx, virt, (const u8 *)F.infl.as<u8>(), F.infl_bytes, F.idx.out_off, F.idx.isize, nb, hdr_off.as<u64>(), (u32 *)(counters.as<u64>() + 2), &p_off, &p_size, s));
                 if (nb) {
                     FASTF_LAUNCH(fastf_bam_tags_kernel, (nb + FASTF_PARSE_WARPS - 1) / FASTF_PARSE_WARPS, FASTF_PARSE_WARPS * 32, 0, s, (const u8 *)F.infl.as<u8>(), (u64)((F.infl_bytes + 15) & ~15ull),
-                                 (const u64 *)F.idx.out_off, (const u32 *)F.idx.isize, nb, (const u64 *)hdr_off.as<u64>(), Q, (const u64 *)stage_off.as<u64>(), stage.as<u64>(), plane, F.idx.nrec,
+                                 p_off, p_size, nb, (const u64 *)hdr_off.as<u64>(), Q, (const u64 *)stage_off.as<u64>(), stage.as<u64>(), plane, F.idx.nrec,
                                  F.idx.ncbv, F.idx.st_parse);
                     CKL("bam_tags");
                 }

@@ -143,6 +143,7 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
     printf("Start to convert bam file to sqlite3 database...\n");
     fflush(stdout);
     if (fastf_ctx_create(fastf_device, &ctx)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(NULL)); goto done; }
+    uint32_t flags = 0;   /* FASTF_BAM_STRADDLE after a first attempt met records that cross BGZF blocks (htsjdk / STAR writers) */
     for (uint32_t umi_bytes = 3; umi_bytes <= 4; umi_bytes++) {   /* 10x UMIs are 10 or 12 bases; retry once with room for 16 */
         fastf_bam2db_params p;
         memset(&p, 0, sizeof p);
@@ -152,6 +153,7 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
         p.seed = seed; p.d0 = d0; p.keep_threshold = fastf_keep_threshold(rate_depth);
         p.umi_max_bytes = umi_bytes;
         p.want_rows = 1;
+        p.inflate_lanes = flags;
         if (fastf_bam2db_begin(ctx, &p, &job)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
         const size_t PIECE = (size_t)256 << 20;
         if (!pin[0] && (fastf_host_alloc(ctx, PIECE, &pin[0]) || fastf_host_alloc(ctx, PIECE, &pin[1]))) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
@@ -165,6 +167,13 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
         if (!failed) failed = fastf_bam2db_finish(job, &res);
         if (!failed) break;
         if (umi_bytes == 3 && strstr(fastf_last_error(ctx), "umi-too-long")) { fastf_bam2db_job_free(job); job = NULL; continue; }
+        if (!flags && strstr(fastf_last_error(ctx), "record-straddles-bgzf-block")) {
+            /* not an htslib-written file: run again with record starts guessed and verified per block (whole file in one chunk) */
+            fastf_bam2db_job_free(job); job = NULL;
+            flags = FASTF_BAM_STRADDLE;
+            umi_bytes--;
+            continue;
+        }
         fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx));
         goto done;
     }

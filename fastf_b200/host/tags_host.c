@@ -56,7 +56,13 @@ static int taghist_open(taghist_t *t, const char *bam_file, const char *tag_a, u
     if (fastf_ctx_create(fastf_device, &t->ctx)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(NULL)); goto done; }
     if (fastf_host_alloc(t->ctx, (size_t)(n > 0 ? n : 1), &t->buf)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(t->ctx)); goto done; }
     if (n > 0 && fread(t->buf, 1, (size_t)n, f) != (size_t)n) { fprintf(stderr, "ERROR: Cannot read bam file %s\n", bam_file); goto done; }
-    if (fastf_taghist_gpu(t->ctx, t->buf, (size_t)n, tag_a, mode, tag_b, 0, &t->res)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(t->ctx)); goto done; }
+    if (fastf_taghist_gpu(t->ctx, t->buf, (size_t)n, tag_a, mode, tag_b, 0, &t->res)) {
+        /* records that cross BGZF blocks (htsjdk / STAR writers): once more with record starts guessed and verified per block */
+        if (!strstr(fastf_last_error(t->ctx), "record-straddles-bgzf-block") || fastf_taghist_gpu(t->ctx, t->buf, (size_t)n, tag_a, mode, tag_b, FASTF_BAM_STRADDLE, &t->res)) {
+            fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(t->ctx));
+            goto done;
+        }
+    }
     const uint64_t ng = t->res.n_groups;
     t->g = (grp_t *)calloc(ng + 1, sizeof(grp_t));
     if (mode == FASTF_TAG_INT) t->itext = (char *)calloc(ng + 1, 16);

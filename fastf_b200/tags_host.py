@@ -14,11 +14,15 @@ from . import _lib
 TAG_STRING, TAG_INT = 0, 1
 
 
-def taghist(ctx, bam_bytes, tag_a, mode=TAG_STRING, tag_b=None, inflate_lanes=0):
+def taghist(ctx, bam_bytes, tag_a, mode=TAG_STRING, tag_b=None, inflate_lanes=0, retry_straddle=False):
     """-> (stats, groups); groups = list of (value_a: bytes, value_b: bytes | None, count, first) in no particular order"""
     buf = np.frombuffer(bam_bytes, dtype=np.uint8) if not isinstance(bam_bytes, np.ndarray) else bam_bytes
     res = _lib.TaghistResult()
-    ctx.check(ctx.lib.fastf_taghist_gpu(ctx.h, C.c_void_p(buf.ctypes.data), buf.size, tag_a.encode(), mode, tag_b.encode() if tag_b else None, inflate_lanes, C.byref(res)), "taghist")
+    rc = ctx.lib.fastf_taghist_gpu(ctx.h, C.c_void_p(buf.ctypes.data), buf.size, tag_a.encode(), mode, tag_b.encode() if tag_b else None, inflate_lanes, C.byref(res))
+    if rc and retry_straddle and not (inflate_lanes & 0x400) and b"record-straddles-bgzf-block" in ctx.lib.fastf_last_error(ctx.h):
+        # not an htslib-written file (records cross BGZF blocks): once more with FASTF_BAM_STRADDLE
+        rc = ctx.lib.fastf_taghist_gpu(ctx.h, C.c_void_p(buf.ctypes.data), buf.size, tag_a.encode(), mode, tag_b.encode() if tag_b else None, inflate_lanes | 0x400, C.byref(res))
+    ctx.check(rc, "taghist")
     try:
         n = int(res.n_groups)
         first = np.ctypeslib.as_array(res.first, (max(n, 1),))[:n].copy()
@@ -54,7 +58,7 @@ def _preorder(ctx, firsts):
 def extract_bam(ctx, bam_file, tag, type_, out_dir="."):
     """reference extract_bam(bam_file, tag, type) (src/extract.c:135-216): writes <out_dir>/tag_summary.csv (the reference writes it into
     the working directory) and returns (total_count, valid_count) as the reference prints them -- total_count is doubled (:162,164)."""
-    stats, groups = taghist(ctx, np.fromfile(bam_file, dtype=np.uint8), tag, TAG_INT if type_ else TAG_STRING)
+    stats, groups = taghist(ctx, np.fromfile(bam_file, dtype=np.uint8), tag, TAG_INT if type_ else TAG_STRING, retry_straddle=True)
     groups.sort(key=lambda g: g[0])
     with open(os.path.join(out_dir, "tag_summary.csv"), "wb") as f:
         for i in _preorder(ctx, [g[3] for g in groups]):
@@ -65,7 +69,7 @@ def extract_bam(ctx, bam_file, tag, type_, out_dir="."):
 def crb(ctx, bam_file, path_out):
     """reference cmd_crb: read_bam + print_CB_node (src/extract.c:47-133, src/main.c:231-286): one gz line "CB;CR,count;CR,count;...\\n"
     per cell barcode, CB nodes and the CR nodes under each in BST pre-order.  Returns read_count."""
-    stats, groups = taghist(ctx, np.fromfile(bam_file, dtype=np.uint8), "CB", TAG_STRING, "CR")
+    stats, groups = taghist(ctx, np.fromfile(bam_file, dtype=np.uint8), "CB", TAG_STRING, "CR", retry_straddle=True)
     by_cb = {}
     for cb, cr, count, first in groups:
         by_cb.setdefault(cb, []).append((cr, count, first))

@@ -30,6 +30,10 @@ extern "C" {
 /* OR this in to skip the CRC-32 check of every inflated block against its BGZF trailer (htslib bgzf_read_block does the same check
  * for the reference, src/bam2db_ds.c:360).  On by default: a mismatch fails the job with "bgzf-crc32-mismatch". */
 #define FASTF_INFLATE_NO_CRC 0x200u
+/* OR this in for BAM files whose records cross BGZF block boundaries (writers other than htslib, e.g. htsjdk or STAR).  Without it such
+ * a file fails with "record-straddles-bgzf-block"; with it every block's first record start is guessed and the per-block kernels verify
+ * the guesses (a wrong one fails the job, never the result).  The mode keeps the whole file in one chunk: the inflated bytes must fit HBM. */
+#define FASTF_BAM_STRADDLE 0x400u
 
 typedef struct fastf_ctx fastf_ctx;
 typedef struct fastf_bam2db_job fastf_bam2db_job;
@@ -111,7 +115,9 @@ typedef struct {
 int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, fastf_bam2db_job **job);
 /* compressed BGZF bytes in host memory; any split (partial blocks are carried to the next call) */
 int fastf_bam2db_feed(fastf_bam2db_job *job, const void *host_bytes, size_t n);
-/* compressed bytes already resident in HBM + their host-side block index (payload offsets relative to dev_bytes) */
+/* compressed bytes already resident in HBM + their host-side block index (payload offsets relative to dev_bytes).  Blocks are launched in
+ * chunks of a fixed number of blocks and may wait for the blocks of the NEXT feed to fill a chunk: dev_bytes must stay valid and unchanged
+ * until fastf_bam2db_counts / _sample / _finish has returned.  (fastf_bam2db_feed copies its bytes before it returns.) */
 int fastf_bam2db_feed_device(fastf_bam2db_job *job, const void *dev_bytes, size_t nbytes, const uint64_t *in_off, const uint32_t *in_len, const uint32_t *isize, uint64_t nblocks);
 /* after the last feed: records and CB-valid reads seen by THIS job (multi-GPU: all-gather these to get ordinal bases) */
 int fastf_bam2db_counts(fastf_bam2db_job *job, uint64_t *n_records, uint64_t *n_cb_valid);

@@ -516,3 +516,33 @@ def test_crb_extract_streamed_chunks_and_forced_collisions(gpu_ctx, oracle, synt
             assert open(tmp_path / "tag_summary.csv", "rb").read() == open(tmp_path / "o.csv", "rb").read(), tag
     finally:
         gpu_ctx.lib.fastf_taghist_test_hooks(gpu_ctx.h, 0, 0)
+
+
+@pytest.mark.gpu
+def test_records_straddling_bgzf_blocks(gpu_ctx, oracle, synth, tmp_path):
+    """a BAM re-cut into BGZF blocks of odd sizes (records cross block boundaries, as htsjdk or STAR write them): refused by the strict
+    default, bit-exact vs the oracle with FASTF_BAM_STRADDLE (guessed record starts, verified by the per-block kernels), for bam2db fed
+    in pieces and for crb / extract; the flag changes nothing on an htslib-style file"""
+    from fastf_b200 import bam2db_host as B, tags_host as T, _lib
+    import bamgen
+    paths, _ = synth.write_bam_set(str(tmp_path), n_reads=120000, n_cells=400, n_genes=600, seed=17, p_umi_n=0.01)
+    whole = gzip.decompress(open(paths["bam"], "rb").read())
+    want = oracle.bam2db(paths["bam"], paths["barcodes"], paths["features"], 0.5, 0.5, 926)
+    inputs = B.Bam2dbInputs(gpu_ctx.lib, paths["barcodes"], paths["features"], 0.5, 926)
+    for cut in (65280, 40001, 1500):
+        p = str(tmp_path / ("cut%d.bam" % cut))
+        open(p, "wb").write(bamgen.bgzf_file([whole[i:i + cut] for i in range(0, len(whole), cut)], [(1, zlib.Z_DEFAULT_STRATEGY)]))
+        img = np.fromfile(p, dtype=np.uint8)
+        with pytest.raises(_lib.FastfError, match="straddles"):
+            B.run_device(gpu_ctx, img, inputs, 0.5, 926)
+        for piece in (0, 1 << 20):
+            st, out = B.run_device(gpu_ctx, img, inputs, 0.5, 926, want_rows=False, inflate_lanes=B.BAM_STRADDLE, feed_piece=piece)
+            for k in ("total", "cb_valid", "sampled", "valid", "nnz"):
+                assert st[k] == want[k], (cut, k)
+            assert np.array_equal(out["m_gene"], want["m_gene"]) and np.array_equal(out["m_cell"], want["m_cell"]) and np.array_equal(out["m_count"], want["m_count"])
+    assert T.crb(gpu_ctx, p, str(tmp_path / "crb.gz")) == oracle.crb(paths["bam"], str(tmp_path / "crb.txt"))   # the 1500-byte cut; retried by the operator
+    assert gzip.open(tmp_path / "crb.gz", "rb").read() == open(tmp_path / "crb.txt", "rb").read()
+    assert T.extract_bam(gpu_ctx, p, "GX", 0, str(tmp_path)) == oracle.extract(paths["bam"], "GX", 0, str(tmp_path / "o.csv"))
+    assert open(tmp_path / "tag_summary.csv", "rb").read() == open(tmp_path / "o.csv", "rb").read()
+    st, out = B.run_device(gpu_ctx, np.fromfile(paths["bam"], dtype=np.uint8), inputs, 0.5, 926, want_rows=False, inflate_lanes=B.BAM_STRADDLE)
+    assert st["nnz"] == want["nnz"] and np.array_equal(out["m_count"], want["m_count"])
