@@ -484,8 +484,9 @@ def main():
                 continue   # rank 0's local clocks only cover the streaming stages in the sharded job
             ms = st["ms_" + k]
             stages[k] = {"ms": round(ms, 3), "alg_GBps": round(bytes_ / (ms * 1e-3) / 1e9, 1) if ms > 0 else None}
-        line = {"metric": "bam2db reads/sec (device-timed)", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        line = {"metric": "bam2db reads/sec", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "timing": "value: device-timed (CUDA events), inputs resident in HBM; e2e: host wall clock from pinned host memory",
                 "config": {"workload": workload, "tiling": f"{base['reads']}-read zlib-6 BGZF segment ({base['compressed'] / 1e6:.0f} MB compressed, {base['inflated'] / 1e6:.0f} MB inflated) streamed {tiles}x per step",
                            "l2": "inputs larger than L2 (compressed segment >> 126 MB); no explicit flush", "timing": "CUDA events on the library's launching stream around the K timed jobs, barrier + synchronize on both sides; max over ranks",
                            "ms_per_step_wall": ms_step_wall, "ms_per_job_library_clock": ms_job_dev, "counters": {k: st.get(k) for k in ("total", "cb_valid", "sampled", "valid", "nnz", "n_blocks", "n_chunks", "exchanged_keys")},
@@ -586,7 +587,7 @@ def bench_freq(args):
     peak, peak_src = measured_peak()
     alg = stq["compressed_bytes"] + stq["inflated_bytes"]
     ach = alg / (stq["ms_inflate"] * 1e-3) / 1e9
-    line = {"metric": "freq reads/sec (device-timed)", "value": n_reads / (ms_step / 1e3), "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+    line = {"metric": "freq reads/sec", "value": n_reads / (ms_step / 1e3), "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"freq on synthetic R1 FASTQ: {n_reads} reads, 16 bp barcode + 12 bp UMI, 20000 true cells + 5 % error variants, -l 16 -u 12 (BASELINE.json configs[1])",
                        "tiling": f"{base_reads}-read BGZF segment x {tiles}", "l2": "inputs larger than L2", "ms_per_step_wall": 1e3 * wall / args.steps,
@@ -673,7 +674,7 @@ def bench_tags(args):
     peak, peak_src = measured_peak()
     alg = st["compressed_bytes"] + st["inflated_bytes"]
     ach = alg / (st["ms_inflate"] * 1e-3) / 1e9
-    line = {"metric": args.workload + " reads/sec (device-timed)", "value": n_reads / (dev_ms / 1e3), "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
+    line = {"metric": args.workload + " reads/sec", "value": n_reads / (dev_ms / 1e3), "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{args.workload} ({TAGS_CMD[args.workload]}) on the synthetic 10x-v3 BAM: {n_reads} reads, {N_CELLS} cells, {N_GENES} genes (SURVEY 8f)",
                        "l2": "inputs larger than L2", "counters": {k: st[k] for k in ("n_records", "n_hits", "n_groups", "n_blocks", "hash_rounds")}},
