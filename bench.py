@@ -227,7 +227,7 @@ def main():
         ms = 1e3 * sum(times) / len(times)
         v = n / (ms / 1e3)
         sample = f"{n}-read synthetic R1 FASTQ per step (whole run of the reference CLI `freq -l 16 -u 12`; wall clock)"
-        print(json.dumps({"impl": "reference", "metric": "freq reads/sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        print(json.dumps({"impl": "reference", "metric": "freq reads/sec (device-timed)", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": {"workload": "freq (BASELINE.json configs[1] shape)", "sample": sample},
                           "cpu_baseline": {"value": v, "unit": "reads/s", "cores": 1, "kind": kind, "sample": sample, "cpu": cpu_model(), "host_cores": threads},
                           "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -246,7 +246,7 @@ def main():
         ms = 1e3 * sum(times) / len(times)
         v = base["reads"] / (ms / 1e3)
         sample = f"{base['reads']}-read synthetic BAM per step (whole run of the reference CLI `{TAGS_CMD[args.workload]}`; wall clock)"
-        print(json.dumps({"impl": "reference", "metric": args.workload + " reads/sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        print(json.dumps({"impl": "reference", "metric": args.workload + " reads/sec (device-timed)", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": {"workload": args.workload + " (SURVEY 8f)", "sample": sample},
                           "cpu_baseline": {"value": v, "unit": "reads/s", "cores": 1, "kind": kind, "sample": sample, "cpu": cpu_model(), "host_cores": threads},
                           "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -271,7 +271,7 @@ def main():
         ms = 1e3 * sum(times) / len(times)
         v = total / (ms / 1e3)
         sample = f"{total}-read prefix of the same synthetic BAM per step (whole run of the unmodified reference CLI: inflate, parse, sample, sqlite insert + GROUP BY, gz output; wall clock)"
-        print(json.dumps({"impl": "reference", "metric": "bam2db reads/sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        print(json.dumps({"impl": "reference", "metric": "bam2db reads/sec (device-timed)", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                           "config": {"workload": workload, "sample": sample},
                           "cpu_baseline": {"value": v, "unit": "reads/s", "cores": 1, "kind": kind, "sample": sample, "cpu": cpu_model(), "host_cores": threads},
@@ -484,7 +484,7 @@ def main():
                 continue   # rank 0's local clocks only cover the streaming stages in the sharded job
             ms = st["ms_" + k]
             stages[k] = {"ms": round(ms, 3), "alg_GBps": round(bytes_ / (ms * 1e-3) / 1e9, 1) if ms > 0 else None}
-        line = {"metric": "bam2db reads/sec", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        line = {"metric": "bam2db reads/sec (device-timed)", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "timing": "value: device-timed (CUDA events), inputs resident in HBM; e2e: host wall clock from pinned host memory",
                 "config": {"workload": workload, "tiling": f"{base['reads']}-read zlib-6 BGZF segment ({base['compressed'] / 1e6:.0f} MB compressed, {base['inflated'] / 1e6:.0f} MB inflated) streamed {tiles}x per step",
@@ -587,7 +587,7 @@ def bench_freq(args):
     peak, peak_src = measured_peak()
     alg = stq["compressed_bytes"] + stq["inflated_bytes"]
     ach = alg / (stq["ms_inflate"] * 1e-3) / 1e9
-    line = {"metric": "freq reads/sec", "value": n_reads / (ms_step / 1e3), "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+    line = {"metric": "freq reads/sec (device-timed)", "value": n_reads / (ms_step / 1e3), "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"freq on synthetic R1 FASTQ: {n_reads} reads, 16 bp barcode + 12 bp UMI, 20000 true cells + 5 % error variants, -l 16 -u 12 (BASELINE.json configs[1])",
                        "tiling": f"{base_reads}-read BGZF segment x {tiles}", "l2": "inputs larger than L2", "ms_per_step_wall": 1e3 * wall / args.steps,
@@ -674,7 +674,7 @@ def bench_tags(args):
     peak, peak_src = measured_peak()
     alg = st["compressed_bytes"] + st["inflated_bytes"]
     ach = alg / (st["ms_inflate"] * 1e-3) / 1e9
-    line = {"metric": args.workload + " reads/sec", "value": n_reads / (dev_ms / 1e3), "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
+    line = {"metric": args.workload + " reads/sec (device-timed)", "value": n_reads / (dev_ms / 1e3), "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{args.workload} ({TAGS_CMD[args.workload]}) on the synthetic 10x-v3 BAM: {n_reads} reads, {N_CELLS} cells, {N_GENES} genes (SURVEY 8f)",
                        "l2": "inputs larger than L2", "counters": {k: st[k] for k in ("n_records", "n_hits", "n_groups", "n_blocks", "hash_rounds")}},
