@@ -203,3 +203,26 @@ def test_emu_records_straddling_bgzf_blocks(emu_lib, tmp_path):
     assert r.returncode == 0, r.stdout[-2000:]
     g = os.path.join(ROOT, "tests", "golden", "edge", "expect_c0.5_r0.5_s926")
     assert gzip.open(w / "out2" / "matrix.mtx.gz", "rb").read() == gzip.open(os.path.join(g, "matrix.mtx.gz"), "rb").read()
+
+
+def test_emu_inflate_random_streams(emu_lib):
+    """seeded random BGZF images (tests/inflate_cases.py: skewed distributions with code lengths up to 15 bits, runs, near and far matches,
+    random zlib levels / strategies / memLevels): byte for byte vs zlib for the thread-per-stream and the lock-step kernel"""
+    code = (
+        "import sys, ctypes as C, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from fastf_b200 import _lib\nimport inflate_cases\n"
+        "ctx = _lib.Context(0)\n"
+        "def inflate(img, lanes):\n"
+        "    buf = np.frombuffer(img, dtype=np.uint8); out, n, ms = C.c_void_p(), C.c_size_t(), C.c_float()\n"
+        "    assert ctx.lib.fastf_inflate_host(ctx.h, C.c_void_p(buf.ctypes.data), buf.size, lanes, C.byref(out), C.byref(n), C.byref(ms)) == 0, ctx.lib.fastf_last_error(ctx.h)\n"
+        "    d = C.string_at(out, n.value); ctx.lib.fastf_free(out); return d\n"
+        "k = 0\n"
+        "for img, want in inflate_cases.images(24):\n"
+        "    for lanes in (0, 32):\n"
+        "        assert inflate(img, lanes) == want, (k, lanes)\n"
+        "    k += 1\n"
+        "print('ok', k)\n"
+    ) % (ROOT, os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FASTF_GPU_LIB=emu_lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
+    assert r.returncode == 0 and "ok 24" in r.stdout, r.stdout[-3000:]

@@ -546,3 +546,12 @@ def test_records_straddling_bgzf_blocks(gpu_ctx, oracle, synth, tmp_path):
     assert open(tmp_path / "tag_summary.csv", "rb").read() == open(tmp_path / "o.csv", "rb").read()
     st, out = B.run_device(gpu_ctx, np.fromfile(paths["bam"], dtype=np.uint8), inputs, 0.5, 926, want_rows=False, inflate_lanes=B.BAM_STRADDLE)
     assert st["nnz"] == want["nnz"] and np.array_equal(out["m_count"], want["m_count"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lanes", [0, 1, 3, 4, 32, 8])
+def test_inflate_random_streams(gpu_ctx, lanes):
+    """seeded random BGZF images (tests/inflate_cases.py) against zlib, every kernel shape"""
+    import inflate_cases
+    for k, (img, want) in enumerate(inflate_cases.images(40, seed=7 + lanes)):
+        assert _inflate(gpu_ctx, img, lanes) == want, k
