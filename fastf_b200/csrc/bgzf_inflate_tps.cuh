@@ -45,8 +45,12 @@
 #endif
 #define FASTF_TPS_THREADS_OF(L, SVC) ((FASTF_TPS_STREAMS / (L) + (SVC)) * 32)
 // defaults (used by the host launch and the emulator test)
+#ifndef FASTF_TPS_LANES
 #define FASTF_TPS_LANES 16
+#endif
+#ifndef FASTF_TPS_SVC_WARPS
 #define FASTF_TPS_SVC_WARPS 24
+#endif
 #define FASTF_TPS_SORTED_U16 320   // per stream in GLOBAL scratch: symbols sorted by code length (288 lit/len + 32 dist), read only for codes longer than the tables
 #define FASTF_TPS_THREADS FASTF_TPS_THREADS_OF(FASTF_TPS_LANES, FASTF_TPS_SVC_WARPS)
 #ifndef FASTF_TPS_RING
@@ -56,7 +60,7 @@
 #define FASTF_TPS_TRIPLES 2           // literal tokens (three literals each) a decoder round may produce in front of a match
 #endif
 #ifndef FASTF_TPS_BATCH_MIN
-#define FASTF_TPS_BATCH_MIN 32u       // tokens that make a stream worth a visit of its service warp
+#define FASTF_TPS_BATCH_MIN (FASTF_TPS_RING >= 64u ? 32u : FASTF_TPS_RING / 2u)       // tokens that make a stream worth a visit of its service warp
 #endif
 #ifndef FASTF_TPS_PREFETCH2
 #define FASTF_TPS_PREFETCH2 0
@@ -84,11 +88,15 @@
 // stream states
 enum { FASTF_TPS_NEXT = 0, FASTF_TPS_RUN = 1, FASTF_TPS_BUILD = 2, FASTF_TPS_DONE = 3 };
 
+// Codes longer than a primary table of TBITS bits have 15 - TBITS possible lengths; per length the decoder needs a range limit and
+// an index offset (fastf_tps_build).  Limits sit in [0, OFFS), offsets in [OFFS, 2 OFFS), OFFS = 8 or 12 (vector loads).
+#define FASTF_TPS_WALK_OFFS(TBITS) ((15 - (TBITS)) <= 8 ? 8 : 12)
+#define FASTF_TPS_WALK_U16(TBITS) (2 * FASTF_TPS_WALK_OFFS(TBITS) < 16 ? 16 : 2 * FASTF_TPS_WALK_OFFS(TBITS))   // >= 16: the build counts code lengths in it first
 struct FastfTpsStream {
     u16 lit[1 << FASTF_TPS_LBITS];
     u16 dist[1 << FASTF_TPS_DBITS];
-    alignas(16) u16 lit_cnt[16];    // codes longer than the table: range limits [0, 8) and index offsets [8, 16) (fastf_tps_build)
-    alignas(16) u16 dist_cnt[16];
+    alignas(16) u16 lit_cnt[FASTF_TPS_WALK_U16(FASTF_TPS_LBITS)];
+    alignas(16) u16 dist_cnt[FASTF_TPS_WALK_U16(FASTF_TPS_DBITS)];
     u32 ring[FASTF_TPS_RING];
     // control block (volatile accesses; every hand-over is fenced)
     u32 state, wr, rd, last;
@@ -100,11 +108,29 @@ struct FastfTpsStream {
     u32 obase_lo, obase_hi;          // offset of the block in the inflated buffer
 };
 
+// Staged LZ77 (FASTF_TPS_STAGED): a service warp assembles the output of a token batch in shared memory -- literals, then the
+// matches whose source lies before the batch (global memory, all loads of a group in flight together), then in token order the
+// ones that read the batch's own bytes (shared memory latency instead of an L2 round trip each) -- and writes it out as whole
+// aligned words.  The staging area doubles as the scratch of stream set-up (a warp does one or the other).
+#ifndef FASTF_TPS_STAGED
+#define FASTF_TPS_STAGED 0
+#endif
+#ifndef FASTF_TPS_SB
+#define FASTF_TPS_SB 768u             // staging bytes per service warp (>= 3 + 258: one token always fits)
+#endif
+struct FastfTpsSvc {
+    union {
+        struct { u8 lens[320]; u16 scratch[32]; } setup;   // code lengths of the block being set up; first[16], start[16] while building
+        alignas(16) u8 sb[FASTF_TPS_SB + 8];
+    };
+#if FASTF_TPS_STAGED
+    alignas(8) u32 farlist[32][2];   // (token, offset in the batch) of the short far matches, compacted
+#endif
+};
 struct FastfTpsShared {
     u32 lenK[32], distK[32];         // base << 8 | extra bits
     u8 cl_order[20];
-    u8 lens[FASTF_TPS_MAX_SVC][320];      // code lengths of the block a service warp is setting up
-    u16 scratch[FASTF_TPS_MAX_SVC][32];   // first[16], start[16] while building
+    alignas(16) FastfTpsSvc svc[FASTF_TPS_MAX_SVC];
 };
 
 
@@ -129,6 +155,19 @@ __device__ __forceinline__ u32 fastf_ld_sorted(const u16 *p) { return *p; }
 #else
 __device__ __forceinline__ u32 fastf_ld_sorted(const u16 *p) { return __ldcg(p); }
 #endif
+#endif
+// A decoder knows the source of a match thousands of cycles before the stream's service warp copies it: it asks the L2 for the line
+// right away (the windows of all resident streams are far larger than the L2, so a distant source is usually a DRAM access).
+#ifndef FASTF_TPS_PREFETCH_SRC
+#define FASTF_TPS_PREFETCH_SRC 0u     // smallest distance worth a prefetch (0 = never)
+#endif
+#ifdef FASTF_EMU
+__device__ __forceinline__ void fastf_prefetch_l2(const void *) {}
+#else
+__device__ __forceinline__ void fastf_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+#ifndef FASTF_TPS_NOCOPY
+#define FASTF_TPS_NOCOPY 0            // measurement builds only: 1 = service warps skip the match copies, 2 = they store nothing at all
 #endif
 __device__ __forceinline__ u32 fastf_ldv(const u32 *p) { return *(const volatile u32 *)p; }
 __device__ __forceinline__ void fastf_stv(u32 *p, u32 v) { *(volatile u32 *)p = v; }
@@ -182,14 +221,18 @@ __device__ __forceinline__ u32 fastf_tps_build(u32 alpha, const u8 *lens, u32 n,
         first[0] = (u16)used;
         // For the codes longer than the table the decoder needs, per length l = tbits+1+k: the left-aligned (15-bit) end of the
         // length's code range (ranges of a canonical code follow one another in length order) and start[l] - first[l], the offset
-        // that turns a code into its index in sorted[].  They replace the counts in cnt[]: limits in [0, 8), offsets in [8, 16).
-        u16 lim[8], off[8];
-        for (u32 k = 0; k < 8; k++) {
+        // that turns a code into its index in sorted[].  They replace the counts in cnt[]: limits in [0, OFFS), offsets behind them.
+        const u32 offs_at = FASTF_TPS_WALK_OFFS(tbits);
+        u16 lim[12], off[12];
+#pragma unroll
+        for (u32 k = 0; k < 12; k++) {
             const u32 l = tbits + 1 + k;
             lim[k] = l <= 15 ? (u16)(((u32)first[l] + cnt[l]) << (15 - l)) : (u16)0xffff;
             off[k] = l <= 15 ? (u16)((u32)start[l] - (u32)first[l]) : (u16)0;
         }
-        for (u32 k = 0; k < 8; k++) { cnt[k] = lim[k]; cnt[8 + k] = off[k]; }
+#pragma unroll
+        for (u32 k = 0; k < 12; k++)
+            if (k < offs_at) { cnt[k] = lim[k]; cnt[offs_at + k] = off[k]; }
     }
     bad = __shfl_sync(FASTF_FULL_MASK, bad, 0);
     wk = __shfl_sync(FASTF_FULL_MASK, wk, 0);
@@ -211,7 +254,7 @@ __device__ __forceinline__ u32 fastf_tps_build(u32 alpha, const u8 *lens, u32 n,
     return 0;
 }
 
-// lock-step lookup used by the service warp while it reads the code-length code (7-bit table in the distance table's storage;
+// lock-step lookup used by the service warp while it reads the code-length code (7-bit table in the literal table's storage;
 // code-length codes are at most 7 bits long, so every valid one is resolved by the table)
 __device__ __forceinline__ u32 fastf_tps_decode16(const FastfBitReader<32> &br, const u16 *lut, u32 tbits)
 {
@@ -245,8 +288,8 @@ __device__ __forceinline__ void fastf_tps_setup(const FastfTpsArgs &A, FastfTpsS
     const u64 in_end = ((u64)S.inend_hi << 32) | S.inend_lo;
     u64 bitpos = ((u64)S.bitpos_hi << 32) | S.bitpos_lo;
     u32 opos = S.opos, err = 0;
-    u8 *lens = G.lens[sw];
-    u16 *first = G.scratch[sw], *start = G.scratch[sw] + 16;
+    u8 *lens = G.svc[sw].setup.lens;
+    u16 *first = G.svc[sw].setup.scratch, *start = G.svc[sw].setup.scratch + 16;
     for (;;) {
         if (bitpos + 3 > in_end) { err |= FASTF_ST_IN_OVERRUN; break; }
         FastfBitReader<32> br;
@@ -294,12 +337,12 @@ __device__ __forceinline__ void fastf_tps_setup(const FastfTpsArgs &A, FastfTpsS
             }
             __syncwarp();
             u32 wk;
-            if (fastf_tps_build(FASTF_ALPHA_PLAIN, lens, 19, S.dist_cnt, dist_sorted, S.dist, 7, first, start, &wk, lane)) { err |= FASTF_ST_BAD_CODELENS; break; }
+            if (fastf_tps_build(FASTF_ALPHA_PLAIN, lens, 19, S.lit_cnt, dist_sorted, S.lit, 7, first, start, &wk, lane)) { err |= FASTF_ST_BAD_CODELENS; break; }
             const u32 n = hlit + hdist;
             u32 i = 0, prev = 0;
             while (i < n) {
                 br.refill();
-                const u32 e = fastf_tps_decode16(br, S.dist, 7);
+                const u32 e = fastf_tps_decode16(br, S.lit, 7);
                 if ((e & 15u) == 0) { err |= FASTF_ST_BAD_CODELENS; break; }
                 br.drop(e & 15u);
                 const u32 sym = e >> 8;
@@ -317,7 +360,7 @@ __device__ __forceinline__ void fastf_tps_setup(const FastfTpsArgs &A, FastfTpsS
             if (lens[256] == 0) { err |= FASTF_ST_BAD_CODELENS; break; }
         }
         u32 wl, wd;
-        // the distance lengths sit behind the literal/length ones in `lens`; the distance table's storage was the code-length table
+        // the distance lengths sit behind the literal/length ones in `lens`; the literal table's storage was the code-length table
         if (fastf_tps_build(FASTF_ALPHA_LITLEN, lens, hlit, S.lit_cnt, lit_sorted, S.lit, FASTF_TPS_LBITS, first, start, &wl, lane)) { err |= FASTF_ST_BAD_CODELENS; break; }
         if (fastf_tps_build(FASTF_ALPHA_DIST, lens + hlit, hdist, S.dist_cnt, dist_sorted, S.dist, FASTF_TPS_DBITS, first, start, &wd, lane)) { err |= FASTF_ST_BAD_CODELENS; break; }
         const u64 consumed = (u64)br.widx * 32u - br.nbits - br.skip_bits;
@@ -364,7 +407,7 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
     }
     const u32 off = inc - mylen;
     const u32 total = __shfl_sync(FASTF_FULL_MASK, inc, 31);
-    if (is_lit) {
+    if (is_lit && FASTF_TPS_NOCOPY < 2) {
         out[opos + off] = (u8)tok;
         if (mylen > 1u) out[opos + off + 1u] = (u8)(tok >> 8);
         if (mylen > 2u) out[opos + off + 2u] = (u8)(tok >> 16);
@@ -381,6 +424,7 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
         const bool far = is_match && len <= FASTF_TPS_FAR_LEN && off + len <= dist;   // source ends before the batch starts (implies dist >= len)
         farm = __ballot_sync(FASTF_FULL_MASK, far);
         slowm = __ballot_sync(FASTF_FULL_MASK, is_match && !far);
+        if (FASTF_TPS_NOCOPY) farm = slowm = 0;
     }
     __syncwarp();
     while (farm) {
@@ -455,6 +499,163 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
     return consumed;
 }
 
+#if FASTF_TPS_STAGED
+// four bytes from an arbitrary address (two aligned words and a funnel shift; the bytes around the range are read and ignored)
+__device__ __forceinline__ u32 fastf_ld4_unaligned(const u8 *p)
+{
+    const u32 al = (u32)(uintptr_t)p & 3u;
+    const u32 *w = reinterpret_cast<const u32 *>(p - al);
+    const u32 w0 = w[0], w1 = w[1];
+#ifdef FASTF_EMU
+    return al ? (w0 >> (8u * al)) | (w1 << (32u - 8u * al)) : w0;
+#else
+    return __funnelshift_r(w0, w1, 8u * al);
+#endif
+}
+__device__ __forceinline__ void fastf_sts_bytes(u8 *d, u32 v, u32 nb)
+{
+    if (nb > 0u) d[0] = (u8)v;
+    if (nb > 1u) d[1] = (u8)(v >> 8);
+    if (nb > 2u) d[2] = (u8)(v >> 16);
+    if (nb > 3u) d[3] = (u8)(v >> 24);
+}
+
+// LZ77 resolution of up to 32 tokens of one stream by a whole warp, through the warp's staging area.  Returns the tokens consumed.
+__device__ __forceinline__ u32 fastf_tps_copy_staged(const FastfTpsArgs &A, FastfTpsStream &S, FastfTpsSvc &W, u32 rd, u32 n, u32 lane)
+{
+    u8 *out = A.out + (((u64)S.obase_hi << 32) | S.obase_lo);
+    const u32 opos = S.opos;
+    const u32 a = (S.obase_lo + opos) & 3u;   // the batch starts at byte a of an aligned global word; staging byte i <-> global byte opos - a + i
+    u8 *sb = W.sb;
+    u32 tok = (lane < n) ? fastf_ldv(&S.ring[(rd + lane) & (FASTF_TPS_RING - 1u)]) : FASTF_TOK_END;
+    const u32 endm = __ballot_sync(FASTF_FULL_MASK, lane < n && (tok >> 30) == 2u);
+    u32 ntok = n;
+    if (endm) ntok = (u32)__ffs((int)endm) - 1u;
+    u32 mylen = 0;
+    if (lane < ntok) mylen = (tok >> 30) == 0u ? ((tok >> 24) & 3u) : (tok & 511u);
+    u32 inc = mylen;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(FASTF_FULL_MASK, inc, o);
+        if ((int)lane >= o) inc += t;
+    }
+    // only what fits the staging area is taken now (a batch is ~130 bytes on BAM data; the cap matters for runs of long matches)
+    const u32 nfit = (u32)__popc(__ballot_sync(FASTF_FULL_MASK, lane < ntok && a + inc <= FASTF_TPS_SB));
+    const bool ended = endm != 0u && nfit == ntok;
+    ntok = nfit;
+    const u32 off = inc - mylen;
+    const u32 total = ntok ? __shfl_sync(FASTF_FULL_MASK, inc, (int)(ntok - 1u)) : 0u;
+    const bool is_lit = lane < ntok && (tok >> 30) == 0u;
+    const bool is_match = lane < ntok && (tok >> 30) == 1u;
+    const u32 len = tok & 511u, dist = (tok >> 9) & 0xffffu;
+    if (is_lit && FASTF_TPS_NOCOPY < 2) fastf_sts_bytes(sb + a + off, tok, mylen);
+    // "far" = the whole source lies before the batch: final bytes in global memory, no dependency on anything in the batch
+    const bool far = is_match && dist >= off + len;
+    const u32 far32m = FASTF_TPS_NOCOPY ? 0u : __ballot_sync(FASTF_FULL_MASK, far && len <= 32u);
+    u32 farlongm = FASTF_TPS_NOCOPY ? 0u : __ballot_sync(FASTF_FULL_MASK, far && len > 32u);
+    u32 nearm = FASTF_TPS_NOCOPY ? 0u : __ballot_sync(FASTF_FULL_MASK, is_match && !far);
+    if (far && len <= 32u) {
+        const u32 r = (u32)__popc(far32m & ((1u << lane) - 1u));
+        W.farlist[r][0] = tok; W.farlist[r][1] = off;
+    }
+    __syncwarp();
+    // short far matches: eight lanes x four bytes each, four matches per step, two steps in flight
+    const u32 nfar = (u32)__popc(far32m);
+    const u32 sub = (lane & 7u) * 4u;
+    for (u32 i = 0; i < nfar; i += 8u) {
+        u32 v[2], nb[2], dpos[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const u32 idx = i + 4u * (u32)u + (lane >> 3);
+            nb[u] = 0; v[u] = 0; dpos[u] = 0;
+            if (idx < nfar) {
+                const uint2 e = *reinterpret_cast<const uint2 *>(W.farlist[idx]);
+                const u32 l = e.x & 511u, d = (e.x >> 9) & 0xffffu;
+                if (sub < l) {
+                    nb[u] = l - sub < 4u ? l - sub : 4u;
+                    dpos[u] = a + e.y + sub;
+                    v[u] = fastf_ld4_unaligned(out + (opos + e.y + sub) - d);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) fastf_sts_bytes(sb + dpos[u], v[u], nb[u]);
+    }
+    // long far matches (up to 258 bytes): 32 lanes x four bytes per step
+    while (farlongm) {
+        const u32 m = (u32)__ffs((int)farlongm) - 1u;
+        farlongm &= farlongm - 1u;
+        const u32 t = __shfl_sync(FASTF_FULL_MASK, tok, (int)m), o = __shfl_sync(FASTF_FULL_MASK, off, (int)m);
+        const u32 l = t & 511u, d = (t >> 9) & 0xffffu;
+        u32 v[3], nb[3];
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const u32 j = lane * 4u + 128u * (u32)u;
+            nb[u] = 0; v[u] = 0;
+            if (j < l) {
+                nb[u] = l - j < 4u ? l - j : 4u;
+                v[u] = fastf_ld4_unaligned(out + (opos + o + j) - d);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; u++) fastf_sts_bytes(sb + a + o + lane * 4u + 128u * (u32)u, v[u], nb[u]);
+    }
+    // the rest reads bytes of this batch (or overlaps itself): token order, out of the staging area; what lies before the batch
+    // comes from global memory
+    while (nearm) {
+        const u32 m = (u32)__ffs((int)nearm) - 1u;
+        nearm &= nearm - 1u;
+        const u32 t = __shfl_sync(FASTF_FULL_MASK, tok, (int)m), o = __shfl_sync(FASTF_FULL_MASK, off, (int)m);
+        const u32 l = t & 511u, d = (t >> 9) & 0xffffu;
+        __syncwarp();   // everything staged so far is ordered before these loads
+        // source byte r of the match sits at batch offset o - d + r; an overlapping match (d < l) repeats its first d bytes
+        const u32 rcp = (u32)(1048576.0f * __frcp_rn((float)d)) + 2u;
+        for (u32 k = 0; k < l; k += 32u) {
+            const u32 j = k + lane;
+            if (j < l) {
+                u32 r = j;
+                if (d < l) {
+                    const u32 q = (j * rcp) >> 20;   // j / d for j < 258, off by at most one
+                    r = j - q * d;
+                    if (r >= d) r += d;
+                }
+                const i32 sp = (i32)(o + r) - (i32)d;
+                sb[a + o + j] = sp < 0 ? out[(i32)opos + sp] : sb[a + (u32)sp];
+            }
+        }
+    }
+    __syncwarp();
+    // write the batch out: whole aligned words, single bytes at the two ends
+    if (FASTF_TPS_NOCOPY < 2) {
+        u8 *gbase = out + opos - a;
+        const u32 hi = a + total;
+        for (u32 w = lane * 4u; w < hi; w += 128u) {
+            if (w >= a && w + 4u <= hi) *reinterpret_cast<u32 *>(gbase + w) = *reinterpret_cast<const u32 *>(sb + w);
+            else {
+#pragma unroll
+                for (u32 b = 0; b < 4u; b++)
+                    if (w + b >= a && w + b < hi) gbase[w + b] = sb[w + b];
+            }
+        }
+    }
+    u32 consumed = ntok;
+    const u32 new_opos = opos + total;
+    if (ended) {
+        const u32 e = __shfl_sync(FASTF_FULL_MASK, tok, (int)ntok) & 0xffffu;
+        if (lane == 0) A.status[S.blk] = e | ((e == 0 && new_opos != S.isize) ? (u32)FASTF_ST_SIZE_MISMATCH : 0u);
+        consumed = ntok + 1;
+    }
+    __syncwarp();   // the staging area and the stores of this batch are done before the next batch starts
+    if (lane == 0) {
+        S.opos = new_opos;
+        FASTF_SMEM_ORDER();
+        fastf_stv(&S.rd, rd + consumed);
+    }
+    __syncwarp();
+    return consumed;
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------------------------
 // decoder side (one thread = one stream)
 // ------------------------------------------------------------------------------------------------------------------
@@ -507,15 +708,20 @@ struct FastfTpsReader {
 template <int TBITS>
 __device__ __forceinline__ u32 fastf_tps_walk(u64 buf, const u16 *lb, const u16 *sorted, u32 alpha)
 {
+    constexpr int NL = 15 - TBITS, OFFS = FASTF_TPS_WALK_OFFS(TBITS);
     const u32 code15 = __brev((u32)buf) >> 17;   // the next 15 stream bits, first bit most significant
     const uint4 L4 = *reinterpret_cast<const uint4 *>(lb);
-    const u32 w[4] = {L4.x, L4.y, L4.z, L4.w};
+    u32 w[6] = {L4.x, L4.y, L4.z, L4.w, 0xffffffffu, 0xffffffffu};
+    if (NL > 8) {
+        const uint2 L2 = *reinterpret_cast<const uint2 *>(lb + 8);
+        w[4] = L2.x; w[5] = L2.y;
+    }
     u32 k = 0;
 #pragma unroll
-    for (int i = 0; i < 15 - TBITS; i++) k += code15 >= ((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu));
-    if (k >= (u32)(15 - TBITS)) return FASTF_T16_BAD << 4;
+    for (int i = 0; i < NL; i++) k += code15 >= ((i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu));
+    if (k >= (u32)NL) return FASTF_T16_BAD << 4;
     const u32 len = (u32)TBITS + 1u + k;
-    const u32 idx = ((code15 >> (15u - len)) + (u32)lb[8 + k]) & 0xffffu;
+    const u32 idx = ((code15 >> (15u - len)) + (u32)lb[OFFS + k]) & 0xffffu;
     return fastf_make16(alpha, fastf_ld_sorted(sorted + idx)) | len;
 }
 
@@ -551,6 +757,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
         bool have = false;
         u32 wr = 0, rd_cache = 0, pos = 0, isize = 0, last = 0;
         u64 in_end = 0;
+        const u8 *obase = A.out;
         for (;;) {
             if (!have) {
                 const u32 st = fastf_ldv(&S.state);
@@ -560,6 +767,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
                 br.init(A.comp, A.comp_total, ((u64)S.bitpos_hi << 32) | S.bitpos_lo);
                 pos = S.pos; isize = S.isize; last = S.last;
                 in_end = ((u64)S.inend_hi << 32) | S.inend_lo;
+                if (FASTF_TPS_PREFETCH_SRC) obase = A.out + (((u64)S.obase_hi << 32) | S.obase_lo);
                 wr = S.wr;
                 have = true;
             }
@@ -626,6 +834,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
                     else if (pos + len > isize) err = FASTF_ST_OUT_OVERFLOW;
                     else {
                         fastf_stv(&S.ring[wr & (FASTF_TPS_RING - 1u)], FASTF_TOK_MATCH | len | (dist << 9));
+                        if (FASTF_TPS_PREFETCH_SRC && dist >= FASTF_TPS_PREFETCH_SRC) fastf_prefetch_l2(obase + pos - dist);
                         wr++;
                         pos += len;
                     }
@@ -696,7 +905,11 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
                 FastfTpsStream &S = streams[sidx];
                 u16 *ssorted = sorted_base + (size_t)sidx * FASTF_TPS_SORTED_U16;
                 if (w == 1) {
+#if FASTF_TPS_STAGED
+                    fastf_tps_copy_staged(A, S, G.svc[sw], krd, kav < 32u ? kav : 32u, lane);
+#else
                     fastf_tps_copy(A, S, krd, kav < 32u ? kav : 32u, lane);
+#endif
                 } else if (w == 2) {
                     // fetch the next BGZF block for this stream
                     u32 b = 0;

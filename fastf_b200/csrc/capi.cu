@@ -218,6 +218,9 @@ extern "C" int fastf_ctx_create(int device, fastf_ctx **out)
     ctx->n_sm = 2;
 #else
     if (cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->n_sm <= 0) ctx->n_sm = 148;
+    // LZ77 match sources are short reads at random places of windows that do not fit the L2 together: a miss should fetch one
+    // 32-byte sector, not a 64/128-byte neighbourhood (measured in profiles/: DRAM read traffic of the inflate kernel)
+    if (const char *g = getenv("FASTF_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
 #endif
     std::thread([] { fastf_mtj::tables(); }).detach();   // GF(2) jump tables (0.2 s of host work) while the first job streams
     ctx->dev_pool = new std::vector<PoolEntry>();

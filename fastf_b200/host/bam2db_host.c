@@ -7,6 +7,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
+#include <fcntl.h>
+#include <unistd.h>
 
 int _umi_copies_flag = 0;
 int fastf_device = 0;
@@ -43,6 +45,63 @@ static int exec_sql(sqlite3 *db, const char *sql)
     return 0;
 }
 
+/* root page of a table (sqlite_master.rootpage); 0 when absent */
+static unsigned table_root(sqlite3 *db, const char *name)
+{
+    sqlite3_stmt *st = NULL;
+    unsigned root = 0;
+    if (sqlite3_prepare_v2(db, "SELECT rootpage FROM sqlite_master WHERE type='table' AND name=?1;", -1, &st, NULL) != SQLITE_OK) return 0;
+    sqlite3_bind_text(st, 1, name, -1, SQLITE_TRANSIENT);
+    if (sqlite3_step(st) == SQLITE_ROW) root = (unsigned)sqlite3_column_int(st, 0);
+    sqlite3_finalize(st);
+    return root;
+}
+
+/* packed row key -> cell, gene, UMI blob (NULL UMI: returns -1 as the blob length) */
+static inline int key_fields(uint64_t k, uint32_t bu, uint32_t bg, uint32_t mb, int64_t *cell, int64_t *gene, uint8_t blob[8], uint64_t *content_out)
+{
+    const uint64_t code = k & ((1ull << bu) - 1);
+    *gene = (int64_t)((k >> bu) & ((1ull << bg) - 1));
+    *cell = (int64_t)(k >> (bu + bg));
+    if (!((code >> (bu - 1)) & 1)) return -1;
+    const uint64_t content = (code >> 3) & ((1ull << (8 * mb)) - 1);
+    for (uint32_t b = 0; b < mb; b++) blob[b] = (uint8_t)(content >> (8 * (mb - 1 - b)));
+    if (content_out) *content_out = content;
+    return (int)(code & 7);
+}
+
+typedef struct { const uint64_t *keys; uint32_t bu, bg, mb; } umi_rows;
+static void umi_row_enc(void *c, uint64_t i, uint8_t *types, unsigned *ncol, uint8_t *body, unsigned *nb)
+{
+    const umi_rows *R = (const umi_rows *)c;
+    int64_t cell, gene;
+    uint8_t blob[8];
+    const int bl = key_fields(R->keys[i], R->bu, R->bg, R->mb, &cell, &gene, blob, NULL);
+    unsigned n = fastf_sqlite_int_col(cell, &types[0], body);
+    n += fastf_sqlite_int_col(gene, &types[1], body + n);
+    types[2] = bl < 0 ? 0 : (uint8_t)(12 + 2 * bl);   /* NULL, or a blob of bl bytes */
+    if (bl > 0) { memcpy(body + n, blob, (size_t)bl); n += (unsigned)bl; }
+    *ncol = 3; *nb = n;
+}
+typedef struct { const uint32_t *gene, *cell, *count; } mtx_rows;
+static void mtx_row_enc(void *c, uint64_t i, uint8_t *types, unsigned *ncol, uint8_t *body, unsigned *nb)
+{
+    const mtx_rows *M = (const mtx_rows *)c;
+    unsigned n = fastf_sqlite_int_col((int)M->gene[i], &types[0], body);
+    n += fastf_sqlite_int_col((int)M->cell[i], &types[1], body + n);
+    n += fastf_sqlite_int_col((int)M->count[i], &types[2], body + n);
+    *ncol = 3; *nb = n;
+}
+static unsigned mtx_line_fmt(void *c, uint64_t i, char *p)
+{
+    const mtx_rows *M = (const mtx_rows *)c;
+    char *q = p;
+    q += fastf_fmt_i64(q, (int)M->gene[i]); *q++ = ' ';
+    q += fastf_fmt_i64(q, (int)M->cell[i]); *q++ = ' ';
+    q += fastf_fmt_i64(q, (int)M->count[i]); *q++ = '\n';
+    return (unsigned)(q - p);
+}
+
 int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, char *features_file, float rate_cell, float rate_depth, unsigned int seed)
 {
     int rc = 1;
@@ -56,14 +115,14 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
     strset cset = {0}, fset = {0};
     uint64_t *samp = NULL;
     void *pin[2] = {NULL, NULL};
-    FILE *bam = NULL;
-    gzFile gb = NULL, gf = NULL, file_barcode = NULL, file_feature = NULL, file_matrix = NULL, file_umi = NULL;
+    int bam = -1;
+    gzFile gb = NULL, gf = NULL, file_barcode = NULL, file_feature = NULL;
     char line[1024], path[2048];
 
     if (sqlite3_open(db_file, &db)) { fprintf(stderr, "Can't open database: %s\n", sqlite3_errmsg(db)); goto done; }
     fprintf(stderr, "Opened database successfully\n");
-    bam = fopen(bam_file, "rb");
-    if (!bam) { fprintf(stderr, "Can't open BAM file %s\n", bam_file); goto done; }
+    bam = open(bam_file, O_RDONLY);
+    if (bam < 0) { fprintf(stderr, "Can't open BAM file %s\n", bam_file); goto done; }
     fprintf(stderr, "Opened BAM file %s successfully\n", bam_file);
     gb = gzopen(barcodes_file, "r");
     if (!gb) { fprintf(stderr, "Can't open cell barcode file %s\n", barcodes_file); goto done; }
@@ -157,13 +216,15 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
         if (fastf_bam2db_begin(ctx, &p, &job)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
         const size_t PIECE = (size_t)256 << 20;
         if (!pin[0] && (fastf_host_alloc(ctx, PIECE, &pin[0]) || fastf_host_alloc(ctx, PIECE, &pin[1]))) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
-        size_t got;
+        ssize_t got;
+        off_t at = 0;
         int which = 0, failed = 0;
-        rewind(bam);
-        while (!failed && (got = fread(pin[which], 1, PIECE, bam)) > 0) {
-            failed = fastf_bam2db_feed(job, pin[which], got);
+        while (!failed && (got = fastf_pread_parallel(bam, pin[which], PIECE, at)) > 0) {   /* several readers: one fread() cannot feed PCIe */
+            failed = fastf_bam2db_feed(job, pin[which], (size_t)got);
+            at += got;
             which ^= 1;
         }
+        if (!failed && got < 0) { fprintf(stderr, "\x1b[31mError:\x1b[0m reading %s failed\n", bam_file); goto done; }
         if (!failed) failed = fastf_bam2db_finish(job, &res);
         if (!failed) break;
         if (umi_bytes == 3 && strstr(fastf_last_error(ctx), "umi-too-long")) { fastf_bam2db_job_free(job); job = NULL; continue; }
@@ -178,33 +239,23 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
         goto done;
     }
 
-    /* ---- table umi in read order (reference :351-435) ---- */
-    exec_sql(db, "BEGIN TRANSACTION");
-    sqlite3_prepare_v2(db, "INSERT INTO umi VALUES (?1, ?2, ?3);", -1, &stmt, NULL);
+    /* ---- tables umi (read order, reference :351-435), mtx (:480-483) and numi (:527-530) ----
+     * sqlite creates the empty tables; the rows are then laid out directly as b-tree pages (sqlite_bulk.c): at 10^8 rows a
+     * sqlite3_step() per row costs minutes behind a device job of seconds. */
+    if (exec_sql(db, "CREATE TABLE mtx(\n  feature_index INT,\n  cell_index INT,\n  expression_level\n)")) goto done;
+    if (_umi_copies_flag && exec_sql(db, "CREATE TABLE numi(\n  feature_index INT,\n  cell_index INT,\n  encoded_umi TEXT,\n  n_copy\n)")) goto done;
+    const unsigned root_umi = table_root(db, "umi"), root_mtx = table_root(db, "mtx"), root_numi = _umi_copies_flag ? table_root(db, "numi") : 0;
+    if (!root_umi || !root_mtx || (_umi_copies_flag && !root_numi)) { fprintf(stderr, "SQL error: table root pages not found\n"); goto done; }
+    if (sqlite3_close(db) != SQLITE_OK) { fprintf(stderr, "SQL error: %s\n", sqlite3_errmsg(db)); goto done; }
+    db = NULL;
+    const uint32_t bu = res.bits_umi, bg = res.bits_gene, mb = res.umi_max_bytes;
     {
-        const uint32_t bu = res.bits_umi, bg = res.bits_gene, mb = res.umi_max_bytes;
-        for (uint64_t i = 0; i < res.n_rows; i++) {
-            uint64_t k = res.row_keys[i];
-            uint64_t code = k & ((1ull << bu) - 1);
-            int gene = (int)((k >> bu) & ((1ull << bg) - 1)), cell = (int)(k >> (bu + bg));
-            sqlite3_bind_int(stmt, 1, cell);
-            sqlite3_bind_int(stmt, 2, gene);
-            if ((code >> (bu - 1)) & 1) {
-                uint8_t blob[8];
-                uint64_t content = (code >> 3) & ((1ull << (8 * mb)) - 1);
-                int nb = (int)(code & 7);
-                for (uint32_t b = 0; b < mb; b++) blob[b] = (uint8_t)(content >> (8 * (mb - 1 - b)));
-                sqlite3_bind_blob(stmt, 3, blob, nb, SQLITE_TRANSIENT);
-            } else {
-                sqlite3_bind_null(stmt, 3);
-            }
-            if (sqlite3_step(stmt) != SQLITE_DONE) { fprintf(stderr, "SQL error: %s\n", sqlite3_errmsg(db)); goto done; }
-            sqlite3_reset(stmt);
-        }
+        fastf_sqlite_bulk *bulk = fastf_sqlite_bulk_begin(db_file, root_umi);
+        if (!bulk) { fprintf(stderr, "SQL error: cannot append to table umi of %s\n", db_file); goto done; }
+        umi_rows R = {res.row_keys, bu, bg, mb};
+        fastf_sqlite_bulk_rows_parallel(bulk, res.n_rows, umi_row_enc, &R);
+        if (fastf_sqlite_bulk_end(bulk)) { fprintf(stderr, "SQL error: writing table umi of %s failed\n", db_file); goto done; }
     }
-    exec_sql(db, "END TRANSACTION");
-    sqlite3_finalize(stmt);
-    stmt = NULL;
     printf("In %s, total fastQ reads: %zu\n", bam_file, (size_t)res.total);
     printf("In %s, sampled fastQ reads: %zu\n", bam_file, (size_t)res.sampled);
     printf("In %s, sampled and valid fastQ reads: %zu\n", bam_file, (size_t)res.valid);
@@ -214,28 +265,29 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
     if (!(file_barcode = gzopen(path, "wb"))) { fprintf(stderr, "\x1b[31mError:\x1b[0m can not open file %s\n", path); goto done; }
     snprintf(path, sizeof path, "%s/features.tsv.gz", path_out);
     if (!(file_feature = gzopen(path, "wb"))) { fprintf(stderr, "\x1b[31mError:\x1b[0m can not open file %s\n", path); goto done; }
-    snprintf(path, sizeof path, "%s/matrix.mtx.gz", path_out);
-    if (!(file_matrix = gzopen(path, "wb"))) { fprintf(stderr, "\x1b[31mError:\x1b[0m can not open file %s\n", path); goto done; }
-    /* table mtx: the device COO, under the schema text sqlite gives `CREATE TABLE mtx AS SELECT ...` */
-    if (exec_sql(db, "CREATE TABLE mtx(\n  feature_index INT,\n  cell_index INT,\n  expression_level\n)")) goto done;
-    exec_sql(db, "BEGIN TRANSACTION");
-    sqlite3_prepare_v2(db, "INSERT INTO mtx VALUES (?1, ?2, ?3);", -1, &stmt, NULL);
-    for (uint64_t i = 0; i < res.nnz; i++) {
-        sqlite3_bind_int(stmt, 1, (int)res.m_gene[i]); sqlite3_bind_int(stmt, 2, (int)res.m_cell[i]); sqlite3_bind_int(stmt, 3, (int)res.m_count[i]);
-        if (sqlite3_step(stmt) != SQLITE_DONE) { fprintf(stderr, "SQL error: %s\n", sqlite3_errmsg(db)); goto done; }
-        sqlite3_reset(stmt);
+    {
+        /* table mtx = the device COO */
+        fastf_sqlite_bulk *bulk = fastf_sqlite_bulk_begin(db_file, root_mtx);
+        if (!bulk) { fprintf(stderr, "SQL error: cannot append to table mtx of %s\n", db_file); goto done; }
+        mtx_rows M = {res.m_gene, res.m_cell, res.m_count};
+        fastf_sqlite_bulk_rows_parallel(bulk, res.nnz, mtx_row_enc, &M);
+        if (fastf_sqlite_bulk_end(bulk)) { fprintf(stderr, "SQL error: writing table mtx of %s failed\n", db_file); goto done; }
     }
-    exec_sql(db, "END TRANSACTION");
-    sqlite3_finalize(stmt);
-    stmt = NULL;
-    /* the reference's "%%%M" prints "%%M" with glibc (src/bam2db_ds.c:500) */
-    gzprintf(file_matrix,
+    {
+        /* matrix.mtx.gz: header (the reference's "%%%M" prints "%%M" with glibc, src/bam2db_ds.c:500), dimensions, one line per entry */
+        fastf_textbuf tb = {0};
+        fastf_textbuf_reserve(&tb, 4096 + strlen(bam_file));
+        tb.n += (size_t)snprintf(tb.p, tb.cap,
              "%%%%MatrixMarket matrix coordinate integer general\n%%metadata_json: \n%%{\n%%\t\"software_version\": \"fastF-1.0.0\",\n%%\t\"format_version\": 1,\n"
              "%%\t\"parent_bam\": \"%s\",\n%%\t\"rate_cell\": %.3f,\n%%\t\"rate_depth\": %.3f,\n%%\t\"total_n_FastQ\": %zu,\n%%\t\"sampled_n_FastQ\": %zu,\n"
-             "%%\t\"sampled_valid_n_FastQ\": %zu\n%%}\n",
-             bam_file, rate_cell, rate_depth, (size_t)res.total, (size_t)res.sampled, (size_t)res.valid);
-    gzprintf(file_matrix, "%zu %zu %zu\n", (size_t)fkeys.n, (size_t)cells.n, (size_t)res.nnz);
-    for (uint64_t i = 0; i < res.nnz; i++) gzprintf(file_matrix, "%d %d %d\n", (int)res.m_gene[i], (int)res.m_cell[i], (int)res.m_count[i]);
+             "%%\t\"sampled_valid_n_FastQ\": %zu\n%%}\n%zu %zu %zu\n",
+             bam_file, rate_cell, rate_depth, (size_t)res.total, (size_t)res.sampled, (size_t)res.valid, (size_t)fkeys.n, (size_t)cells.n, (size_t)res.nnz);
+        snprintf(path, sizeof path, "%s/matrix.mtx.gz", path_out);
+        mtx_rows M = {res.m_gene, res.m_cell, res.m_count};
+        const int wrc = fastf_gz_write_lines_parallel(path, tb.p, tb.n, res.nnz, mtx_line_fmt, &M);
+        fastf_textbuf_free(&tb);
+        if (wrc) { fprintf(stderr, "\x1b[31mError:\x1b[0m can not open file %s\n", path); goto done; }
+    }
     printf("matrix.mtx.gz is generated.\n");
     for (uint32_t i = 0; i < cells.n; i++) { gzwrite(file_barcode, cells.buf + cells.off[i], cells.off[i + 1] - cells.off[i]); gzputc(file_barcode, '\n'); }
     printf("barcodes.tsv.gz is generated.\n");
@@ -246,41 +298,47 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
     }
     printf("features.tsv.gz is generated.\n");
     if (_umi_copies_flag) {
-        /* numi: copies per distinct (cell, gene, umi) in (cell, gene, umi) order, NULL first (reference :527-556); decode_DNA(blob, 10) at :629 */
-        snprintf(path, sizeof path, "%s/umi.tsv.gz", path_out);
-        if (!(file_umi = gzopen(path, "wb"))) { fprintf(stderr, "\x1b[31mError:\x1b[0m can not open file %s\n", path); goto done; }
+        /* numi: copies per distinct (cell, gene, umi) in (cell, gene, umi) order, NULL first (reference :527-556); decode_DNA(blob, 10) at :629.
+         * The rows are sorted on the device; the run lengths are counted here while the table and the text are laid out. */
         uint64_t n = res.n_rows, *k = (uint64_t *)malloc(sizeof(uint64_t) * (n ? n : 1));
         memcpy(k, res.row_keys, sizeof(uint64_t) * n);
         if (fastf_sort_u64_host(ctx, k, NULL, n, res.bits_cell + res.bits_gene + res.bits_umi)) { free(k); fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
-        if (exec_sql(db, "CREATE TABLE numi(\n  feature_index INT,\n  cell_index INT,\n  encoded_umi TEXT,\n  n_copy\n)")) { free(k); goto done; }
-        exec_sql(db, "BEGIN TRANSACTION");
-        sqlite3_prepare_v2(db, "INSERT INTO numi VALUES (?1, ?2, ?3, ?4);", -1, &stmt, NULL);
-        const uint32_t bu = res.bits_umi, bg = res.bits_gene, mb = res.umi_max_bytes;
+        fastf_sqlite_bulk *bulk = fastf_sqlite_bulk_begin(db_file, root_numi);
+        if (!bulk) { free(k); fprintf(stderr, "SQL error: cannot append to table numi of %s\n", db_file); goto done; }
+        fastf_textbuf tb = {0};
         for (uint64_t i = 0; i < n;) {
             uint64_t j = i;
             while (j < n && k[j] == k[i]) j++;
-            uint64_t code = k[i] & ((1ull << bu) - 1);
-            int gene = (int)((k[i] >> bu) & ((1ull << bg) - 1)), cell = (int)(k[i] >> (bu + bg));
-            sqlite3_bind_int(stmt, 1, gene); sqlite3_bind_int(stmt, 2, cell);
+            int64_t cell, gene;
+            uint8_t blob[8];
+            uint64_t content = 0;
+            const int nb = key_fields(k[i], bu, bg, mb, &cell, &gene, blob, &content);
+            /* columns: feature_index, cell_index, encoded_umi, n_copy -- the blob sits in the middle, so the row is laid out by hand */
+            {
+                const int64_t head[2] = {gene, cell};
+                const int64_t copies = (int64_t)(j - i);
+                if (fastf_sqlite_bulk_row4(bulk, head, nb < 0 ? NULL : blob, nb < 0 ? 0u : (unsigned)nb, copies)) break;
+            }
             char dec[16] = "NULL";
-            if ((code >> (bu - 1)) & 1) {
-                uint8_t blob[8];
-                uint64_t content = (code >> 3) & ((1ull << (8 * mb)) - 1);
-                for (uint32_t b = 0; b < mb; b++) blob[b] = (uint8_t)(content >> (8 * (mb - 1 - b)));
-                sqlite3_bind_blob(stmt, 3, blob, (int)(code & 7), SQLITE_TRANSIENT);
+            if (nb >= 0) {
                 for (int b = 0; b < 10; b++) { int sh = (int)(8 * mb) - 2 * (b + 1); dec[b] = "ACGT"[sh >= 0 ? (content >> sh) & 3 : 0]; }
                 dec[10] = 0;
-            } else sqlite3_bind_null(stmt, 3);
-            sqlite3_bind_int(stmt, 4, (int)(j - i));
-            sqlite3_step(stmt);
-            sqlite3_reset(stmt);
-            gzprintf(file_umi, "%d\t%d\t%s\t%d\n", gene, cell, dec, (int)(j - i));
+            }
+            fastf_textbuf_reserve(&tb, 96);
+            char *q = tb.p + tb.n;
+            q += fastf_fmt_i64(q, gene); *q++ = '\t';
+            q += fastf_fmt_i64(q, cell); *q++ = '\t';
+            size_t dl = strlen(dec); memcpy(q, dec, dl); q += dl; *q++ = '\t';
+            q += fastf_fmt_i64(q, (int64_t)(j - i)); *q++ = '\n';
+            tb.n = (size_t)(q - tb.p);
             i = j;
         }
-        exec_sql(db, "END TRANSACTION");
-        sqlite3_finalize(stmt);
-        stmt = NULL;
         free(k);
+        if (fastf_sqlite_bulk_end(bulk)) { fastf_textbuf_free(&tb); fprintf(stderr, "SQL error: writing table numi of %s failed\n", db_file); goto done; }
+        snprintf(path, sizeof path, "%s/umi.tsv.gz", path_out);
+        const int wrc = fastf_gz_write_parallel(path, tb.p, tb.n);
+        fastf_textbuf_free(&tb);
+        if (wrc) { fprintf(stderr, "\x1b[31mError:\x1b[0m can not open file %s\n", path); goto done; }
         printf("umi.tsv.gz is generated.\n");
     }
     rc = 0;
@@ -288,11 +346,9 @@ done:
     if (stmt) sqlite3_finalize(stmt);
     if (file_barcode) gzclose(file_barcode);
     if (file_feature) gzclose(file_feature);
-    if (file_matrix) gzclose(file_matrix);
-    if (file_umi) gzclose(file_umi);
     if (gb) gzclose(gb);
     if (gf) gzclose(gf);
-    if (bam) fclose(bam);
+    if (bam >= 0) close(bam);
     fastf_bam2db_result_free(&res);
     if (job) fastf_bam2db_job_free(job);
     if (ctx) { fastf_host_free(ctx, pin[0]); fastf_host_free(ctx, pin[1]); fastf_ctx_destroy(ctx); }

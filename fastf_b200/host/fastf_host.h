@@ -6,7 +6,9 @@
 #ifndef FASTF_HOST_H
 #define FASTF_HOST_H
 #include <stddef.h>
+#include <stdint.h>
 #include <stdio.h>
+#include <sys/types.h>
 #include <zlib.h>
 extern int _umi_copies_flag;   /* reference src/bam2db_ds.h:23 */
 extern int fastf_device;       /* CUDA device ordinal (env FASTF_DEVICE, default 0) */
@@ -19,4 +21,27 @@ int freq_whitelist(const char *r1_path, size_t len_cellbarcode, size_t len_umi, 
 int extract_bam(char *bam_file, const char *tag, int type);
 /* reference read_bam() + print_CB_node() (src/extract.c:47-133): per cell barcode, its raw barcodes (CR) with counts, one gz line each */
 int crb_write(char *bam_file, gzFile out);
+
+/* ---- host writers / readers that keep up with the device (sqlite_bulk.c, fast_writers.c) ---- */
+typedef struct fastf_sqlite_bulk fastf_sqlite_bulk;
+/* direct table b-tree loader: the table (created through sqlite, still empty, connection closed) gets rows with rowids 1..n */
+fastf_sqlite_bulk *fastf_sqlite_bulk_begin(const char *db_file, unsigned root_page);
+int fastf_sqlite_bulk_row(fastf_sqlite_bulk *b, const int64_t *ints, unsigned n_int, int has_tail, const void *tail_blob_or_null, unsigned tail_len);
+int fastf_sqlite_bulk_row4(fastf_sqlite_bulk *b, const int64_t head[2], const void *blob_or_null, unsigned blob_len, int64_t last);
+/* row i of a bulk load -> record: ncol serial types (< 128 each) and their nb body bytes (see sqlite_bulk.c) */
+typedef void (*fastf_row_encoder)(void *ctx, uint64_t i, uint8_t *types, unsigned *ncol, uint8_t *body, unsigned *nb);
+int fastf_sqlite_bulk_rows_parallel(fastf_sqlite_bulk *b, uint64_t n, fastf_row_encoder enc, void *ctx);
+unsigned fastf_sqlite_int_col(int64_t v, uint8_t *type, uint8_t *body);   /* minimal-width integer column; returns the body bytes */
+int fastf_sqlite_bulk_end(fastf_sqlite_bulk *b);
+typedef struct { char *p; size_t n, cap; } fastf_textbuf;
+void fastf_textbuf_reserve(fastf_textbuf *b, size_t extra);
+void fastf_textbuf_free(fastf_textbuf *b);
+unsigned fastf_fmt_u64(char *p, uint64_t v);
+unsigned fastf_fmt_i64(char *p, int64_t v);
+int fastf_gz_write_parallel(const char *path, const char *text, size_t n);
+#define FASTF_LINE_MAX 96
+typedef unsigned (*fastf_line_fmt)(void *ctx, uint64_t i, char *p);   /* writes the line of row i (<= FASTF_LINE_MAX bytes), returns its length */
+int fastf_gz_write_lines_parallel(const char *path, const char *head, size_t head_n, uint64_t n_rows, fastf_line_fmt fmt, void *ctx);
+ssize_t fastf_pread_parallel(int fd, void *dst, size_t n, off_t off);
+int fastf_host_threads(void);
 #endif

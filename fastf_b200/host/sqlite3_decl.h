@@ -21,4 +21,6 @@ int sqlite3_bind_null(sqlite3_stmt *s, int i);
 int sqlite3_step(sqlite3_stmt *s);
 int sqlite3_reset(sqlite3_stmt *s);
 int sqlite3_finalize(sqlite3_stmt *s);
+int sqlite3_column_int(sqlite3_stmt *s, int col);
+#define SQLITE_ROW 100
 #endif

@@ -20,6 +20,7 @@ struct dim3 {
 };
 typedef void *cudaStream_t;
 struct uint4 { unsigned x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
 
 // ---- just enough of the CUDA runtime for the host orchestration (capi.cu) to run on host memory ----
 typedef int cudaError_t;

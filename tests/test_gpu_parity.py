@@ -291,6 +291,16 @@ def test_bam2db_rejects_truncated_and_foreign_input(gpu_ctx, synth, tmp_path):
         B.run_device(gpu_ctx, np.frombuffer(img, dtype=np.uint8), inputs, 1.0, 926)
 
 
+def test_bam2db_default_chunking_vs_oracle_14M_reads(gpu_ctx, oracle, synth, tmp_path):
+    """BASELINE configs[2] shape (10k cells, 36k genes, -c 1.0 -r 0.3 -s 926) at 14 M distinct reads with the DEFAULT chunking the
+    benchmark runs with: several chunks of 2 x n_sm x streams-per-SM BGZF blocks (blocks pending across feed calls, ring-buffer reuse,
+    `cand` growth from counter snapshots, 4 M draws through the jump-ahead segments), fed in 256 MiB pieces like the file readers do.
+    Counters, COO and the kept rows (the sqlite `umi` table, in read order) equal the oracle's."""
+    paths, st = synth.write_bam_set(str(tmp_path), n_reads=14_000_000, n_cells=10000, n_genes=36000, seed=1234, p_umi_n=0.001)
+    stats, _ = _check_against_oracle(gpu_ctx, oracle, paths, 1.0, 0.3, 926, feed_piece=256 << 20)
+    assert stats["total"] == 14_000_000 and stats["n_chunks"] >= 2, stats["n_chunks"]
+
+
 def test_bam2db_large_properties(gpu_ctx, synth, tmp_path):
     """size-independent properties on a run too large for the oracle to be comfortable: counters are consistent, the COO is
     strictly ascending in (cell, gene), sum(count) = number of distinct non-NULL keys, -r 1.0 keeps every draw but u = 2^32-1,
