@@ -82,6 +82,16 @@ def build_cli(force=False, emu=False):
 def build_oracle():
     """Test infrastructure: the CPU restatement and, when /root/reference exists, the unmodified reference."""
     _run(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    # INTEGRATION.md section B as a test target: the reference's own main.c linked against this repository's bam2db()
+    _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref_gpu"])
+
+
+def build_ref_main_emu():
+    """Test infrastructure: reference main.c + our host, linked against the SIMT-emulator build (boxes without a GPU).  Returns the path or None."""
+    build_emu()
+    _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref_emu"])
+    p = os.path.join(ROOT, "oracle", "_ref", "fastF_gpu_emu")
+    return p if os.path.exists(p) else None
 
 
 def build_emu():
