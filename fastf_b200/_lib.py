@@ -78,6 +78,9 @@ _SIGS = {
     "fastf_bam2db_stats": (C.c_int, [C.c_void_p, C.POINTER(Bam2dbResult)]),
     "fastf_bam2db_job_free": (None, [C.c_void_p]),
     "fastf_bam2db_result_free": (None, [C.POINTER(Bam2dbResult)]),
+    "fastf_bam2db_run_sharded": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(Bam2dbParams), C.c_void_p, C.c_size_t, C.POINTER(Bam2dbResult)]),
+    "fastf_sharded_last_error": (C.c_char_p, []),
+    "fastf_sharded_exchanged": (C.c_uint64, []),
     "fastf_sort_u64_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]),
     "fastf_dedup_count_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, c_u64p, C.POINTER(c_u32p), C.POINTER(c_u32p), C.POINTER(c_u32p)]),
     "fastf_dedup_count_device_out": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, c_u64p, C.c_void_p, C.c_void_p, C.c_void_p]),

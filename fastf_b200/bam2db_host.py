@@ -133,29 +133,62 @@ def decode_rows(row_keys, bits_gene, bits_umi, umi_max_bytes):
 BAM_STRADDLE = 0x400   # FASTF_BAM_STRADDLE (include/fastf_gpu.h)
 
 
+def make_params(lib, inputs, rate_depth, seed, want_rows=True, inflate_lanes=0, chunk_inflated_bytes=0, umi_max_bytes=0, headerless=False):
+    """fastf_bam2db_params for these inputs; the second value keeps the packed tables alive"""
+    ckeys, coff = _pack_table(inputs.cells)
+    gkeys, goff = _pack_table([f[0] for f in inputs.features])
+    p = _lib.Bam2dbParams()
+    p.cell_keys = ckeys
+    p.cell_off = coff.ctypes.data_as(_lib.c_u32p)
+    p.n_cells = len(inputs.cells)
+    p.gene_keys = gkeys
+    p.gene_off = goff.ctypes.data_as(_lib.c_u32p)
+    p.n_genes = len(inputs.features)
+    p.seed = seed
+    p.d0 = inputs.d0
+    p.keep_threshold = lib.fastf_keep_threshold(C.c_float(rate_depth))
+    p.umi_max_bytes = umi_max_bytes
+    p.want_rows = 1 if want_rows else 0
+    p.inflate_lanes = inflate_lanes
+    p.chunk_inflated_bytes = chunk_inflated_bytes
+    p.headerless = 1 if headerless else 0
+    return p, (ckeys, coff, gkeys, goff)
+
+
+def _result_to_python(lib, res, want_rows):
+    z32 = np.zeros(0, np.uint32)
+    out = {
+        "m_gene": np.ctypeslib.as_array(res.m_gene, (res.nnz,)).copy() if res.nnz else z32,
+        "m_cell": np.ctypeslib.as_array(res.m_cell, (res.nnz,)).copy() if res.nnz else z32,
+        "m_count": np.ctypeslib.as_array(res.m_count, (res.nnz,)).copy() if res.nnz else z32,
+        "row_keys": np.ctypeslib.as_array(res.row_keys, (res.n_rows,)).copy() if (want_rows and res.n_rows) else np.zeros(0, np.uint64),
+    }
+    stats = {f: getattr(res, f) for f, _ in _lib.Bam2dbResult._fields_ if not f.startswith("m_") and f != "row_keys"}
+    lib.fastf_bam2db_result_free(C.byref(res))
+    return stats, out
+
+
+def run_sharded(lib, bam_bytes, inputs, rate_depth, seed, n_devices, want_rows=True, devices=None, **kw):
+    """bam2db over n_devices GPUs of this node in ONE process: the C driver fastf_bam2db_run_sharded (contexts, feeder threads and the
+    NCCL all-to-all live in the library).  Returns (stats, arrays) like run_device; stats gains "exchanged_keys"."""
+    p, keep = make_params(lib, inputs, rate_depth, seed, want_rows, **kw)
+    buf = np.frombuffer(bam_bytes, dtype=np.uint8)
+    res = _lib.Bam2dbResult()
+    devs = (C.c_int * n_devices)(*devices) if devices else None
+    if lib.fastf_bam2db_run_sharded(n_devices, devs, C.byref(p), C.c_void_p(buf.ctypes.data), buf.size, C.byref(res)) != 0:
+        raise _lib.FastfError("bam2db_run_sharded: " + lib.fastf_sharded_last_error().decode())
+    stats, out = _result_to_python(lib, res, want_rows)
+    stats["exchanged_keys"] = int(lib.fastf_sharded_exchanged())
+    del keep
+    return stats, out
+
+
 class Bam2dbJob:
     """One streaming bam2db job on one GPU: begin -> feed*/feed_device* -> (counts -> sample(base)) -> finish."""
 
     def __init__(self, ctx, inputs, rate_depth, seed, want_rows=True, inflate_lanes=0, chunk_inflated_bytes=0, umi_max_bytes=0, headerless=False):
         self.ctx, self.lib = ctx, ctx.lib
-        ckeys, coff = _pack_table(inputs.cells)
-        gkeys, goff = _pack_table([f[0] for f in inputs.features])
-        self._keep = (ckeys, coff, gkeys, goff)
-        p = _lib.Bam2dbParams()
-        p.cell_keys = ckeys
-        p.cell_off = coff.ctypes.data_as(_lib.c_u32p)
-        p.n_cells = len(inputs.cells)
-        p.gene_keys = gkeys
-        p.gene_off = goff.ctypes.data_as(_lib.c_u32p)
-        p.n_genes = len(inputs.features)
-        p.seed = seed
-        p.d0 = inputs.d0
-        p.keep_threshold = self.lib.fastf_keep_threshold(C.c_float(rate_depth))
-        p.umi_max_bytes = umi_max_bytes
-        p.want_rows = 1 if want_rows else 0
-        p.inflate_lanes = inflate_lanes
-        p.chunk_inflated_bytes = chunk_inflated_bytes
-        p.headerless = 1 if headerless else 0
+        p, self._keep = make_params(self.lib, inputs, rate_depth, seed, want_rows, inflate_lanes, chunk_inflated_bytes, umi_max_bytes, headerless)
         self.want_rows = want_rows
         self.job = C.c_void_p()
         ctx.check(self.lib.fastf_bam2db_begin(ctx.h, C.byref(p), C.byref(self.job)), "bam2db_begin")

@@ -45,7 +45,7 @@ def build_cuda(force=False):
             return LIB   # GPU box without a changed source tree: the prebuilt library travelled with the snapshot
         raise RuntimeError("nvcc not found and no prebuilt libfastf_gpu.so")
     os.makedirs(BUILD, exist_ok=True)
-    _run([nvcc] + NVCC_FLAGS + ["-o", LIB, os.path.join(csrc, "capi.cu")])
+    _run([nvcc] + NVCC_FLAGS + ["-o", LIB, os.path.join(csrc, "capi.cu"), os.path.join(csrc, "sharded.cu"), "-ldl"])
     return LIB
 
 
@@ -103,7 +103,7 @@ def build_emu():
         return out
     os.makedirs(os.path.dirname(out), exist_ok=True)
     _run(["g++", "-O2", "-std=c++17", "-DFASTF_EMU", "-I" + os.path.join(ROOT, "tests", "emu"), "-x", "c++", "-fPIC", "-shared", "-o", out,
-          os.path.join(csrc, "capi.cu"), "-lz"])
+          os.path.join(csrc, "capi.cu"), os.path.join(csrc, "sharded.cu"), "-lz", "-lpthread"])
     return out
 
 

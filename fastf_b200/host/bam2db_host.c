@@ -8,10 +8,13 @@
 #include <string.h>
 #include <zlib.h>
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 int _umi_copies_flag = 0;
 int fastf_device = 0;
+int fastf_gpus = 1;     /* > 1: the one-process multi-GPU driver of the library (FASTF_GPUS / --gpus) */
 
 typedef struct { char *buf; uint32_t *off; uint32_t n, cap; size_t len, bcap; } strlist;
 static void sl_push(strlist *l, const char *s, size_t n)
@@ -118,6 +121,11 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
     int bam = -1;
     gzFile gb = NULL, gf = NULL, file_barcode = NULL, file_feature = NULL;
     char line[1024], path[2048];
+    {   /* also honoured when the reference's own main() is the caller */
+        const char *e = getenv("FASTF_GPUS");
+        if (e && atoi(e) > 0) fastf_gpus = atoi(e);
+        if ((e = getenv("FASTF_DEVICE")) != NULL) fastf_device = atoi(e);
+    }
 
     if (sqlite3_open(db_file, &db)) { fprintf(stderr, "Can't open database: %s\n", sqlite3_errmsg(db)); goto done; }
     fprintf(stderr, "Opened database successfully\n");
@@ -201,6 +209,34 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
     /* ---- the hot path: device job fed with the raw BGZF bytes ---- */
     printf("Start to convert bam file to sqlite3 database...\n");
     fflush(stdout);
+    if (fastf_gpus > 1) {
+        /* several GPUs of this node: contiguous block shards, global draw ordinals, NCCL all-to-all by cell (csrc/sharded.cu) */
+        struct stat sb;
+        if (fstat(bam, &sb) || sb.st_size <= 0) { fprintf(stderr, "\x1b[31mError:\x1b[0m cannot stat %s\n", bam_file); goto done; }
+        void *map = mmap(NULL, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, bam, 0);
+        if (map == MAP_FAILED) { fprintf(stderr, "\x1b[31mError:\x1b[0m cannot map %s\n", bam_file); goto done; }
+        madvise(map, (size_t)sb.st_size, MADV_SEQUENTIAL);
+        int failed = 1;
+        for (uint32_t umi_bytes = 3; umi_bytes <= 4 && failed; umi_bytes++) {
+            fastf_bam2db_params p;
+            memset(&p, 0, sizeof p);
+            uint32_t zero_off[1] = {0};
+            p.cell_keys = cells.buf ? cells.buf : ""; p.cell_off = cells.off ? cells.off : zero_off; p.n_cells = cells.n;
+            p.gene_keys = fkeys.buf ? fkeys.buf : ""; p.gene_off = fkeys.off ? fkeys.off : zero_off; p.n_genes = fkeys.n;
+            p.seed = seed; p.d0 = d0; p.keep_threshold = fastf_keep_threshold(rate_depth);
+            p.umi_max_bytes = umi_bytes;
+            p.want_rows = 1;
+            failed = fastf_bam2db_run_sharded(fastf_gpus, NULL, &p, map, (size_t)sb.st_size, &res);
+            if (failed && !(umi_bytes == 3 && strstr(fastf_sharded_last_error(), "umi-too-long"))) break;
+        }
+        munmap(map, (size_t)sb.st_size);
+        if (failed) {
+            fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_sharded_last_error());
+            if (strstr(fastf_sharded_last_error(), "record-straddles-bgzf-block")) fprintf(stderr, "(records cross BGZF blocks: not an htslib-written file; run it on one GPU, FASTF_GPUS=1)\n");
+            goto done;
+        }
+        if (_umi_copies_flag && fastf_ctx_create(fastf_device, &ctx)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(NULL)); goto done; }
+    } else {
     if (fastf_ctx_create(fastf_device, &ctx)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(NULL)); goto done; }
     uint32_t flags = 0;   /* FASTF_BAM_STRADDLE after a first attempt met records that cross BGZF blocks (htsjdk / STAR writers) */
     for (uint32_t umi_bytes = 3; umi_bytes <= 4; umi_bytes++) {   /* 10x UMIs are 10 or 12 bases; retry once with room for 16 */
@@ -237,6 +273,7 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
         }
         fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx));
         goto done;
+    }
     }
 
     /* ---- tables umi (read order, reference :351-435), mtx (:480-483) and numi (:527-530) ----

@@ -12,6 +12,7 @@
 #include <zlib.h>
 extern int _umi_copies_flag;   /* reference src/bam2db_ds.h:23 */
 extern int fastf_device;       /* CUDA device ordinal (env FASTF_DEVICE, default 0) */
+extern int fastf_gpus;         /* bam2db over this many GPUs of the node (env FASTF_GPUS or --gpus N, default 1) */
 int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, char *features_file, float rate_cell, float rate_depth, unsigned int seed);
 /* cell_counts + print_tree in one call: histogram of the first l+u bases of every read of R1 (BGZF or plain text), written to fp
  * in the reference's BST pre-order.  Returns 0 / 1. */

@@ -72,10 +72,10 @@ static int cmd_bam2db(int argc, const char **argv)
     const char *bam = NULL, *feat = NULL, *bc = NULL, *db = NULL, *out = ".";
     float rate_cell = 0.0f, rate_depth = 0.0f;   /* the reference leaves these uninitialised (src/main.c:293-294): pass -c and -r */
     unsigned seed = 926;
-    static const optdef defs[] = {{'b', "bam", 1}, {'f', "feature", 1}, {'a', "barcode", 1}, {'d', "dbname", 1}, {'c', "cell", 1}, {'r', "depth", 1}, {'o', "out", 1}, {'s', "seed", 1}, {'u', "umicopies", 0}, {'h', "help", 0}};
+    static const optdef defs[] = {{'b', "bam", 1}, {'f', "feature", 1}, {'a', "barcode", 1}, {'d', "dbname", 1}, {'c', "cell", 1}, {'r', "depth", 1}, {'o', "out", 1}, {'s', "seed", 1}, {'u', "umicopies", 0}, {'h', "help", 0}, {'g', "gpus", 1}};
     for (int i = 1; i < argc; i++) {
         const char *v;
-        switch (next_opt(argc, argv, &i, defs, 10, &v)) {
+        switch (next_opt(argc, argv, &i, defs, 11, &v)) {
         case 0: bam = v; break;
         case 1: feat = v; break;
         case 2: bc = v; break;
@@ -85,7 +85,8 @@ static int cmd_bam2db(int argc, const char **argv)
         case 6: out = v; break;
         case 7: seed = (unsigned)(int)strtol(v, NULL, 0); break;
         case 8: _umi_copies_flag = 1; break;
-        default: printf("Usage: fastF bam2db -b BAM -f FEATURES -a BARCODES -d DB -c RATE_CELL -r RATE_DEPTH [-o OUT] [-s 926] [-u]\n\nFilter bam file with desired cell proportion and read depth, then summarise it into UMI matrix.\n"); exit(0);
+        case 10: fastf_gpus = (int)strtol(v, NULL, 0); break;   /* not a reference option: GPUs of this node to shard the BAM over */
+        default: printf("Usage: fastF bam2db -b BAM -f FEATURES -a BARCODES -d DB -c RATE_CELL -r RATE_DEPTH [-o OUT] [-s 926] [-u] [--gpus N]\n\nFilter bam file with desired cell proportion and read depth, then summarise it into UMI matrix.\n"); exit(0);
         }
     }
     if (!bam || access(bam, F_OK) == -1) { fprintf(stderr, "\x1b[31mError:\x1b[0m bam file: %s does not exist.\n", bam ? bam : "(null)"); exit(1); }
@@ -141,6 +142,8 @@ int main(int argc, const char **argv)
 {
     const char *dev = getenv("FASTF_DEVICE");
     if (dev) fastf_device = atoi(dev);
+    const char *gpus = getenv("FASTF_GPUS");
+    if (gpus) fastf_gpus = atoi(gpus);
     if (argc < 2 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) {
         printf("Usage: fastF [-h] <command> [<args>]\n\nCommands (GPU build): freq, bam2db, crb, extract\n");
         return argc < 2 ? -1 : 0;

@@ -134,6 +134,17 @@ int fastf_bam2db_stats(fastf_bam2db_job *job, fastf_bam2db_result *res);
 void fastf_bam2db_job_free(fastf_bam2db_job *job);
 void fastf_bam2db_result_free(fastf_bam2db_result *res);
 
+/* ---- bam2db over several GPUs of one node, driven by ONE host process (fastf_b200/csrc/sharded.cu) ----
+ * The whole BGZF file image (host memory; an mmap of the file will do) is cut into contiguous block shards, one per device; every
+ * device runs the single-GPU streaming path on its shard, the shards agree on the global MT19937 draw ordinals, exchange their
+ * locally deduplicated keys with an NCCL all-to-all (ncclSend / ncclRecv over NVLink) partitioned by cell, and count locally.
+ * res is laid out exactly like fastf_bam2db_finish's and is identical to the single-GPU result (and to the reference's tables:
+ * src/bam2db_ds.c:360-438,480-483).  devices == NULL means 0..n_devices-1.  p->want_rows / umi_max_bytes / inflate_lanes as in
+ * fastf_bam2db_begin (FASTF_BAM_STRADDLE is single-GPU only).  Returns 0, or 1 with fastf_sharded_last_error(). */
+int fastf_bam2db_run_sharded(int n_devices, const int *devices, const fastf_bam2db_params *p, const void *bgzf_bytes, size_t n_bytes, fastf_bam2db_result *res);
+const char *fastf_sharded_last_error(void);
+uint64_t fastf_sharded_exchanged(void);   /* keys that crossed the all-to-all in the last call (diagnostic) */
+
 /* ---- device-level building blocks (multi-GPU driver, unit tests) ---- */
 /* in-place stable LSD radix sort of n u64 keys on device over key_bits low bits (vals optional, may be NULL) */
 int fastf_sort_u64_device(fastf_ctx *ctx, uint64_t *dev_keys, uint32_t *dev_vals, uint64_t n, uint32_t key_bits);

@@ -33,7 +33,7 @@ inline double emu_now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); r
 inline const char *cudaGetErrorString(cudaError_t) { return "emu"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int *n) { const char *e = getenv("FASTF_EMU_DEVICES"); *n = e ? atoi(e) : 1; return cudaSuccess; }   // several "devices" = the same host
 inline cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : 2; }
 inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMallocHost(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : 2; }
