@@ -95,11 +95,11 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_base(base_reads, threads):
+def make_base(base_reads, threads, seed=None):
     """Synthetic base segment + barcode / feature lists.  Returns dict with the BGZF image (numpy u8) and text lists."""
     import synth_binding
     S = synth_binding.load()
-    p = S.params(n_reads=base_reads, n_cells=N_CELLS, n_genes=N_GENES, seed=DATA_SEED)
+    p = S.params(n_reads=base_reads, n_cells=N_CELLS, n_genes=N_GENES, seed=DATA_SEED if seed is None else seed)
     t = time.time()
     bam, st = S.bam(p, threads)
     log(f"[bench] generated {base_reads} reads: {st.compressed_bytes / 1e6:.0f} MB BGZF, {st.inflated_bytes / 1e6:.0f} MB inflated, {st.n_blocks} blocks in {time.time() - t:.1f}s on {threads} threads")
@@ -107,7 +107,7 @@ def make_base(base_reads, threads):
             "inflated": st.inflated_bytes, "compressed": st.compressed_bytes}
 
 
-def write_inputs(base, d, prefix_reads=None):
+def write_inputs(base, d, prefix_reads=None, write_bam=True):
     """files for the reference CLI; with prefix_reads a BAM holding only about that many reads (whole blocks)"""
     import gzip
     paths = {"bam": os.path.join(d, "synth.bam"), "barcodes": os.path.join(d, "barcodes.tsv.gz"), "features": os.path.join(d, "features.tsv.gz")}
@@ -130,8 +130,9 @@ def write_inputs(base, d, prefix_reads=None):
         cut = int(in_off[k]) - 18
         bam = bam[:cut] + bam[-28:]
         reads = None   # counted by the reference itself
-    with open(paths["bam"], "wb") as f:
-        f.write(bam)
+    if write_bam:
+        with open(paths["bam"], "wb") as f:
+            f.write(bam)
     return paths, reads
 
 
@@ -161,6 +162,32 @@ def run_reference_cli(paths, outdir, rate_cell, rate_depth, seed):
     return dt, total, kind
 
 
+def cli_leg(paths, ref_out, our_out, total, ref_seconds, ref_kind, device):
+    """wall clock of `fastf_b200/_build/fastF bam2db` on the files the reference CLI just processed; every output compared"""
+    import gzip
+    from fastf_b200 import build
+    from dbdigest import db_digest
+    cli = build.build_cli()
+    shutil.rmtree(our_out, ignore_errors=True)
+    os.makedirs(our_out)
+    cmd = [cli, "bam2db", "-b", paths["bam"], "-f", paths["features"], "-a", paths["barcodes"], "-d", os.path.join(our_out, "ours.db"), "-c", str(RATE_CELL), "-r", str(RATE_DEPTH), "-o", our_out, "-s", str(SEED)]
+    t = time.time()
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=dict(os.environ, FASTF_DEVICE=str(device)))
+    ours = time.time() - t
+    if r.returncode != 0:
+        return {"failed": r.stderr[-300:]}
+    out = {"reads": total, "ours_seconds": round(ours, 3), "reference_seconds": round(ref_seconds, 3), "speedup": round(ref_seconds / ours, 1), "reference_kind": ref_kind,
+           "what": "whole CLI run, file on /dev/shm -> sqlite database + matrix/barcodes/features gz files; includes CUDA context creation"}
+    if ref_kind == "reference":
+        same = all(gzip.open(os.path.join(our_out, f), "rb").read() == gzip.open(os.path.join(ref_out, f), "rb").read() for f in ("matrix.mtx.gz", "barcodes.tsv.gz", "features.tsv.gz"))
+        t = time.time()
+        a, b = db_digest(os.path.join(our_out, "ours.db")), db_digest(os.path.join(ref_out, "ref.db"))
+        out["outputs_identical"] = bool(same and all(a[k] == b[k] for k in ("cell", "feature", "umi", "mtx")))
+        out["compared"] = "decompressed matrix.mtx / barcodes / features bytes; sha256 of every row of tables cell, feature, umi, mtx"
+        assert out["outputs_identical"], "the drop-in CLI and the reference CLI disagree"
+    return out
+
+
 def cpu_model():
     try:
         for ln in open("/proc/cpuinfo"):
@@ -178,7 +205,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=500_000_000, help="reads per GPU per step")
-    ap.add_argument("--base-reads", type=int, default=8_000_000, help="reads in the generated BGZF segment that is tiled")
+    ap.add_argument("--base-reads", type=int, default=0, help="DISTINCT reads generated per GPU (a zlib-6 BGZF image, every rank its own data seed) and cycled ceil(reads/base) times per step; "
+                    "0 = as many as the host cores of this rank generate in ~90 s, between 8 M and 64 M")
+    ap.add_argument("--check-reads", type=int, default=2_000_000, help="prefix of the data whose single-GPU result is compared with the CPU oracle before anything is timed (0 = skip)")
+    ap.add_argument("--cli-reads", type=int, default=0, help="also time `fastF bam2db` (file in /dev/shm -> sqlite + gz files) against the reference CLI on a file of this many reads, outputs compared (0 = on the cpu_baseline sample)")
+    ap.add_argument("--freq-reads", type=int, default=32_000_000, help="reads of the `freq` run reported as the `secondary` object of the line (0 = skip)")
     ap.add_argument("--ref-sample-reads", type=int, default=5_000_000)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--lanes", type=int, default=0)
@@ -198,6 +229,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     threads = os.cpu_count() or 1
+    if args.base_reads <= 0:
+        # zlib-6 generation runs at ~44 k reads/s per host thread; every rank generates its own distinct segment on its share of the cores
+        per_rank_threads = max(1, threads // max(1, world))
+        args.base_reads = int(min(64_000_000, max(8_000_000, per_rank_threads * 4_000_000), max(args.reads, 1_000_000)))
     workload = f"bam2db synthetic 10x-v3 BAM: {args.reads} reads/GPU, {N_CELLS} cells, {N_GENES} genes, -c {RATE_CELL} -r {RATE_DEPTH} -s {SEED} (BASELINE.json configs[{args.config}])"
 
     # ------------------------------------------------------------------ reference arm: the reference's own CPU path
@@ -305,31 +340,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.Context(local_rank)
     lib = ctx.lib
-    # the synthetic segment is generated once per node (local rank 0, all host threads) and shared through /dev/shm
-    share = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(), f"fastf_bench_base_{os.environ.get('MASTER_PORT', '0')}_{args.base_reads}_{args.config}")
-    if world > 1:
-        if local_rank == 0:
-            base = make_base(args.base_reads, threads)
-            os.makedirs(share, exist_ok=True)
-            with open(os.path.join(share, "base.bam"), "wb") as f:
-                f.write(base["bam"])
-            json.dump({k: base[k] for k in ("reads", "n_blocks", "inflated", "compressed")}, open(os.path.join(share, "meta.json"), "w"))
-            open(os.path.join(share, "barcodes.txt"), "wb").write(base["barcodes"])
-            open(os.path.join(share, "features.txt"), "wb").write(base["features"])
+    # every rank generates its OWN distinct reads (data seed + rank) on its share of the host cores: nothing is replayed across GPUs
+    base = make_base(args.base_reads, max(1, threads // max(1, world)), seed=DATA_SEED + rank)
+    if dist:
         dist.barrier()
-        if local_rank != 0:
-            base = json.load(open(os.path.join(share, "meta.json")))
-            base["bam"] = open(os.path.join(share, "base.bam"), "rb").read()
-            base["barcodes"] = open(os.path.join(share, "barcodes.txt"), "rb").read()
-            base["features"] = open(os.path.join(share, "features.txt"), "rb").read()
-        dist.barrier()
-        if local_rank == 0:
-            shutil.rmtree(share, ignore_errors=True)
-    else:
-        base = make_base(args.base_reads, threads)
     tmp = tempfile.mkdtemp(prefix=f"fastf_bench_{rank}_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     try:
-        paths, _ = write_inputs(base, tmp)
+        paths, _ = write_inputs(base, tmp, write_bam=False)   # the lists only: the image stays in memory
         inputs = B.Bam2dbInputs(lib, paths["barcodes"], paths["features"], RATE_CELL, SEED)
         bam = np.frombuffer(base["bam"], dtype=np.uint8)
         nbytes = bam.size
@@ -359,6 +376,39 @@ def main():
 
         HW = 0x100   # FASTF_INFLATE_HW_ENGINE
         engine = {"lanes": args.lanes | (HW if args.engine == "hw" else 0)}
+
+        # ---- parity before speed: a prefix of this very data through the GPU path and through the CPU oracle (bit-exact), and the
+        # counters of ONE tile, which every timed job must reproduce tiles-fold ----
+        checks = {"oracle_prefix_reads": 0}
+        if args.check_reads and rank == 0:
+            import oracle_binding
+            O = oracle_binding.load()
+            dck = os.path.join(tmp, "check")
+            os.makedirs(dck, exist_ok=True)
+            pck, _ = write_inputs(base, dck, prefix_reads=min(args.check_reads, base["reads"]))
+            t0 = time.time()
+            want = O.bam2db(pck["bam"], pck["barcodes"], pck["features"], RATE_CELL, RATE_DEPTH, SEED)
+            gst, gout = B.run_device(ctx, np.fromfile(pck["bam"], dtype=np.uint8), inputs, RATE_DEPTH, SEED, want_rows=False, inflate_lanes=engine["lanes"])
+            for k in ("total", "cb_valid", "sampled", "valid", "nnz"):
+                assert gst[k] == want[k], ("GPU result differs from the oracle on the check prefix", k, gst[k], want[k])
+            assert np.array_equal(gout["m_gene"], want["m_gene"]) and np.array_equal(gout["m_cell"], want["m_cell"]) and np.array_equal(gout["m_count"], want["m_count"]), "COO differs from the oracle"
+            checks = {"oracle_prefix_reads": int(want["total"]), "oracle_prefix_nnz": int(want["nnz"]), "oracle_prefix_seconds": round(time.time() - t0, 1), "oracle_prefix": "counters + COO bit-exact"}
+            log(f"[bench] check: {want['total']}-read prefix, GPU == oracle (nnz {want['nnz']}) in {time.time() - t0:.1f}s")
+        with B.Bam2dbJob(ctx, inputs, RATE_DEPTH, SEED, want_rows=False, inflate_lanes=engine["lanes"], headerless=False) as job1:
+            job1.feed_device(dptr.value, nbytes, in_off[0:rec_hi], in_len[0:rec_hi], isz[0:rec_hi])
+            tile_stats, _ = job1.finish(copy=False)
+        assert tile_stats["total"] == base["reads"], ("one tile does not hold the generated reads", tile_stats["total"], base["reads"])
+
+        def check_job(st_):
+            """what every timed job must satisfy (a silent miscount at chunk 40 of 80 would otherwise still print reads/s)"""
+            if world > 1:
+                return
+            assert st_["total"] == tiles * base["reads"], ("total", st_["total"], tiles * base["reads"])
+            assert st_["cb_valid"] == tiles * tile_stats["cb_valid"], ("cb_valid", st_["cb_valid"], tiles * tile_stats["cb_valid"])
+            n_, p_ = float(st_["cb_valid"]), RATE_DEPTH * 1.0
+            assert abs(st_["sampled"] - n_ * p_) <= 6.0 * (n_ * p_ * (1 - p_)) ** 0.5 + 1, ("sampled is not a Binomial(cb_valid, rate) draw", st_["sampled"], n_ * p_)
+            assert st_["valid"] <= st_["sampled"] and tile_stats["nnz"] <= st_["nnz"] <= st_["valid"], ("valid / nnz", st_["valid"], st_["sampled"], st_["nnz"])
+            assert st_["status"] == 0, ("status", st_["status"])
 
         rate = {"depth": RATE_DEPTH}
 
@@ -393,6 +443,9 @@ def main():
             for _ in range(steps):
                 st, _out = one_job(device_resident)
                 stats_all.append(st)
+            for st in stats_all:
+                check_job(st)
+            assert all(x["nnz"] == stats_all[0]["nnz"] and x["valid"] == stats_all[0]["valid"] for x in stats_all), "steps over the same input disagree"
             e1.record(lib_stream)
             ctx.check(lib.fastf_synchronize(ctx.h), "sync")
             torch.cuda.synchronize()
@@ -487,7 +540,9 @@ def main():
         line = {"metric": "bam2db reads/sec (device-timed)", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "timing": "value: device-timed (CUDA events), inputs resident in HBM; e2e: host wall clock from pinned host memory",
-                "config": {"workload": workload, "tiling": f"{base['reads']}-read zlib-6 BGZF segment ({base['compressed'] / 1e6:.0f} MB compressed, {base['inflated'] / 1e6:.0f} MB inflated) streamed {tiles}x per step",
+                "config": {"workload": workload, "tiling": f"{base['reads']} DISTINCT reads per GPU (zlib-6 BGZF image, {base['compressed'] / 1e6:.0f} MB compressed, {base['inflated'] / 1e6:.0f} MB inflated; data seed {DATA_SEED}+rank) cycled {tiles}x per step "
+                                     f"(5e8 distinct reads take ~12 min of host zlib time per GPU; the MT19937 draw ordinal keeps running, so every cycle keeps a different {RATE_DEPTH:.0%})",
+                           "checks": dict(checks, per_job="total == tiles x reads, cb_valid == tiles x one-tile cb_valid, sampled within 6 sigma of Binomial(cb_valid, rate), status 0, steps agree"),
                            "l2": "inputs larger than L2 (compressed segment >> 126 MB); no explicit flush", "timing": "CUDA events on the library's launching stream around the K timed jobs, barrier + synchronize on both sides; max over ranks",
                            "ms_per_step_wall": ms_step_wall, "ms_per_job_library_clock": ms_job_dev, "counters": {k: st.get(k) for k in ("total", "cb_valid", "sampled", "valid", "nnz", "n_blocks", "n_chunks", "exchanged_keys")},
                            "parallelism": ("single GPU" if world == 1 else f"{world} ranks: contiguous BGZF block shards, all-gather of counts, NCCL all-to-all of locally deduplicated keys by cell hash, gather of COO")},
@@ -499,13 +554,28 @@ def main():
                 "stages": stages, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "inflate_engine": args.engine, "hw_decompress_engine": hw_extra}
         if sweep is not None:
             line["depth_sweep"] = sweep
+        if world > 1:
+            assert st["total"] == world * tiles * base["reads"], ("gathered total", st["total"], world * tiles * base["reads"])
         if not args.no_cpu_baseline:
             d2 = os.path.join(tmp, "refin")
             os.makedirs(d2, exist_ok=True)
-            p2, _ = write_inputs(base, d2, prefix_reads=args.ref_sample_reads)
+            p2, _ = write_inputs(base, d2, prefix_reads=args.cli_reads or args.ref_sample_reads)
             dt, total, kind = run_reference_cli(p2, os.path.join(tmp, "refout"), RATE_CELL, RATE_DEPTH, SEED)
             line["cpu_baseline"] = {"value": total / dt, "unit": "reads/s", "cores": 1, "kind": kind, "cpu": cpu_model(), "host_cores": threads,
                                     "sample": f"one run of the unmodified reference CLI on a {total}-read prefix of the same synthetic BAM ({dt:.1f}s wall; inflate via zlib shim, sqlite on /dev/shm)"}
+            # the drop-in CLI on the very same files: the number a user of `fastF bam2db` sees (file -> sqlite database + gz files), outputs compared
+            line["cli"] = cli_leg(p2, os.path.join(tmp, "refout"), os.path.join(tmp, "ourout"), total, dt, kind, local_rank)
+        if args.freq_reads and world == 1:
+            # BASELINE.json configs[1] rides in the same driver-parsed line
+            fa = argparse.Namespace(**vars(args))
+            fa.reads, fa.base_reads, fa.steps, fa.warmup, fa.e2e_steps = args.freq_reads, args.freq_reads, max(1, min(args.steps, 3)), 1, 1
+            lib.fastf_device_free(ctx.h, dptr)
+            lib.fastf_host_free(ctx.h, hptr)
+            ctx.close()
+            try:
+                line["secondary"] = bench_freq(fa, emit=False)
+            except Exception as e:   # the headline stands on its own
+                line["secondary"] = {"workload": "freq", "failed": str(e)[:300]}
         if saved_stdout is not None:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
@@ -515,7 +585,7 @@ def main():
     return 0
 
 
-def bench_freq(args):
+def bench_freq(args, emit=True):
     """`fastF freq` (BASELINE.json configs[1]): R1 FASTQ, 20k true barcodes + 5 % single-base errors, -l 16 -u 12.  One step = one
     fastf_freq_gpu call over the whole BGZF image (value: image + index resident in HBM; e2e: pinned host bytes in, histogram out)."""
     import torch
@@ -613,6 +683,9 @@ def bench_freq(args):
                                     "sample": f"one run of the reference CLI `freq -l 16 -u 12` on {sub.n_reads} reads of the same shape ({dt:.1f}s wall)"}
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
+    ctx.close()
+    if not emit:
+        return line
     print(json.dumps(line))
     return 0
 
