@@ -92,11 +92,17 @@ enum { FASTF_TPS_NEXT = 0, FASTF_TPS_RUN = 1, FASTF_TPS_BUILD = 2, FASTF_TPS_DON
 // an index offset (fastf_tps_build).  Limits sit in [0, OFFS), offsets in [OFFS, 2 OFFS), OFFS = 8 or 12 (vector loads).
 #define FASTF_TPS_WALK_OFFS(TBITS) ((15 - (TBITS)) <= 8 ? 8 : 12)
 #define FASTF_TPS_WALK_U16(TBITS) (2 * FASTF_TPS_WALK_OFFS(TBITS) < 16 ? 16 : 2 * FASTF_TPS_WALK_OFFS(TBITS))   // >= 16: the build counts code lengths in it first
+// Lane i of a decoder warp (and lane k of a polling service warp) works on stream i: the same field of consecutive streams must
+// not fall into the same shared-memory bank.  The structure is 8-byte aligned and FASTF_TPS_PAD makes its size = 8 (mod 16) bytes,
+// i.e. a bank step of 2 between streams (an exact multiple of 128 bytes would put every lane on one bank).
+#ifndef FASTF_TPS_PAD
+#define FASTF_TPS_PAD 8
+#endif
 struct FastfTpsStream {
     u16 lit[1 << FASTF_TPS_LBITS];
     u16 dist[1 << FASTF_TPS_DBITS];
-    alignas(16) u16 lit_cnt[FASTF_TPS_WALK_U16(FASTF_TPS_LBITS)];
-    alignas(16) u16 dist_cnt[FASTF_TPS_WALK_U16(FASTF_TPS_DBITS)];
+    alignas(8) u16 lit_cnt[FASTF_TPS_WALK_U16(FASTF_TPS_LBITS)];
+    alignas(8) u16 dist_cnt[FASTF_TPS_WALK_U16(FASTF_TPS_DBITS)];
     u32 ring[FASTF_TPS_RING];
     // control block (volatile accesses; every hand-over is fenced)
     u32 state, wr, rd, last;
@@ -106,6 +112,9 @@ struct FastfTpsStream {
     u32 blk, opos;                   // service side: block index, bytes written
     u32 inend_lo, inend_hi;          // absolute bit offset of the end of the payload
     u32 obase_lo, obase_hi;          // offset of the block in the inflated buffer
+#if FASTF_TPS_PAD
+    u8 pad[FASTF_TPS_PAD];
+#endif
 };
 
 // Staged LZ77 (FASTF_TPS_STAGED): a service warp assembles the output of a token batch in shared memory -- literals, then the
@@ -121,7 +130,9 @@ struct FastfTpsStream {
 struct FastfTpsSvc {
     union {
         struct { u8 lens[320]; u16 scratch[32]; } setup;   // code lengths of the block being set up; first[16], start[16] while building
+#if FASTF_TPS_STAGED
         alignas(16) u8 sb[FASTF_TPS_SB + 8];
+#endif
     };
 #if FASTF_TPS_STAGED
     alignas(8) u32 farlist[32][2];   // (token, offset in the batch) of the short far matches, compacted
@@ -710,8 +721,8 @@ __device__ __forceinline__ u32 fastf_tps_walk(u64 buf, const u16 *lb, const u16 
 {
     constexpr int NL = 15 - TBITS, OFFS = FASTF_TPS_WALK_OFFS(TBITS);
     const u32 code15 = __brev((u32)buf) >> 17;   // the next 15 stream bits, first bit most significant
-    const uint4 L4 = *reinterpret_cast<const uint4 *>(lb);
-    u32 w[6] = {L4.x, L4.y, L4.z, L4.w, 0xffffffffu, 0xffffffffu};
+    const uint2 La = *reinterpret_cast<const uint2 *>(lb), Lb = *reinterpret_cast<const uint2 *>(lb + 4);
+    u32 w[6] = {La.x, La.y, Lb.x, Lb.y, 0xffffffffu, 0xffffffffu};
     if (NL > 8) {
         const uint2 L2 = *reinterpret_cast<const uint2 *>(lb + 8);
         w[4] = L2.x; w[5] = L2.y;
@@ -875,9 +886,12 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
         const u32 sw = warp;
         constexpr u32 NPER = (FASTF_TPS_STREAMS + SVC - 1) / SVC;
         static_assert(NPER <= 32, "one lane per owned stream");
-        const u32 my_sidx = sw + lane * (u32)SVC;
-        const bool mine = lane < NPER && my_sidx < FASTF_TPS_STREAMS;
-        FastfTpsStream &MS = streams[mine ? my_sidx : sw];
+        // a service warp owns NPER consecutive streams: lane k polls stream sw * NPER + k (neighbouring structures, distinct banks)
+        constexpr u32 Q = FASTF_TPS_STREAMS / SVC, R = FASTF_TPS_STREAMS % SVC;
+        const u32 first_sidx = sw * Q + (sw < R ? sw : R), n_mine = Q + (sw < R ? 1u : 0u);
+        const u32 my_sidx = first_sidx + lane;
+        const bool mine = lane < n_mine;
+        FastfTpsStream &MS = streams[mine ? my_sidx : first_sidx];
         for (;;) {
             u32 st = FASTF_TPS_DONE, rd = 0, avail = 0;
             if (mine) {
@@ -901,7 +915,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
                 const u32 w = __shfl_sync(FASTF_FULL_MASK, work, (int)k);
                 const u32 krd = __shfl_sync(FASTF_FULL_MASK, rd, (int)k);
                 const u32 kav = __shfl_sync(FASTF_FULL_MASK, avail, (int)k);
-                const u32 sidx = sw + k * (u32)SVC;
+                const u32 sidx = first_sidx + k;
                 FastfTpsStream &S = streams[sidx];
                 u16 *ssorted = sorted_base + (size_t)sidx * FASTF_TPS_SORTED_U16;
                 if (w == 1) {

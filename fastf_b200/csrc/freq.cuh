@@ -19,7 +19,9 @@
 #define FASTF_FREQ_MAX_KEY 31        // bases; 2 bits each, one spare bit pattern for the sentinel
 #define FASTF_FREQ_EXC_STRIDE 32     // bytes kept per exceptional read
 
-__device__ __forceinline__ u32 fastf_count_nl16(const u8 *__restrict__ text, u64 off, u64 n, u32 *mask)
+// newlines among the 16 bytes at off (as a bit mask); bytes in front of `skip` do not exist (the text of a streamed chunk starts at
+// text + skip so that text itself stays 16-byte aligned)
+__device__ __forceinline__ u32 fastf_count_nl16(const u8 *__restrict__ text, u64 off, u64 n, u32 *mask, u64 skip = 0)
 {
     u32 m = 0;
     if (off + 16 <= n && ((off & 15u) == 0)) {
@@ -33,18 +35,19 @@ __device__ __forceinline__ u32 fastf_count_nl16(const u8 *__restrict__ text, u64
     } else {
         for (u32 k = 0; k < 16; k++) if (off + k < n && text[off + k] == '\n') m |= 1u << k;
     }
+    if (off < skip) m = (skip - off >= 16u) ? 0u : (m & ~((1u << (u32)(skip - off)) - 1u));
     *mask = m;
     return (u32)__popc(m);
 }
 
-__global__ void __launch_bounds__(FASTF_NL_THREADS) fastf_nl_count_kernel(const u8 *__restrict__ text, u64 n, u32 *__restrict__ tile_counts)
+__global__ void __launch_bounds__(FASTF_NL_THREADS) fastf_nl_count_kernel(const u8 *__restrict__ text, u64 n, u32 *__restrict__ tile_counts, u64 skip)
 {
     __shared__ u32 s_c;
     if (threadIdx.x == 0) s_c = 0;
     __syncthreads();
     const u64 off = (u64)blockIdx.x * FASTF_NL_TILE + (u64)threadIdx.x * FASTF_NL_BYTES_PER_THREAD;
     u32 m;
-    u32 c = off < n ? fastf_count_nl16(text, off, n, &m) : 0u;
+    u32 c = off < n ? fastf_count_nl16(text, off, n, &m, skip) : 0u;
     c = __reduce_add_sync(FASTF_FULL_MASK, c);
     if ((threadIdx.x & 31u) == 0) atomicAdd(&s_c, c);
     __syncthreads();
@@ -53,21 +56,24 @@ __global__ void __launch_bounds__(FASTF_NL_THREADS) fastf_nl_count_kernel(const 
 
 // For every newline with global index j = 4r: pack the key of record r.
 // exc_count counts ALL exceptional reads; only the first exc_cap are stored (host re-runs with a larger cap on overflow).
+// Streaming (the text is one chunk of a larger file, preceded by the tail of the previous chunk): nl_base = global index of the first
+// newline at or behind `skip`; a key whose FASTF_FREQ_EXC_STRIDE bytes end at or before `done_below` was emitted by the previous
+// chunk, one whose bytes run past n waits for the next chunk unless this is the last one.
 __global__ void __launch_bounds__(FASTF_NL_THREADS)
 fastf_freq_keys_kernel(const u8 *__restrict__ text, u64 n, const u32 *__restrict__ tile_off, u32 klen, u64 *__restrict__ keys, u64 n_keys_cap,
-                       u32 *__restrict__ exc_count, u32 exc_cap, u32 *__restrict__ exc_ord, u8 *__restrict__ exc_bytes)
+                       u32 *__restrict__ exc_count, u32 exc_cap, u32 *__restrict__ exc_ord, u8 *__restrict__ exc_bytes, u64 skip, u64 nl_base, u64 done_below, u32 last_chunk)
 {
     const u64 off = (u64)blockIdx.x * FASTF_NL_TILE + (u64)threadIdx.x * FASTF_NL_BYTES_PER_THREAD;
     u32 m = 0;
-    u32 c = off < n ? fastf_count_nl16(text, off, n, &m) : 0u;
+    u32 c = off < n ? fastf_count_nl16(text, off, n, &m, skip) : 0u;
     u32 tot;
-    u64 j = (u64)tile_off[blockIdx.x] + fastf_block_exscan<FASTF_NL_THREADS>(c, &tot);
+    u64 j = nl_base + (u64)tile_off[blockIdx.x] + fastf_block_exscan<FASTF_NL_THREADS>(c, &tot);
     while (m) {
         const u32 k = (u32)__ffs((int)m) - 1u;
         m &= m - 1u;
-        if ((j & 3ull) == 0) {
+        const u64 start = off + k + 1;
+        if ((j & 3ull) == 0 && start + FASTF_FREQ_EXC_STRIDE > done_below && (last_chunk || start + FASTF_FREQ_EXC_STRIDE <= n)) {
             const u64 r = j >> 2;
-            const u64 start = off + k + 1;
             u64 key = 0;
             bool good = true;
             for (u32 cidx = 0; cidx < klen; cidx++) {

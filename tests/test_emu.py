@@ -49,6 +49,37 @@ def test_emu_freq_ragged(emu_lib):
     _run(emu_lib, ["freq-ragged_nonl-l16-u12", "freq-ragged_trunc-l5-u3"])
 
 
+@pytest.mark.parametrize("blocks", [1, 2, 5])
+def test_emu_freq_streams_in_chunks(emu_lib, blocks, tmp_path, monkeypatch):
+    """freq keeps only the keys resident: the text streams through in chunks of whole BGZF blocks; lines (and keys) that cross a chunk
+    boundary, chunks without a newline, a carried tail shorter than the carry window -- every golden whitelist and a synthetic FASTQ
+    (its BGZF blocks end at arbitrary text positions) come out as with one chunk"""
+    monkeypatch.setenv("FASTF_STREAM_CHUNK_BLOCKS", str(blocks))
+    _run(emu_lib, ["freq-ragged-l16-u12", "freq-ragged_nonl-l16-u12", "freq-ragged_trunc-l5-u3", "freq-ragged-l16-u0"])
+    code = (
+        "import sys, os\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import fastf_b200, oracle_binding, synth_binding\n"
+        "O, S = oracle_binding.load(), synth_binding.load()\n"
+        "d = %r\n"
+        "p = S.params(n_reads=9000, n_cells=40, seed=3, p_umi_n=0.02, zlevel=1)\n"
+        "fq, st = S.fastq(p, 2)\n"
+        "assert st.n_blocks > 6, st.n_blocks\n"
+        "open(os.path.join(d, 'R1.fastq.gz'), 'wb').write(fq)\n"
+        "import gzip\n"
+        "open(os.path.join(d, 'plain.fastq'), 'wb').write(gzip.decompress(fq)[:300000])\n"
+        "O.freq(os.path.join(d, 'plain.fastq'), 16, 12, os.path.join(d, 'want.txt'))\n"
+        "assert fastf_b200.freq(os.path.join(d, 'plain.fastq'), d, 16, 12) == 0\n"
+        "assert open(os.path.join(d, 'whitelist.txt'), 'rb').read() == open(os.path.join(d, 'want.txt'), 'rb').read(), 'plain text'\n"
+        "for l, u in ((16, 12), (7, 0), (16, 15)):\n"
+        "    assert fastf_b200.freq(os.path.join(d, 'R1.fastq.gz'), d, l, u) == 0\n"
+        "    O.freq(os.path.join(d, 'R1.fastq.gz'), l, u, os.path.join(d, 'want.txt'))\n"
+        "    assert open(os.path.join(d, 'whitelist.txt'), 'rb').read() == open(os.path.join(d, 'want.txt'), 'rb').read(), (l, u)\n"
+        "print('ok')\n") % (ROOT, os.path.join(ROOT, "tests"), str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FASTF_GPU_LIB=emu_lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-3000:]
+
+
 def test_emu_c_host_cli(emu_lib):
     """the C host (fastf_b200/host: option parsing, list readers, sqlite + gz writers, -u) linked against the emulator build"""
     _run(emu_lib, ["synth4k-c0.5-r0.5-s926", "freq-ragged-l16-u0"], cli=True)
