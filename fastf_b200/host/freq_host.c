@@ -4,9 +4,12 @@
  * the pre-order of the reference's BST (fastf_cartesian_preorder). */
 #include "fastf_host.h"
 #include "../../include/fastf_gpu.h"
+#include <fcntl.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 typedef struct { char key[36]; uint32_t len; uint32_t first; uint64_t count; } exc_t;
 static int exc_cmp(const void *a, const void *b)
@@ -33,14 +36,13 @@ int freq_whitelist(const char *r1_path, size_t len_cellbarcode, size_t len_umi, 
     uint32_t *first_all = NULL, *src = NULL;
     uint64_t *order = NULL;
     const uint32_t klen = (uint32_t)(len_cellbarcode + len_umi);
-    FILE *f = fopen(r1_path, "rb");
-    if (!f) { fprintf(stderr, "Cannot open file %s \n", r1_path); return 1; }
-    fseek(f, 0, SEEK_END);
-    long long n = ftell(f);
-    fseek(f, 0, SEEK_SET);
+    const int f = open(r1_path, O_RDONLY);
+    struct stat sb;
+    if (f < 0 || fstat(f, &sb)) { fprintf(stderr, "Cannot open file %s \n", r1_path); if (f >= 0) close(f); return 1; }
+    long long n = (long long)sb.st_size;
     if (fastf_ctx_create(fastf_device, &ctx)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(NULL)); goto done; }
     if (fastf_host_alloc(ctx, (size_t)(n > 0 ? n : 1), &buf)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
-    if (n > 0 && fread(buf, 1, (size_t)n, f) != (size_t)n) { fprintf(stderr, "Cannot read file %s \n", r1_path); goto done; }
+    if (n > 0 && fastf_pread_parallel(f, buf, (size_t)n, 0) != (ssize_t)n) { fprintf(stderr, "Cannot read file %s \n", r1_path); goto done; }   /* several readers into pinned memory */
     if (fastf_freq_gpu(ctx, buf, (size_t)n, klen, 0, &res)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
 
     /* exceptional reads -> distinct keys sorted by bytes */
@@ -84,16 +86,32 @@ int freq_whitelist(const char *r1_path, size_t len_cellbarcode, size_t len_umi, 
     }
     if (fastf_cartesian_preorder(first_all, total, order)) { fprintf(stderr, "\x1b[31mError:\x1b[0m pre-order failed\n"); goto done; }
     {
-        char dk[36];
+        /* "key,count\n" lines formatted into a block buffer: 10^8 fprintf calls would cost more than the device job */
+        const size_t BLK = (size_t)4 << 20;
+        char *out = (char *)malloc(BLK + 128);
+        size_t o = 0;
+        if (!out) { fprintf(stderr, "\x1b[31mError:\x1b[0m out of host memory\n"); goto done; }
         for (uint64_t i = 0; i < total; i++) {
             uint32_t s = src[order[i]];
-            if (s & 0x80000000u) fprintf(fp, "%s,%ld\n", exc[s & 0x7fffffffu].key, (long)exc[s & 0x7fffffffu].count);
-            else { decode_key(res.key[s], klen, dk); fprintf(fp, "%s,%ld\n", dk, (long)res.count[s]); }
+            if (s & 0x80000000u) {
+                const exc_t *e = &exc[s & 0x7fffffffu];
+                memcpy(out + o, e->key, e->len); o += e->len;
+                out[o++] = ',';
+                o += fastf_fmt_u64(out + o, e->count);
+            } else {
+                decode_key(res.key[s], klen, out + o); o += klen;
+                out[o++] = ',';
+                o += fastf_fmt_u64(out + o, res.count[s]);
+            }
+            out[o++] = '\n';
+            if (o >= BLK) { fwrite(out, 1, o, fp); o = 0; }
         }
+        if (o) fwrite(out, 1, o, fp);
+        free(out);
     }
     rc = 0;
 done:
-    fclose(f);
+    close(f);
     free(exc); free(first_all); free(src); free(order);
     fastf_freq_result_free(&res);
     if (ctx) { fastf_host_free(ctx, buf); fastf_ctx_destroy(ctx); }

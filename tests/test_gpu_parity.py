@@ -351,6 +351,17 @@ def test_freq_matches_oracle(gpu_ctx, oracle, synth, tmp_path, n, cells, l, u):
     assert open(tmp_path / "whitelist.txt", "rb").read() == open(tmp_path / "want.txt", "rb").read()
 
 
+def test_freq_streaming_10M_reads_vs_oracle(gpu_ctx, oracle, synth, tmp_path, monkeypatch):
+    """BASELINE configs[1] shape (20k true barcodes + error variants, -l 16 -u 12) at 10 M reads, streamed through HBM in chunks of 4096
+    BGZF blocks (the default chunk would swallow this file whole): ~10^7 distinct keys, whitelist byte-identical to the oracle's"""
+    import fastf_b200
+    fq, _ = synth.write_fastq(str(tmp_path), n_reads=10_000_000, n_cells=20000, seed=77, p_umi_n=0.001)
+    oracle.freq(fq, 16, 12, str(tmp_path / "want.txt"))
+    monkeypatch.setenv("FASTF_STREAM_CHUNK_BLOCKS", "4096")
+    assert fastf_b200.freq(fq, str(tmp_path), 16, 12, ctx=gpu_ctx) == 0
+    assert open(tmp_path / "whitelist.txt", "rb").read() == open(tmp_path / "want.txt", "rb").read()
+
+
 def test_freq_plain_text_input_and_gzip_refusal(gpu_ctx, oracle, tmp_path):
     import fastf_b200
     raw = gzip.open(os.path.join(GOLD, "freq", "ragged.fastq.gz"), "rb").read()
