@@ -49,6 +49,7 @@ class TaghistResult(C.Structure):
 
 _SIGS = {
     "fastf_abi_version": (C.c_int, []),
+    "fastf_build_info": (C.c_char_p, []),
     "fastf_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "fastf_ctx_destroy": (None, [C.c_void_p]),
     "fastf_last_error": (C.c_char_p, [C.c_void_p]),
@@ -120,8 +121,17 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    # a prebuilt binary that does not match the sources next to it is an error, not a surprise (variant builds opt out)
+    info = dict(kv.split("=", 1) for kv in lib.fastf_build_info().decode().split())
+    if not os.environ.get("FASTF_GPU_LIB") and info.get("src") not in ("unknown", _build.source_hash()):
+        raise RuntimeError(f"{path} was built from other sources (src={info.get('src')}, tree={_build.source_hash()}): run `python -m fastf_b200.build`")
     _lib = lib
     return lib
+
+
+def build_info():
+    """dict of the loaded library's build parameters (streams per SM, kernel shape, source hash)"""
+    return dict(kv.split("=", 1) for kv in load().fastf_build_info().decode().split())
 
 
 class FastfError(RuntimeError):

@@ -34,6 +34,17 @@ def _sources(d, exts):
     return [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(exts)]
 
 
+def source_hash():
+    """sha256 (first 16 hex digits) over the kernel sources and the C-ABI header: baked into the library (fastf_build_info) so that a
+    stale prebuilt binary is noticed at load time"""
+    import hashlib
+    csrc = os.path.join(PKG, "csrc")
+    h = hashlib.sha256()
+    for f in _sources(csrc, (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "fastf_gpu.h")]:
+        h.update(os.path.basename(f).encode() + b"\0" + open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def build_cuda(force=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     csrc = os.path.join(PKG, "csrc")
@@ -42,10 +53,11 @@ def build_cuda(force=False):
         return LIB
     if not os.path.exists(nvcc):
         if os.path.exists(LIB):
-            return LIB   # GPU box without a changed source tree: the prebuilt library travelled with the snapshot
+            sys.stderr.write("fastf_b200.build: nvcc not found, keeping the prebuilt libfastf_gpu.so although sources are newer (the source hash is checked at load time)\n")
+            return LIB
         raise RuntimeError("nvcc not found and no prebuilt libfastf_gpu.so")
     os.makedirs(BUILD, exist_ok=True)
-    _run([nvcc] + NVCC_FLAGS + ["-o", LIB, os.path.join(csrc, "capi.cu"), os.path.join(csrc, "sharded.cu"), "-ldl"])
+    _run([nvcc] + NVCC_FLAGS + ['-DFASTF_SRC_HASH="%s"' % source_hash(), "-o", LIB, os.path.join(csrc, "capi.cu"), os.path.join(csrc, "sharded.cu"), "-ldl"])
     return LIB
 
 
@@ -102,7 +114,7 @@ def build_emu():
     if _newer(out, deps):
         return out
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    _run(["g++", "-O2", "-std=c++17", "-DFASTF_EMU", "-I" + os.path.join(ROOT, "tests", "emu"), "-x", "c++", "-fPIC", "-shared", "-o", out,
+    _run(["g++", "-O2", "-std=c++17", "-DFASTF_EMU", '-DFASTF_SRC_HASH="%s"' % source_hash(), "-I" + os.path.join(ROOT, "tests", "emu"), "-x", "c++", "-fPIC", "-shared", "-o", out,
           os.path.join(csrc, "capi.cu"), os.path.join(csrc, "sharded.cu"), "-lz", "-lpthread"])
     return out
 

@@ -29,32 +29,39 @@
 #pragma once
 #include "bgzf_inflate.cuh"
 
+// Shape and table sizes (round 2, measured on B200 with scripts/gpu_inflate_ab.sh on images of exactly two rounds of each shape's
+// own stream count; profiles/r02_inflate_ab.md).  The kernel is bound by the number of independent Huffman chains an SM keeps
+// going: a stream decodes a symbol every ~1000 cycles whatever the shape, so throughput follows the stream count, which shared
+// memory limits.  8-bit literal/length and 6-bit distance tables with a 32-token ring fit 224 streams per SM (7 full decoder
+// warps + 25 service warps = 1024 threads): 179-183 GB/s algorithmic against 156 GB/s for the round-1 shape (128 streams, 9/7-bit
+// tables, 16 lanes x 8 warps + 24).  16-lane decoder warps at 224 streams leave too few service warps (138 GB/s); 256 streams need
+// a 16-token ring that starves the decoders (147 GB/s).
 #ifndef FASTF_TPS_LBITS
-#define FASTF_TPS_LBITS 9
+#define FASTF_TPS_LBITS 8
 #endif
 #ifndef FASTF_TPS_DBITS
-#define FASTF_TPS_DBITS 7
+#define FASTF_TPS_DBITS 6
 #endif
-// kernel shape (template parameters L = decoding lanes per decoder warp, SVC = service warps): 128 streams per CTA,
-// 128 / L decoder warps.  Divergent paths of a warp serialise, so few lanes and many warps decode faster.
+// kernel shape (template parameters L = decoding lanes per decoder warp, SVC = service warps): FASTF_TPS_STREAMS streams per CTA,
+// FASTF_TPS_STREAMS / L decoder warps
 #ifndef FASTF_TPS_STREAMS
-#define FASTF_TPS_STREAMS 128
-#endif
-#ifndef FASTF_TPS_MAX_SVC
-#define FASTF_TPS_MAX_SVC 28
+#define FASTF_TPS_STREAMS 224
 #endif
 #define FASTF_TPS_THREADS_OF(L, SVC) ((FASTF_TPS_STREAMS / (L) + (SVC)) * 32)
-// defaults (used by the host launch and the emulator test)
+// the shape the host launches (and the emulator tests)
 #ifndef FASTF_TPS_LANES
-#define FASTF_TPS_LANES 16
+#define FASTF_TPS_LANES 32
 #endif
 #ifndef FASTF_TPS_SVC_WARPS
-#define FASTF_TPS_SVC_WARPS 24
+#define FASTF_TPS_SVC_WARPS 25
+#endif
+#ifndef FASTF_TPS_MAX_SVC
+#define FASTF_TPS_MAX_SVC FASTF_TPS_SVC_WARPS
 #endif
 #define FASTF_TPS_SORTED_U16 320   // per stream in GLOBAL scratch: symbols sorted by code length (288 lit/len + 32 dist), read only for codes longer than the tables
 #define FASTF_TPS_THREADS FASTF_TPS_THREADS_OF(FASTF_TPS_LANES, FASTF_TPS_SVC_WARPS)
 #ifndef FASTF_TPS_RING
-#define FASTF_TPS_RING 64u
+#define FASTF_TPS_RING 32u
 #endif
 #ifndef FASTF_TPS_TRIPLES
 #define FASTF_TPS_TRIPLES 2           // literal tokens (three literals each) a decoder round may produce in front of a match
@@ -62,11 +69,17 @@
 #ifndef FASTF_TPS_BATCH_MIN
 #define FASTF_TPS_BATCH_MIN (FASTF_TPS_RING >= 64u ? 32u : FASTF_TPS_RING / 2u)       // tokens that make a stream worth a visit of its service warp
 #endif
+#ifndef FASTF_TPS_BRANCHFREE
+#define FASTF_TPS_BRANCHFREE 1      // 1: literal triples without inner branches (+4 % at 224 streams, +7 % on the decoders alone); 2: also the bit-buffer refills
+#endif
 #ifndef FASTF_TPS_PREFETCH2
 #define FASTF_TPS_PREFETCH2 0
 #endif
 #ifndef FASTF_TPS_FAR_LEN
 #define FASTF_TPS_FAR_LEN 32u         // longest match handled in the far group (32 or 64: one or two bytes per lane)
+#endif
+#ifndef FASTF_TPS_WAVES
+#define FASTF_TPS_WAVES 0            // service copy in waves of independent matches (long far matches as pieces, near matches grouped)
 #endif
 #ifndef FASTF_TPS_FAR
 #define FASTF_TPS_FAR 4              // far matches whose source loads are in flight together
@@ -170,7 +183,7 @@ __device__ __forceinline__ u32 fastf_ld_sorted(const u16 *p) { return __ldcg(p);
 // A decoder knows the source of a match thousands of cycles before the stream's service warp copies it: it asks the L2 for the line
 // right away (the windows of all resident streams are far larger than the L2, so a distant source is usually a DRAM access).
 #ifndef FASTF_TPS_PREFETCH_SRC
-#define FASTF_TPS_PREFETCH_SRC 0u     // smallest distance worth a prefetch (0 = never)
+#define FASTF_TPS_PREFETCH_SRC 512u   // smallest distance worth a prefetch (0 = never); +2 % at 224 streams
 #endif
 #ifdef FASTF_EMU
 __device__ __forceinline__ void fastf_prefetch_l2(const void *) {}
@@ -429,6 +442,65 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
     // one at a time in token order behind a __syncwarp.  A far match never reads what a later-handled one writes, and the
     // bytes a slow match reads lie before its own position, so handling the far ones first preserves the result.
     // (Synthetic 10x BAM: a batch of 32 tokens holds ~10 matches of 12 bytes on average, 9 % longer than 32, 14 % closer than 200.)
+#if FASTF_TPS_WAVES
+    // Waves of independent copies (FASTF_TPS_WAVES): a set of non-overlapping matches (dist >= len) whose sources are final is cut into
+    // pieces of <= 32 bytes; the source loads of FASTF_TPS_FAR pieces are in flight together, then stored.  Wave 0 = every match
+    // whose source lies before the batch, whatever its length (a 64-byte match is two pieces, not a trip of its own).  The rest is
+    // taken in token order: all remaining non-overlapping matches whose source ends at or before the destination of the FIRST
+    // remaining one read only bytes that are already stored -- one wave, one round trip; a match that overlaps itself goes alone.
+    const u32 mlen = tok & 511u, mdist = (tok >> 9) & 0xffffu;
+    u32 wavem = __ballot_sync(FASTF_FULL_MASK, is_match && off + mlen <= mdist);
+    u32 restm = __ballot_sync(FASTF_FULL_MASK, is_match && !(off + mlen <= mdist));
+    if (FASTF_TPS_NOCOPY) wavem = restm = 0;
+    __syncwarp();
+    for (;;) {
+        u32 c_o = 0, c_len = 0, c_dist = 0, c_k = 0;   // the match being cut into pieces (warp-uniform)
+        while (wavem || c_k < c_len) {
+            u32 dpos[FASTF_TPS_FAR], dlen[FASTF_TPS_FAR], dbyte[FASTF_TPS_FAR];
+#pragma unroll
+            for (int u = 0; u < FASTF_TPS_FAR; u++) {
+                dlen[u] = 0; dpos[u] = 0; dbyte[u] = 0;
+                if (c_k >= c_len && wavem) {
+                    const u32 m = (u32)__ffs((int)wavem) - 1u;
+                    wavem &= wavem - 1u;
+                    const u32 t = __shfl_sync(FASTF_FULL_MASK, tok, (int)m);
+                    c_o = __shfl_sync(FASTF_FULL_MASK, off, (int)m);
+                    c_len = t & 511u; c_dist = (t >> 9) & 0xffffu; c_k = 0;
+                }
+                if (c_k < c_len) {
+                    dpos[u] = opos + c_o + c_k;
+                    dlen[u] = c_len - c_k < 32u ? c_len - c_k : 32u;
+                    if (lane < dlen[u]) dbyte[u] = out[dpos[u] - c_dist + lane];
+                    c_k += 32u;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < FASTF_TPS_FAR; u++)
+                if (lane < dlen[u]) out[dpos[u] + lane] = (u8)dbyte[u];
+        }
+        if (!restm) break;
+        const u32 m0 = (u32)__ffs((int)restm) - 1u;
+        const u32 d0 = __shfl_sync(FASTF_FULL_MASK, off, (int)m0);
+        wavem = __ballot_sync(FASTF_FULL_MASK, ((restm >> lane) & 1u) && mdist >= mlen && off + mlen <= mdist + d0);
+        __syncwarp();   // everything stored so far in this batch is ordered before the next loads
+        if (wavem) { restm &= ~wavem; continue; }
+        // the first remaining match overlaps itself: the pattern src[0..dist) repeats; j % dist by a reciprocal multiply (exact for j < 258)
+        restm &= restm - 1u;
+        const u32 t = __shfl_sync(FASTF_FULL_MASK, tok, (int)m0);
+        const u32 len = t & 511u, dist = (t >> 9) & 0xffffu, dst = opos + d0;
+        const u8 *src = out + dst - dist;
+        const u32 rcp = (u32)(1048576.0f * __frcp_rn((float)dist)) + 2u;
+        for (u32 k = 0; k < len; k += 32) {
+            const u32 j = k + lane;
+            if (j < len) {
+                const u32 q = (j * rcp) >> 20;
+                u32 r = j - q * dist;
+                if (r >= dist) r += dist;   // q overshoots by at most one
+                out[dst + j] = src[r];
+            }
+        }
+    }
+#else
     u32 farm, slowm;
     {
         const u32 len = tok & 511u, dist = (tok >> 9) & 0xffffu;
@@ -492,6 +564,7 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
             }
         }
     }
+#endif
     u32 consumed = ntok;
     u32 new_opos = opos + total;
     if (endm) {
@@ -697,6 +770,15 @@ struct FastfTpsReader {
     }
     __device__ __forceinline__ void refill()
     {
+#if FASTF_TPS_BRANCHFREE >= 2 && !FASTF_TPS_PREFETCH2
+        // straight-line form: in a warp of 32 streams some lane refills at nearly every refill point, so nobody gains from jumping
+        // over the block, and the branch costs its resolution.  Only the load of the next word stays predicated.
+        const bool take_w = nbits <= 32u;
+        buf |= take_w ? ((u64)nextw << nbits) : 0ull;
+        nbits += take_w ? 32u : 0u;
+        widx += take_w ? 1u : 0u;
+        if (take_w) nextw = ldw(widx);
+#else
         if (nbits <= 32u) {
             buf |= (u64)nextw << nbits;
             nbits += 32u;
@@ -708,6 +790,7 @@ struct FastfTpsReader {
             nextw = ldw(widx);
 #endif
         }
+#endif
     }
     __device__ __forceinline__ u32 take(u32 n) { u32 v = (u32)buf & ((1u << n) - 1u); buf >>= n; nbits -= n; return v; }
     __device__ __forceinline__ void drop(u32 n) { buf >>= n; nbits -= n; }
@@ -800,6 +883,42 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
             u32 err = 0;
             const u32 wr0 = wr;
             bool end_stream = false, end_block = false;
+#if FASTF_TPS_BRANCHFREE
+            // The literal run without inner branches: with 32 streams per warp some lane takes every path of a branchy triple in
+            // nearly every round, so all lanes walk the longest chain anyway and only pay for resolving the branches.  Every lane does
+            // the three look-ups of a triple; a lane whose run has ended drops zero bits and looks the same entry up again.
+            if (kind == FASTF_T16_LIT) {
+                bool act = true;
+#pragma unroll
+                for (int triple = 0; triple < FASTF_TPS_TRIPLES; triple++) {
+                    br.drop(act ? (e & 15u) : 0u);
+                    u32 tok = e >> 8;
+                    const u32 e1 = S.lit[(u32)br.buf & ((1u << FASTF_TPS_LBITS) - 1u)];
+                    const bool l1 = act && FASTF_T16_IS_TABLE_LIT(e1);
+                    br.drop(l1 ? (e1 & 15u) : 0u);
+                    tok |= l1 ? (e1 & 0xff00u) : 0u;
+                    const u32 e2 = S.lit[(u32)br.buf & ((1u << FASTF_TPS_LBITS) - 1u)];
+                    const bool l2 = l1 && FASTF_T16_IS_TABLE_LIT(e2);
+                    br.drop(l2 ? (e2 & 15u) : 0u);
+                    tok |= l2 ? ((e2 & 0xff00u) << 8) : 0u;
+                    const u32 cnt = 1u + (u32)l1 + (u32)l2;
+                    br.refill();
+                    const u32 e3 = S.lit[(u32)br.buf & ((1u << FASTF_TPS_LBITS) - 1u)];
+                    if (act) {
+                        if (pos + cnt > isize) { err = FASTF_ST_OUT_OVERFLOW; }   // never hand out bytes beyond the block
+                        else {
+                            fastf_stv(&S.ring[wr & (FASTF_TPS_RING - 1u)], tok | (cnt << 24));
+                            wr++;
+                            pos += cnt;
+                        }
+                        e = e3;
+                    }
+                    act = act && !err && l2 && FASTF_T16_IS_TABLE_LIT(e3);
+                }
+                kind = (((e >> 4) & 3u) == FASTF_T16_SYM && !err) ? (u32)FASTF_T16_SYM : 4u;
+                if (kind == FASTF_T16_SYM) br.refill();
+            }
+#else
             if (kind == FASTF_T16_LIT) {
 #pragma unroll
                 for (int triple = 0; triple < FASTF_TPS_TRIPLES; triple++) {
@@ -829,6 +948,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
                 kind = (((e >> 4) & 3u) == FASTF_T16_SYM && !err) ? (u32)FASTF_T16_SYM : 4u;
                 if (kind == FASTF_T16_SYM) br.refill();
             }
+#endif
             if (kind == FASTF_T16_SYM) {
                 br.drop(e & 15u);
                 const u32 K = G.lenK[e >> 8];

@@ -192,6 +192,16 @@ struct Timer {   // CUDA-event stopwatch on one stream; accumulates into *acc at
 // context
 // ---------------------------------------------------------------------------------------------------
 extern "C" int fastf_abi_version(void) { return FASTF_ABI_VERSION; }
+#ifndef FASTF_SRC_HASH
+#define FASTF_SRC_HASH "unknown"
+#endif
+#define FASTF_STR2(x) #x
+#define FASTF_STR(x) FASTF_STR2(x)
+extern "C" const char *fastf_build_info(void)
+{
+    return "streams=" FASTF_STR(FASTF_TPS_STREAMS) " lanes=" FASTF_STR(FASTF_TPS_LANES) " svc=" FASTF_STR(FASTF_TPS_SVC_WARPS) " lbits=" FASTF_STR(FASTF_TPS_LBITS) " dbits=" FASTF_STR(FASTF_TPS_DBITS)
+           " ring=" FASTF_STR(FASTF_TPS_RING) " staged=" FASTF_STR(FASTF_TPS_STAGED) " src=" FASTF_SRC_HASH;
+}
 
 static char g_create_err[512] = "";
 
@@ -395,7 +405,7 @@ struct DeScratch {   // per-launch state of the inflate engines
     DevBuf sorted;                                // its per-stream sorted-symbol lists (global scratch)
 };
 #define FASTF_INFLATE_TPS 1u   // inflate_lanes 1..4 select a shape of the thread-per-stream kernel; 8/16/32 the lock-step kernel
-#define FASTF_INFLATE_DEFAULT 2u   // 0 = default: thread-per-stream, 128 streams per SM: 16 decoding lanes x 8 decoder warps + 24 service warps
+#define FASTF_INFLATE_DEFAULT 2u   // 0 = default: the thread-per-stream kernel
 
 // CRC-32 of every inflated block against its BGZF trailer (htslib does this in bgzf_read_block); sets FASTF_ST_BAD_CRC in status[]
 static int launch_crc(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_total, const u64 *in_off, const u32 *in_len, const u8 *infl, const u64 *out_off, const u32 *isize, u32 nblocks,
@@ -462,7 +472,7 @@ static int launch_inflate(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_to
     lanes &= 0xffu;   // the kernel shape; the flag bits (no-CRC, straddle) were for the callers
     if (lanes >= 1 && lanes <= 4) {
         // thread-per-stream kernel: persistent CTAs (one per SM), FASTF_TPS_STREAMS streams each; blocks are handed out by a global counter.
-        // lanes selects the shape <decoding lanes per decoder warp, service warps>: 1 = <8, 16>, 2 = <16, 24> (default), 3 = <16, 16>, 4 = <32, 28>
+        // one shape is built: <FASTF_TPS_LANES decoding lanes per decoder warp, FASTF_TPS_SVC_WARPS service warps> (bgzf_inflate_tps.cuh); lanes 1..4 all select it
         const size_t smem = sizeof(FastfTpsStream) * FASTF_TPS_STREAMS + sizeof(FastfTpsShared);
         TRY(dev_reserve(ctx, de->counter, 64));
         CK(cudaMemsetAsync(de->counter.p, 0, sizeof(u32), s));
@@ -474,21 +484,12 @@ static int launch_inflate(fastf_ctx *ctx, u32 lanes, const u8 *comp, u64 comp_to
         TRY(dev_reserve(ctx, de->sorted, (size_t)grid * FASTF_TPS_STREAMS * FASTF_TPS_SORTED_U16 * sizeof(u16)));
         A.sorted = de->sorted.as<u16>();
 #ifndef FASTF_EMU
-#define FASTF_TPS_ATTR(L, SVC) CK(cudaFuncSetAttribute(fastf_bgzf_inflate_tps_kernel<L, SVC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
-#else
-#define FASTF_TPS_ATTR(L, SVC) ((void)0)
+        if (!ctx->tps_attr_set) {
+            CK(cudaFuncSetAttribute(fastf_bgzf_inflate_tps_kernel<FASTF_TPS_LANES, FASTF_TPS_SVC_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->tps_attr_set = true;
+        }
 #endif
-#ifdef FASTF_TPS_ALT_L
-        // experiment builds (-DFASTF_TPS_STREAMS=... -DFASTF_TPS_ALT_L=... -DFASTF_TPS_ALT_SVC=...): one shape only
-        if (!ctx->tps_attr_set) { FASTF_TPS_ATTR(FASTF_TPS_ALT_L, FASTF_TPS_ALT_SVC); ctx->tps_attr_set = true; }
-        FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<FASTF_TPS_ALT_L, FASTF_TPS_ALT_SVC>), grid, FASTF_TPS_THREADS_OF(FASTF_TPS_ALT_L, FASTF_TPS_ALT_SVC), smem, s, A);
-#else
-        if (!ctx->tps_attr_set) { FASTF_TPS_ATTR(8, 16); FASTF_TPS_ATTR(16, 24); FASTF_TPS_ATTR(16, 16); FASTF_TPS_ATTR(32, 28); ctx->tps_attr_set = true; }
-        if (lanes == 1) { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<8, 16>), grid, FASTF_TPS_THREADS_OF(8, 16), smem, s, A); }
-        else if (lanes == 2) { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<16, 24>), grid, FASTF_TPS_THREADS_OF(16, 24), smem, s, A); }
-        else if (lanes == 3) { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<16, 16>), grid, FASTF_TPS_THREADS_OF(16, 16), smem, s, A); }
-        else { FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<32, 28>), grid, FASTF_TPS_THREADS_OF(32, 28), smem, s, A); }
-#endif
+        FASTF_LAUNCH((fastf_bgzf_inflate_tps_kernel<FASTF_TPS_LANES, FASTF_TPS_SVC_WARPS>), grid, FASTF_TPS_THREADS, smem, s, A);
         CKL("bgzf_inflate_tps");
         return 0;
     }

@@ -7,6 +7,7 @@
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
+#include <string.h>
 
 #ifdef FASTF_EMU
 #include "cuda_emu.h"
@@ -64,6 +65,38 @@ __device__ __forceinline__ void fastf_spin_poll() { emu::spin_yield(); }
 #endif
 __device__ __forceinline__ void fastf_spin_pause() { __nanosleep(FASTF_PAUSE_NS); }
 __device__ __forceinline__ void fastf_spin_poll() {}
+#endif
+
+// ---- TMA 1-D bulk copy global -> shared memory, completion on an mbarrier (sm_90+/sm_100a: SASS UBLKCP + SYNCS) ----
+// One lane issues the copy of a whole window; the TMA engine streams it without occupying the warp's load/store slots and every
+// lane then waits on the barrier's phase.  dst, src and bytes are multiples of 16.  The emulator build copies synchronously.
+#ifdef FASTF_EMU
+__device__ __forceinline__ void fastf_mbar_init(u64 *, u32) {}
+__device__ __forceinline__ void fastf_tma_load_1d(void *dst_smem, const void *src_gmem, u32 bytes, u64 *) { memcpy(dst_smem, src_gmem, bytes); }
+__device__ __forceinline__ void fastf_mbar_wait(u64 *, u32) {}
+#else
+__device__ __forceinline__ u32 fastf_smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fastf_mbar_init(u64 *mbar, u32 arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fastf_smem_addr(mbar)), "r"(arrivals));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// the calling thread is the barrier's one arrival: it announces the byte count, then starts the copy
+__device__ __forceinline__ void fastf_tma_load_1d(void *dst_smem, const void *src_gmem, u32 bytes, u64 *mbar)
+{
+    const u32 d = fastf_smem_addr(dst_smem), b = fastf_smem_addr(mbar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses of the window are ordered before the engine's writes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src_gmem), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void fastf_mbar_wait(u64 *mbar, u32 parity)
+{
+    const u32 b = fastf_smem_addr(mbar);
+    u32 done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(b), "r"(parity) : "memory");
+    }
+}
 #endif
 
 __device__ __forceinline__ u32 fastf_lane_id() { return threadIdx.x & 31u; }

@@ -39,6 +39,9 @@ typedef struct fastf_ctx fastf_ctx;
 typedef struct fastf_bam2db_job fastf_bam2db_job;
 
 int fastf_abi_version(void);
+/* how this binary was built: "streams=<BGZF blocks in flight per SM> lanes=.. svc=.. lbits=.. dbits=.. ring=.. staged=.. src=<hash of the kernel sources>";
+ * hosts compare src with the sources they ship (fastf_b200/_lib.py refuses a stale library) */
+const char *fastf_build_info(void);
 int fastf_ctx_create(int device, fastf_ctx **out);
 void fastf_ctx_destroy(fastf_ctx *ctx);
 const char *fastf_last_error(const fastf_ctx *ctx);

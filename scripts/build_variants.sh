@@ -6,7 +6,7 @@ mkdir -p fastf_b200/_build/variants
 rm -f fastf_b200/_build/variants/*.so
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"
-  nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared $flags -o fastf_b200/_build/variants/$name.so fastf_b200/csrc/capi.cu fastf_b200/csrc/sharded.cu -ldl &
+  nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -DFASTF_SRC_HASH=\"variant\" $flags -o fastf_b200/_build/variants/$name.so fastf_b200/csrc/capi.cu fastf_b200/csrc/sharded.cu -ldl &
 done
 wait
 ls -la fastf_b200/_build/variants/

@@ -1,8 +1,7 @@
 #!/bin/bash
-# A/B of the inflate kernel alone over library variants (scripts/build_variants.sh) on one chunk-sized BGZF image.
+# A/B of the inflate kernel alone over library variants (scripts/build_variants.sh); every variant gets an image of exactly two rounds
+# of its own stream count (scripts/inflate_ab.py).
 # usage: gpu_inflate_ab.sh "<lanes values for the default-shape builds>" [ncu-full-variant[:lanes] ...]
-# Every variant .so is timed (ALT builds hold one shape; the others are run once per lanes value); the named ones also get one
-# `ncu --set full` capture of the kernel (after their plain run).
 mkdir -p gpurun_out
 LOG=gpurun_out/inflate_ab.log
 : > $LOG
@@ -10,14 +9,10 @@ LANES="${1:-0}"; shift
 python scripts/inflate_ab.py --reps 1 2>gpurun_out/ab_err.txt >> $LOG || tail -3 gpurun_out/ab_err.txt >> $LOG   # generates + caches the image
 for lib in fastf_b200/_build/variants/*.so; do
   NOCRC=""; case "$lib" in *nocopy*|*_l1*) NOCRC=1;; esac
-  LL="0"; case "$(basename $lib)" in b*|s0*) LL="$LANES";; esac
+  LL="0"; case "$(basename $lib)" in zz*) LL="$LANES";; esac
   for l in $LL; do
     FASTF_AB_NOCRC=$NOCRC FASTF_GPU_LIB=$PWD/$lib python scripts/inflate_ab.py --lanes $l 2>gpurun_out/ab_err.txt >> $LOG || { echo "FAILED $lib lanes $l" >> $LOG; tail -2 gpurun_out/ab_err.txt >> $LOG; }
   done
-done
-for g in 32 128; do
-  echo "FASTF_L2_FETCH=$g (default build)" >> $LOG
-  FASTF_L2_FETCH=$g python scripts/inflate_ab.py 2>gpurun_out/ab_err.txt >> $LOG || tail -2 gpurun_out/ab_err.txt >> $LOG
 done
 for spec in "$@"; do
   v="${spec%%:*}"; l="${spec#*:}"; [ "$l" = "$spec" ] && l=0
