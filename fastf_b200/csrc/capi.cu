@@ -276,7 +276,8 @@ extern "C" void fastf_ctx_trim(fastf_ctx *ctx) { if (ctx) { cudaSetDevice(ctx->d
 extern "C" uint64_t fastf_keep_threshold(float rate_depth)
 {
     const double r = (double)rate_depth;
-    if (!(r > 0.0)) return 0;   // also NaN: every comparison `x >= NaN` is false -> the reference keeps everything... handled below
+    if (r <= 0.0) return 0;     // every draw is >= rate: nothing is kept.  A NaN rate falls through: `x >= NaN` is false for every draw, the reference
+                                // drops nothing, and the search below ends at 2^32 (keep everything)
     uint64_t lo = 0, hi = 4294967296ull;   // smallest u with u*(1/4294967295) >= r, or 2^32 if none
     while (lo < hi) {
         uint64_t mid = (lo + hi) >> 1;

@@ -29,6 +29,69 @@ def shard_ranges(n_items, world):
     return out
 
 
+def _bgzf_block_size(buf, o):
+    """size of the BGZF block whose header starts at byte o (RFC 1952 member with the BC extra subfield, SAMv1 4.1), or 0"""
+    n = len(buf)
+    if o + 18 > n or buf[o] != 0x1f or buf[o + 1] != 0x8b or buf[o + 2] != 8 or not (buf[o + 3] & 4):
+        return 0
+    xlen = int(buf[o + 10]) | (int(buf[o + 11]) << 8)
+    p, end = o + 12, o + 12 + xlen
+    if end > n:
+        return 0
+    while p + 4 <= end:
+        slen = int(buf[p + 2]) | (int(buf[p + 3]) << 8)
+        if buf[p] == 66 and buf[p + 1] == 67 and slen == 2 and p + 6 <= end:
+            bsize = (int(buf[p + 4]) | (int(buf[p + 5]) << 8)) + 1
+            return bsize if bsize >= xlen + 20 and o + bsize <= n else 0
+        p += 4 + slen
+    return 0
+
+
+def find_block_start(buf, pos):
+    """first BGZF block boundary at or behind byte pos: a header whose BSIZE leads to two more headers (or to the end of the file).
+    Every rank finds its own shard this way and walks nothing but its own byte range."""
+    n = len(buf)
+    if pos <= 0:
+        return 0
+    o = pos
+    while o + 18 <= n:
+        # next candidate: the gzip magic with FEXTRA
+        win = bytes(buf[o:min(n, o + (1 << 20))])
+        k = win.find(b"\x1f\x8b\x08\x04")
+        if k < 0:
+            o += max(1, len(win) - 3)
+            continue
+        o += k
+        q, good = o, 0
+        while good < 3:
+            bs = _bgzf_block_size(buf, q)
+            if not bs:
+                break
+            q += bs
+            good += 1
+            if q == n:
+                good = 3
+        if good == 3:
+            return o
+        o += 1
+    return n
+
+
+def shard_bytes(buf, rank, world):
+    """this rank's byte range [lo, hi) of the file: whole BGZF blocks, contiguous, rank by rank"""
+    n = len(buf)
+    lo = find_block_start(buf, (n * rank) // world)
+    hi = find_block_start(buf, (n * (rank + 1)) // world) if rank + 1 < world else n
+    return lo, max(lo, hi)
+
+
+def agree(dist, torch, device, code):
+    """max of an error code over all ranks (0 = everybody is fine): a rank that failed must not leave the others in a collective"""
+    t = torch.tensor([int(code)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
 def index_blocks(lib, buf):
     """host BGZF index of a whole file image (numpy u8): (in_off, in_len, isize) arrays"""
     cap = max(16, buf.size // 64 + 16)
@@ -47,26 +110,30 @@ def index_blocks(lib, buf):
 def sharded_tail(ctx, job, dist, torch, device, rank, world, n_cells, want_rows=False):
     """steps 2-5 above for a job that has been fed this rank's shard.  Returns on rank 0 (stats, out) like Bam2dbJob.finish; None elsewhere."""
     lib = ctx.lib
-    n_rec, n_cbv = job.counts()
+    n_rec, n_cbv = job.counts()   # the caller has agreed with the other ranks that every feed succeeded
     cnt = torch.tensor([n_rec, n_cbv], dtype=torch.int64, device=device)
     allc = [torch.zeros_like(cnt) for _ in range(world)]
     dist.all_gather(allc, cnt)
     allc = [c.tolist() for c in allc]
     base = sum(c[1] for c in allc[:rank])
-    job.sample(base)
-    sampled, valid = job.sample_counts()
-    kp, n = job.kept_device()
-    bits_cell, bits_gene, bits_umi = job.key_layout()
-    key_bits = bits_cell + bits_gene + bits_umi
-    rows = None
-    if want_rows:
-        rows = np.zeros(n, dtype=np.uint64)
-        if n:
-            ctx.check(lib.fastf_memcpy_d2h(ctx.h, C.c_void_p(rows.ctypes.data), C.c_void_p(kp), n * 8), "d2h rows")
-    # 4. unique + partition by destination (order-preserving range partition of the cell index), then one all-to-all
-    send_buf = torch.empty(max(n, 1), dtype=torch.int64, device=device)
-    pc = (C.c_uint64 * world)()
-    ctx.check(lib.fastf_unique_partition_device(ctx.h, C.c_void_p(kp), n, key_bits, bits_gene, bits_umi, n_cells, world, C.c_void_p(send_buf.data_ptr()), pc), "unique_partition")
+    err, rows, n, send_buf, pc, key_bits = None, None, 0, None, (C.c_uint64 * world)(), 0
+    try:
+        job.sample(base)
+        sampled, valid = job.sample_counts()
+        kp, n = job.kept_device()
+        bits_cell, bits_gene, bits_umi = job.key_layout()
+        key_bits = bits_cell + bits_gene + bits_umi
+        if want_rows:
+            rows = np.zeros(n, dtype=np.uint64)
+            if n:
+                ctx.check(lib.fastf_memcpy_d2h(ctx.h, C.c_void_p(rows.ctypes.data), C.c_void_p(kp), n * 8), "d2h rows")
+        # 4. unique + partition by destination (order-preserving range partition of the cell index), then one all-to-all
+        send_buf = torch.empty(max(n, 1), dtype=torch.int64, device=device)
+        ctx.check(lib.fastf_unique_partition_device(ctx.h, C.c_void_p(kp), n, key_bits, bits_gene, bits_umi, n_cells, world, C.c_void_p(send_buf.data_ptr()), pc), "unique_partition")
+    except _lib.FastfError as e:
+        err = e
+    if agree(dist, torch, device, 1 if err else 0):
+        raise err or _lib.FastfError("another rank failed while sampling")
     send = [int(x) for x in pc]
     sc = torch.tensor(send, dtype=torch.int64, device=device)
     rc_t = torch.zeros(world, dtype=torch.int64, device=device)
@@ -80,10 +147,15 @@ def sharded_tail(ctx, job, dist, torch, device, rank, world, n_cells, want_rows=
     # 5. local sort + dedup/count, results stay on the device
     nnz = C.c_uint64()
     coo_dev = torch.empty((3, max(m, 1)), dtype=torch.int32, device=device)
-    if m:
-        ctx.check(lib.fastf_sort_u64_device(ctx.h, C.c_void_p(recv_buf.data_ptr()), None, m, key_bits), "sort")
-    ctx.check(lib.fastf_dedup_count_device_out(ctx.h, C.c_void_p(recv_buf.data_ptr()), m, bits_gene, bits_umi, C.byref(nnz), C.c_void_p(coo_dev[0].data_ptr()),
-                                               C.c_void_p(coo_dev[1].data_ptr()), C.c_void_p(coo_dev[2].data_ptr())), "dedup_count")
+    try:
+        if m:
+            ctx.check(lib.fastf_sort_u64_device(ctx.h, C.c_void_p(recv_buf.data_ptr()), None, m, key_bits), "sort")
+        ctx.check(lib.fastf_dedup_count_device_out(ctx.h, C.c_void_p(recv_buf.data_ptr()), m, bits_gene, bits_umi, C.byref(nnz), C.c_void_p(coo_dev[0].data_ptr()),
+                                                   C.c_void_p(coo_dev[1].data_ptr()), C.c_void_p(coo_dev[2].data_ptr())), "dedup_count")
+    except _lib.FastfError as e:
+        err = e
+    if agree(dist, torch, device, 1 if err else 0):
+        raise err or _lib.FastfError("another rank failed while counting")
     k = nnz.value
     # 6. rank 0 collects counters and the COO pieces; pieces are ordered by rank (cells are range partitioned), so they concatenate
     meta = torch.tensor([n_rec, n_cbv, sampled, valid, k, sum(send), n], dtype=torch.int64, device=device)
@@ -140,16 +212,33 @@ def bam2db_sharded(bam_file, db_file, path_out, barcodes_file, features_file, ra
             sys.stdout.flush()
         else:
             inputs = B.Bam2dbInputs(lib, barcodes_file, features_file, rate_cell, seed)
-        buf = np.fromfile(bam_file, dtype=np.uint8)   # page cache; each rank only touches its own byte range below
-        io, il, isz = index_blocks(lib, buf)
-        # contiguous block ranges; the BAM header must lie inside rank 0's range (the device header walk fails loudly otherwise)
-        lo, hi = shard_ranges(len(io), world)[rank]
-        start = int(io[lo]) - 18 if lo < len(io) else buf.size     # 18 = BGZF header with the 6-byte BC extra field
-        end = int(io[hi]) - 18 if hi < len(io) else buf.size
-        with B.Bam2dbJob(ctx, inputs, rate_depth, seed, want_rows=True, umi_max_bytes=3, headerless=(rank != 0)) as job:
-            if end > start:
-                job.feed(buf.ctypes.data + start, end - start)
-            res = sharded_tail(ctx, job, dist, torch, device, rank, world, len(inputs.cells), want_rows=True)
+        buf = np.memmap(bam_file, dtype=np.uint8, mode="r")   # the page cache is shared: no private copy, and a rank reads nothing but its own range
+        start, end = shard_bytes(buf, rank, world)
+        res = None
+        for umi_max_bytes in (3, 4):   # 10x UMIs are 10 or 12 bases; every rank retries together with room for 16
+            code, err = 0, None
+            job = None
+            try:
+                job = B.Bam2dbJob(ctx, inputs, rate_depth, seed, want_rows=True, umi_max_bytes=umi_max_bytes, headerless=(rank != 0))
+                piece = 256 << 20
+                for o in range(start, end, piece):
+                    chunk = np.ascontiguousarray(buf[o:min(end, o + piece)])
+                    job.feed(chunk.ctypes.data, chunk.size)
+                job.counts()
+            except _lib.FastfError as e:
+                err, code = e, (1 if "umi-too-long" in str(e) else 2)
+            worst = agree(dist, torch, device, code)   # nobody enters a collective unless everybody got this far
+            if worst == 0:
+                try:
+                    res = sharded_tail(ctx, job, dist, torch, device, rank, world, len(inputs.cells), want_rows=True)
+                finally:
+                    job.close()
+                break
+            if job is not None:
+                job.close()
+            if worst == 1 and umi_max_bytes == 3:
+                continue
+            raise err or _lib.FastfError("another rank failed (%s)" % ("UMI longer than 16 bases" if worst == 1 else "see its message"))
         rc = 0
         if rank == 0:
             stats, out = res

@@ -44,7 +44,7 @@ def test_keep_threshold_matches_reference_rule(lib, oracle):
     for r, T in table.items():
         assert lib.fastf_keep_threshold(C.c_float(r)) == T
     rng = np.random.default_rng(1)
-    for r in list(rng.random(40).astype(np.float32)) + [0.0, 1.0, 1.5, -0.5, 1e-9, 0.99999994]:
+    for r in list(rng.random(40).astype(np.float32)) + [0.0, 1.0, 1.5, -0.5, 1e-9, 0.99999994, float("nan"), float("inf"), -0.0]:   # NaN: `x >= NaN` is false, the reference drops nothing
         T = lib.fastf_keep_threshold(C.c_float(float(r)))
         for u in {0, 1, 0xFFFFFFFF, max(T - 1, 0), min(T, 0xFFFFFFFF), min(T + 1, 0xFFFFFFFF)}:
             assert oracle.depth_keep(u, float(r)) == (u < T), (r, u, T)
