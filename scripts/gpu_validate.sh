@@ -8,7 +8,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 ( time python -m pytest tests -m gpu -x -q ) > gpurun_out/${TAG}_pytest_gpu.log 2>&1; tail -4 gpurun_out/${TAG}_pytest_gpu.log
 ( time python bench.py ) > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -3 gpurun_out/${TAG}_bench.err; head -c 1500 gpurun_out/${TAG}_bench.json
 ( time python bench.py --impl reference --steps 1 --warmup 0 ) > gpurun_out/${TAG}_bench_reference_arm.json 2>> gpurun_out/${TAG}_bench.err
-bash scripts/gpu_parity_scale.sh $PREADS 1 | tail -14
+[ "$PREADS" -gt 0 ] && bash scripts/gpu_parity_scale.sh $PREADS 1 | tail -14
 CMD="python bench.py --reads 64000000 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-hw-extra --freq-reads 0 --check-reads 0"
 $CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1

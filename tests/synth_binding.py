@@ -40,7 +40,8 @@ class Synth:
         out, n, st = C.POINTER(C.c_uint8)(), C.c_size_t(), Stats()
         if fn(C.byref(p), threads, C.byref(out), C.byref(n), C.byref(st)):
             raise RuntimeError("synth failed")
-        data = C.string_at(out, n.value)
+        # images beyond 2 GiB: ctypes.string_at takes a C int
+        data = memoryview((C.c_char * n.value).from_address(C.addressof(out.contents))).tobytes() if n.value else b""
         self.lib.fastf_synth_free(out)
         return data, st
 
