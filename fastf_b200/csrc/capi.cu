@@ -178,6 +178,39 @@ static void pools_trim(fastf_ctx *ctx)
     ctx->pin_pool->clear();
 }
 
+// Large results go to pageable host memory the caller owns (malloc'ed result arrays).  A plain cudaMemcpy into pageable memory is
+// staged by the driver at a few GB/s; here the bytes cross PCIe into two pinned bounce buffers (from the context's pool) while
+// the host copies the previous piece out, so the transfer runs at memcpy speed.  Synchronous: dst is complete on return.
+static int d2h_pageable(fastf_ctx *ctx, void *dst, const void *src_dev, size_t bytes, cudaStream_t s)
+{
+    if (bytes == 0) return 0;
+    const size_t PIECE = (size_t)16 << 20;
+    if (bytes <= ((size_t)1 << 20)) {
+        CK(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return 0;
+    }
+    PinBuf bounce[2];
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int rc = 0;
+    for (int k = 0; k < 2 && !rc; k++) { rc = pin_reserve(ctx, bounce[k], PIECE); if (!rc && cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) rc = ctx_fail(ctx, "d2h: event creation failed"); }
+    const size_t n_pieces = (bytes + PIECE - 1) / PIECE;
+    for (size_t k = 0; k <= n_pieces && !rc; k++) {
+        if (k < n_pieces) {
+            const size_t o = k * PIECE, m = std::min(PIECE, bytes - o);
+            if (cudaMemcpyAsync(bounce[k & 1].p, (const u8 *)src_dev + o, m, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaEventRecord(ev[k & 1], s) != cudaSuccess) rc = ctx_fail(ctx, "d2h: copy failed");
+        }
+        if (k > 0 && !rc) {
+            const size_t o = (k - 1) * PIECE, m = std::min(PIECE, bytes - o);
+            if (cudaEventSynchronize(ev[(k - 1) & 1]) != cudaSuccess) rc = ctx_fail(ctx, "d2h: copy failed");
+            else memcpy((u8 *)dst + o, bounce[(k - 1) & 1].p, m);
+        }
+    }
+    cudaStreamSynchronize(s);
+    for (int k = 0; k < 2; k++) { if (ev[k]) cudaEventDestroy(ev[k]); pin_release(ctx, bounce[k]); }
+    return rc;
+}
+
 struct Timer {   // CUDA-event stopwatch on one stream; accumulates into *acc at collect()
     cudaEvent_t a = nullptr, b = nullptr;
     bool armed = false;
@@ -262,7 +295,8 @@ extern "C" void fastf_host_free(fastf_ctx *ctx, void *p) { (void)ctx; if (p) cud
 extern "C" int fastf_device_alloc(fastf_ctx *ctx, size_t bytes, void **out) { CK(cudaSetDevice(ctx->device)); CK(cudaMalloc(out, bytes ? bytes : 1)); return 0; }
 extern "C" void fastf_device_free(fastf_ctx *ctx, void *p) { (void)ctx; if (p) cudaFree(p); }
 extern "C" int fastf_memcpy_h2d(fastf_ctx *ctx, void *d, const void *s, size_t n) { CK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, ctx->compute)); CK(cudaStreamSynchronize(ctx->compute)); return 0; }
-extern "C" int fastf_memcpy_d2h(fastf_ctx *ctx, void *d, const void *s, size_t n) { CK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, ctx->compute)); CK(cudaStreamSynchronize(ctx->compute)); return 0; }
+static int d2h_pageable(fastf_ctx *ctx, void *dst, const void *src_dev, size_t bytes, cudaStream_t s);
+extern "C" int fastf_memcpy_d2h(fastf_ctx *ctx, void *d, const void *s, size_t n) { CK(cudaSetDevice(ctx->device)); return d2h_pageable(ctx, d, s, n, ctx->compute); }
 extern "C" int fastf_synchronize(fastf_ctx *ctx) { CK(cudaStreamSynchronize(ctx->copy)); CK(cudaStreamSynchronize(ctx->infl)); CK(cudaStreamSynchronize(ctx->mt)); CK(cudaStreamSynchronize(ctx->compute)); return 0; }
 extern "C" void fastf_free(void *p) { free(p); }
 extern "C" void fastf_ctx_trim(fastf_ctx *ctx) { if (ctx) { cudaSetDevice(ctx->device); cudaDeviceSynchronize(); pools_trim(ctx); } }
@@ -1394,9 +1428,9 @@ static int coo_to_host(fastf_ctx *ctx, RleScratch &R, u64 nnz, u32 **m_gene, u32
     *m_count = (u32 *)malloc(std::max<u64>(nnz, 1) * sizeof(u32));
     if (!*m_gene || !*m_cell || !*m_count) return ctx_fail(ctx, "out of host memory for %llu COO rows", (unsigned long long)nnz);
     if (nnz) {
-        CK(cudaMemcpyAsync(*m_gene, R.out_gene.p, nnz * sizeof(u32), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(*m_cell, R.out_cell.p, nnz * sizeof(u32), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(*m_count, R.count.p, nnz * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        TRY(d2h_pageable(ctx, *m_gene, R.out_gene.p, nnz * sizeof(u32), s));
+        TRY(d2h_pageable(ctx, *m_cell, R.out_cell.p, nnz * sizeof(u32), s));
+        TRY(d2h_pageable(ctx, *m_count, R.count.p, nnz * sizeof(u32), s));
         CK(cudaStreamSynchronize(s));
     }
     return 0;
@@ -1449,7 +1483,7 @@ extern "C" int fastf_bam2db_finish(fastf_bam2db_job *job, fastf_bam2db_result *r
     if (job->prm.want_rows) {
         res->row_keys = (u64 *)malloc(std::max<u64>(n, 1) * sizeof(u64));
         if (!res->row_keys) return ctx_fail(ctx, "out of host memory for %llu rows", (unsigned long long)n);
-        if (n) CK(cudaMemcpyAsync(res->row_keys, job->kept.p, n * sizeof(u64), cudaMemcpyDeviceToHost, ctx->compute));
+        if (n) TRY(d2h_pageable(ctx, res->row_keys, job->kept.p, n * sizeof(u64), ctx->compute));
         res->n_rows = n;
     }
     u64 nnz = 0;
@@ -1963,9 +1997,9 @@ static int freq_stream_finish(fastf_ctx *ctx, FreqStream &Q, fastf_freq_result *
         if (!res->key || !res->count || !res->first || !res->exc_ordinal || !res->exc_bytes) return ctx_fail(ctx, "freq: out of host memory");
         if (ngroups) {
             // with group_shift 0 every distinct key is a group and counts all its copies: count = next first - first
-            CK(cudaMemcpyAsync(res->key, R.grp_key.p, ngroups * sizeof(u64), cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(res->first, R.grp_val.p, ngroups * sizeof(u32), cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(res->count, R.grp_first.p, ngroups * sizeof(u32), cudaMemcpyDeviceToHost, s));
+            TRY(d2h_pageable(ctx, res->key, R.grp_key.p, ngroups * sizeof(u64), s));
+            TRY(d2h_pageable(ctx, res->first, R.grp_val.p, ngroups * sizeof(u32), s));
+            TRY(d2h_pageable(ctx, res->count, R.grp_first.p, ngroups * sizeof(u32), s));
         }
         if (n_exc) {
             CK(cudaMemcpyAsync(res->exc_ordinal, Q.exc_ord.p, (size_t)n_exc * sizeof(u32), cudaMemcpyDeviceToHost, s));

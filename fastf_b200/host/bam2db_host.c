@@ -48,6 +48,19 @@ static int exec_sql(sqlite3 *db, const char *sql)
     return 0;
 }
 
+/* FASTF_HOST_TIMING=1: wall clock of the host phases on stderr (where does a run spend its time next to the device job?) */
+#include <time.h>
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
+static double g_t_last = 0;
+static void phase(const char *what)
+{
+    static int on = -1;
+    if (on < 0) on = getenv("FASTF_HOST_TIMING") != NULL;
+    const double t = now_s();
+    if (on && g_t_last > 0) fprintf(stderr, "[host timing] %-34s %8.3f s\n", what, t - g_t_last);
+    g_t_last = t;
+}
+
 /* root page of a table (sqlite_master.rootpage); 0 when absent */
 static unsigned table_root(sqlite3 *db, const char *name)
 {
@@ -127,6 +140,8 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
         if ((e = getenv("FASTF_DEVICE")) != NULL) fastf_device = atoi(e);
     }
 
+    g_t_last = 0;
+    phase("start");
     if (sqlite3_open(db_file, &db)) { fprintf(stderr, "Can't open database: %s\n", sqlite3_errmsg(db)); goto done; }
     fprintf(stderr, "Opened database successfully\n");
     bam = open(bam_file, O_RDONLY);
@@ -209,6 +224,7 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
     /* ---- the hot path: device job fed with the raw BGZF bytes ---- */
     printf("Start to convert bam file to sqlite3 database...\n");
     fflush(stdout);
+    phase("lists + small tables");
     if (fastf_gpus > 1) {
         /* several GPUs of this node: contiguous block shards, global draw ordinals, NCCL all-to-all by cell (csrc/sharded.cu) */
         struct stat sb;
@@ -276,6 +292,7 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
     }
     }
 
+    phase("device job (ctx, read, feed, finish)");
     /* ---- tables umi (read order, reference :351-435), mtx (:480-483) and numi (:527-530) ----
      * sqlite creates the empty tables; the rows are then laid out directly as b-tree pages (sqlite_bulk.c): at 10^8 rows a
      * sqlite3_step() per row costs minutes behind a device job of seconds. */
@@ -293,6 +310,7 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
         fastf_sqlite_bulk_rows_parallel(bulk, res.n_rows, umi_row_enc, &R);
         if (fastf_sqlite_bulk_end(bulk)) { fprintf(stderr, "SQL error: writing table umi of %s failed\n", db_file); goto done; }
     }
+    phase("table umi (direct b-tree)");
     printf("In %s, total fastQ reads: %zu\n", bam_file, (size_t)res.total);
     printf("In %s, sampled fastQ reads: %zu\n", bam_file, (size_t)res.sampled);
     printf("In %s, sampled and valid fastQ reads: %zu\n", bam_file, (size_t)res.valid);
@@ -325,6 +343,7 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
         fastf_textbuf_free(&tb);
         if (wrc) { fprintf(stderr, "\x1b[31mError:\x1b[0m can not open file %s\n", path); goto done; }
     }
+    phase("table mtx + matrix.mtx.gz");
     printf("matrix.mtx.gz is generated.\n");
     for (uint32_t i = 0; i < cells.n; i++) { gzwrite(file_barcode, cells.buf + cells.off[i], cells.off[i + 1] - cells.off[i]); gzputc(file_barcode, '\n'); }
     printf("barcodes.tsv.gz is generated.\n");
@@ -378,6 +397,7 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
         if (wrc) { fprintf(stderr, "\x1b[31mError:\x1b[0m can not open file %s\n", path); goto done; }
         printf("umi.tsv.gz is generated.\n");
     }
+    phase("barcodes / features (/ umi.tsv) gz");
     rc = 0;
 done:
     if (stmt) sqlite3_finalize(stmt);

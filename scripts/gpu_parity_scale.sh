@@ -12,7 +12,7 @@ echo "== parity at scale: $READS distinct reads, $GPUS GPU(s), $(nproc) host cor
 T0=$(date +%s%N); fastf_b200/_build/fastf_synth bam --out $D --reads $READS --cells 10000 --genes 36000 --seed 4242 2>&1 | tail -2; echo "generate: $(( ($(date +%s%N) - T0) / 1000000 )) ms"
 ls -l $D/synth.bam | awk '{print "BAM bytes:", $5}'
 T0=$(date +%s%N); oracle/_ref/fastF_ref bam2db -b $D/synth.bam -f $D/features.tsv.gz -a $D/barcodes.tsv.gz -d $D/ref/x.db -c 1.0 -r 0.3 -o $D/ref -s 926 2>&1 | grep -v "^Opened\|generated" | tail -6; echo "reference CLI: $(( ($(date +%s%N) - T0) / 1000000 )) ms wall"
-T0=$(date +%s%N); FASTF_GPUS=$GPUS fastf_b200/_build/fastF bam2db -b $D/synth.bam -f $D/features.tsv.gz -a $D/barcodes.tsv.gz -d $D/ours/x.db -c 1.0 -r 0.3 -o $D/ours -s 926 2>&1 | grep -v "^Opened\|generated" | tail -6; echo "fastF (B200) CLI: $(( ($(date +%s%N) - T0) / 1000000 )) ms wall"
+T0=$(date +%s%N); FASTF_HOST_TIMING=1 FASTF_GPUS=$GPUS fastf_b200/_build/fastF bam2db -b $D/synth.bam -f $D/features.tsv.gz -a $D/barcodes.tsv.gz -d $D/ours/x.db -c 1.0 -r 0.3 -o $D/ours -s 926 2>&1 | grep -v "^Opened\|generated" | tail -12; echo "fastF (B200) CLI: $(( ($(date +%s%N) - T0) / 1000000 )) ms wall"
 python - $D <<'PY'
 import gzip, hashlib, sqlite3, sys, time
 sys.path.insert(0, "tests")
