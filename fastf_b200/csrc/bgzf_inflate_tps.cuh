@@ -78,6 +78,9 @@
 #ifndef FASTF_TPS_FAR_LEN
 #define FASTF_TPS_FAR_LEN 32u         // longest match handled in the far group (32 or 64: one or two bytes per lane)
 #endif
+#ifndef FASTF_TPS_SLOW_UNROLL
+#define FASTF_TPS_SLOW_UNROLL 0      // long non-overlapping matches: four pieces' loads in flight
+#endif
 #ifndef FASTF_TPS_WAVES
 #define FASTF_TPS_WAVES 0            // service copy in waves of independent matches (long far matches as pieces, near matches grouped)
 #endif
@@ -546,10 +549,22 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
         __syncwarp();   // everything stored so far in this batch is ordered before these loads
         const u8 *src = out + dst - dist;
         if (dist >= len) {
+#if FASTF_TPS_SLOW_UNROLL
+            // the source does not overlap the destination: the loads of four 32-byte pieces are issued before any store (a long match
+            // costs one round trip, not one per piece -- matches longer than 32 bytes hold a quarter of the output of BAM data)
+            for (u32 k = 0; k < len; k += 128) {
+                u32 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const u32 j = k + 32u * (u32)u + lane; v[u] = j < len ? src[j] : 0u; }
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const u32 j = k + 32u * (u32)u + lane; if (j < len) out[dst + j] = (u8)v[u]; }
+            }
+#else
             for (u32 k = 0; k < len; k += 32) {
                 const u32 j = k + lane;
                 if (j < len) out[dst + j] = src[j];
             }
+#endif
         } else {
             // overlapping copy: the pattern src[0..dist) repeats; j % dist by a reciprocal multiply (exact for j < 258)
             const u32 rcp = (u32)(1048576.0f * __frcp_rn((float)dist)) + 2u;

@@ -40,7 +40,7 @@ for cmd in (["nvidia-smi", "topo", "-m"], ["bash", "-c", "lspci -tv 2>/dev/null 
 for k in (1, 2, 4, 8):
     if k > ng:
         break
-    start = time.time() + 25.0   # process start-up + pinning 1 GiB takes seconds
+    start = time.time() + 14.0   # process start-up + pinning 1 GiB takes seconds
     ps = [subprocess.Popen([sys.executable, __file__, "--child", str(g), str(start)], stdout=subprocess.PIPE, text=True) for g in range(k)]
     outs = [p.communicate()[0].strip() for p in ps]
     rates = [float(o.split(":")[1].split()[0]) for o in outs if "GB/s" in o]
