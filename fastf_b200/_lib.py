@@ -116,15 +116,35 @@ def load():
     path = library_path()
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: run `python -m fastf_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
-    lib = C.CDLL(path)
-    for name, (res, args) in _SIGS.items():
-        fn = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
-        fn.restype = res
-        fn.argtypes = args
-    # a prebuilt binary that does not match the sources next to it is an error, not a surprise (variant builds opt out)
-    info = dict(kv.split("=", 1) for kv in lib.fastf_build_info().decode().split())
+
+    def bind(p):
+        lib = C.CDLL(p)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        return lib, dict(kv.split("=", 1) for kv in lib.fastf_build_info().decode().split())
+
+    lib, info = bind(path)
+    # A prebuilt binary that does not match the sources next to it is rebuilt (one rank at a time) or refused -- never used silently.
+    # Variant builds named by FASTF_GPU_LIB opt out.
     if not os.environ.get("FASTF_GPU_LIB") and info.get("src") not in ("unknown", _build.source_hash()):
-        raise RuntimeError(f"{path} was built from other sources (src={info.get('src')}, tree={_build.source_hash()}): run `python -m fastf_b200.build`")
+        import fcntl
+        os.makedirs(_build.BUILD, exist_ok=True)
+        with open(os.path.join(_build.BUILD, ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                # another rank may have rebuilt it while we waited; dlopen caches by path, so the fresh file is loaded under a new name
+                fresh = os.path.join(_build.BUILD, "libfastf_gpu.%s.so" % _build.source_hash())
+                if not os.path.exists(fresh):
+                    _build.build_cuda(force=True)
+                    import shutil
+                    shutil.copyfile(path, fresh)
+                lib, info = bind(fresh)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
+        if info.get("src") != _build.source_hash():
+            raise RuntimeError(f"{path} was built from other sources (src={info.get('src')}, tree={_build.source_hash()}) and could not be rebuilt: run `python -m fastf_b200.build`")
     _lib = lib
     return lib
 

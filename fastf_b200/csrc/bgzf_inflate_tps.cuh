@@ -58,7 +58,20 @@
 #ifndef FASTF_TPS_MAX_SVC
 #define FASTF_TPS_MAX_SVC FASTF_TPS_SVC_WARPS
 #endif
+// Second-level tables (FASTF_TPS_SUBTABLES): a code longer than the primary table is resolved by ONE more look-up instead of the
+// canonical walk (~45 instructions that every lane of the warp sits through whenever one lane meets such a code -- with 32 streams
+// per warp that is nearly every round).  The primary entry of a long prefix names a sub-table (offset / 8, index bits); sub-tables
+// live in the stream's global scratch (L2) next to the sorted symbol lists.  A code whose sub-tables would not fit keeps the walk.
+#ifndef FASTF_TPS_SUBTABLES
+#define FASTF_TPS_SUBTABLES 1
+#endif
+#define FASTF_TPS_LITSUB_U16 1016u   // capacity of the literal/length sub-tables (7-bit offset field x 8)
+#define FASTF_TPS_DISTSUB_U16 512u
+#if FASTF_TPS_SUBTABLES
+#define FASTF_TPS_SORTED_U16 (320 + 1024 + 512)   // per stream in GLOBAL scratch: sorted symbols (288 lit/len + 32 dist), then the two sub-table areas
+#else
 #define FASTF_TPS_SORTED_U16 320   // per stream in GLOBAL scratch: symbols sorted by code length (288 lit/len + 32 dist), read only for codes longer than the tables
+#endif
 #define FASTF_TPS_THREADS FASTF_TPS_THREADS_OF(FASTF_TPS_LANES, FASTF_TPS_SVC_WARPS)
 #ifndef FASTF_TPS_RING
 #define FASTF_TPS_RING 32u
@@ -145,7 +158,7 @@ struct FastfTpsStream {
 #endif
 struct FastfTpsSvc {
     union {
-        struct { u8 lens[320]; u16 scratch[32]; } setup;   // code lengths of the block being set up; first[16], start[16] while building
+        struct { u8 lens[320]; u16 scratch[32]; u8 submax[256]; } setup;   // code lengths of the block being set up; first[16], start[16] while building; longest code per table prefix
 #if FASTF_TPS_STAGED
         alignas(16) u8 sb[FASTF_TPS_SB + 8];
 #endif
@@ -214,7 +227,8 @@ __device__ __forceinline__ u32 fastf_make16(u32 alpha, u32 sym)
 
 // Cooperative (32 lanes, lock step) construction of one 16-bit decode table.  Returns non-zero for an invalid code.
 // *walk = (first canonical code of length tbits+1) << 16 | (index of its first symbol in sorted[]).
-__device__ __forceinline__ u32 fastf_tps_build(u32 alpha, const u8 *lens, u32 n, u16 *cnt, u16 *sorted, u16 *lut, u32 tbits, u16 *first, u16 *start, u32 *walk, u32 lane)
+__device__ __forceinline__ u32 fastf_tps_build(u32 alpha, const u8 *lens, u32 n, u16 *cnt, u16 *sorted, u16 *lut, u32 tbits, u16 *first, u16 *start, u32 *walk, u32 lane,
+                                               u16 *sub = nullptr, u32 sub_cap = 0, u8 *submax = nullptr)
 {
     for (u32 i = lane; i < (1u << tbits); i += 32) lut[i] = FASTF_T16_LONG;
     u32 bad = 0, wk = 0;
@@ -276,10 +290,61 @@ __device__ __forceinline__ u32 fastf_tps_build(u32 alpha, const u8 *lens, u32 n,
             for (u32 j = rev; j < (1u << tbits); j += (1u << l)) lut[j] = e;
         }
     }
+    const u32 long_from = start[tbits + 1];   // read before the barrier: lane 0 of the NEXT build overwrites the scratch as soon as it gets there
     __syncwarp();
+#if FASTF_TPS_SUBTABLES
+    if (sub && used && long_from < used) {
+        // (1) per table index j (the code's first tbits bits, in stream order): the longest code that starts with them.  The canonical
+        // codes of length l are [first[l], first[l] + cnt[l]); the ones with the (MSB-first) prefix q are q << (l - tbits) ... .
+        const u32 nidx = 1u << tbits;
+        for (u32 j = lane; j < nidx; j += 32) {
+            const u32 q = __brev(j) >> (32 - tbits);
+            u32 mx = 0;
+            for (u32 l = tbits + 1; l <= 15; l++) {
+                const u32 c = (l < 15 ? (u32)start[l + 1] : used) - (u32)start[l];
+                const u32 lo = q << (l - tbits), hi = (q + 1u) << (l - tbits);
+                if (c && (u32)first[l] < hi && (u32)first[l] + c > lo) mx = l;
+            }
+            submax[j] = (u8)(mx ? mx - tbits : 0u);
+        }
+        __syncwarp();
+        // (2) sub-table offsets: sizes 2^bits padded to 8 entries, exclusive prefix sum over the indices (lane k owns a contiguous run)
+        const u32 per = (nidx + 31u) / 32u, j0 = lane * per;
+        u32 mine = 0;
+        for (u32 j = j0; j < j0 + per && j < nidx; j++) { const u32 b = submax[j]; mine += b ? (b < 3u ? 8u : (1u << b)) : 0u; }
+        u32 inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(FASTF_FULL_MASK, inc, o); if ((int)lane >= o) inc += t; }
+        const u32 total = __shfl_sync(FASTF_FULL_MASK, inc, 31);
+        if (total <= sub_cap) {
+            u32 at = inc - mine;
+            for (u32 j = j0; j < j0 + per && j < nidx; j++) {
+                const u32 b = submax[j];
+                if (b) { lut[j] = (u16)(FASTF_T16_LONG | (b << 6) | ((at >> 3) << 9)); at += b < 3u ? 8u : (1u << b); }
+            }
+            __syncwarp();
+            // (3) every long code fills its slots of its prefix's sub-table
+            for (u32 i = long_from + lane; i < used; i += 32) {
+                const u32 sym = fastf_ld_sorted(sorted + i);
+                const u32 l = lens[sym];
+                const u32 code = (u32)first[l] + (i - (u32)start[l]);
+                const u32 rev = __brev(code) >> (32 - l);
+                const u32 pe = lut[rev & (nidx - 1u)];
+                const u32 b = (pe >> 6) & 7u, at = (pe >> 9) << 3;
+                const u16 e = (u16)(fastf_make16(alpha, sym) | l);
+                for (u32 k = rev >> tbits; k < (1u << b); k += 1u << (l - tbits)) sub[at + k] = e;
+            }
+        }
+        __syncwarp();
+    }
+#endif
     *walk = wk;
     return 0;
 }
+
+// entry of a code longer than the primary table: through its sub-table when the primary entry names one, else by the canonical walk
+template <int TBITS>
+__device__ __forceinline__ u32 fastf_tps_long(u32 e, u64 buf, const u16 *lb, const u16 *sorted, const u16 *sub, u32 alpha);
 
 // lock-step lookup used by the service warp while it reads the code-length code (7-bit table in the literal table's storage;
 // code-length codes are at most 7 bits long, so every valid one is resolved by the table)
@@ -388,8 +453,13 @@ __device__ __forceinline__ void fastf_tps_setup(const FastfTpsArgs &A, FastfTpsS
         }
         u32 wl, wd;
         // the distance lengths sit behind the literal/length ones in `lens`; the literal table's storage was the code-length table
+#if FASTF_TPS_SUBTABLES
+        if (fastf_tps_build(FASTF_ALPHA_LITLEN, lens, hlit, S.lit_cnt, lit_sorted, S.lit, FASTF_TPS_LBITS, first, start, &wl, lane, lit_sorted + 320, FASTF_TPS_LITSUB_U16, G.svc[sw].setup.submax)) { err |= FASTF_ST_BAD_CODELENS; break; }
+        if (fastf_tps_build(FASTF_ALPHA_DIST, lens + hlit, hdist, S.dist_cnt, dist_sorted, S.dist, FASTF_TPS_DBITS, first, start, &wd, lane, lit_sorted + 320 + 1024, FASTF_TPS_DISTSUB_U16, G.svc[sw].setup.submax)) { err |= FASTF_ST_BAD_CODELENS; break; }
+#else
         if (fastf_tps_build(FASTF_ALPHA_LITLEN, lens, hlit, S.lit_cnt, lit_sorted, S.lit, FASTF_TPS_LBITS, first, start, &wl, lane)) { err |= FASTF_ST_BAD_CODELENS; break; }
         if (fastf_tps_build(FASTF_ALPHA_DIST, lens + hlit, hdist, S.dist_cnt, dist_sorted, S.dist, FASTF_TPS_DBITS, first, start, &wd, lane)) { err |= FASTF_ST_BAD_CODELENS; break; }
+#endif
         const u64 consumed = (u64)br.widx * 32u - br.nbits - br.skip_bits;
         bitpos = origin + consumed;
         if (lane == 0) {
@@ -834,6 +904,16 @@ __device__ __forceinline__ u32 fastf_tps_walk(u64 buf, const u16 *lb, const u16 
     return fastf_make16(alpha, fastf_ld_sorted(sorted + idx)) | len;
 }
 
+template <int TBITS>
+__device__ __forceinline__ u32 fastf_tps_long(u32 e, u64 buf, const u16 *lb, const u16 *sorted, const u16 *sub, u32 alpha)
+{
+#if FASTF_TPS_SUBTABLES
+    const u32 b = (e >> 6) & 7u;
+    if (b) return fastf_ld_sorted(sub + ((e >> 9) << 3) + ((u32)(buf >> TBITS) & ((1u << b) - 1u)));
+#endif
+    return fastf_tps_walk<TBITS>(buf, lb, sorted, alpha);
+}
+
 template <int L, int SVC>
 __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_inflate_tps_kernel(FastfTpsArgs A)
 {
@@ -893,7 +973,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
             // Bit budget: a refill leaves >= 33 bits; 15 + 9 + 9 for the first triple, 27 for the second, 9 + 5 for a length.
             br.refill();
             u32 e = S.lit[(u32)br.buf & ((1u << FASTF_TPS_LBITS) - 1u)];
-            if ((e & 15u) == 0) e = fastf_tps_walk<FASTF_TPS_LBITS>(br.buf, S.lit_cnt, lit_sorted, FASTF_ALPHA_LITLEN);
+            if ((e & 15u) == 0) e = fastf_tps_long<FASTF_TPS_LBITS>(e, br.buf, S.lit_cnt, lit_sorted, lit_sorted + 320, FASTF_ALPHA_LITLEN);
             u32 kind = (e >> 4) & 3u;
             u32 err = 0;
             const u32 wr0 = wr;
@@ -970,7 +1050,7 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
                 const u32 len = (K >> 8) + br.take(K & 255u);
                 br.refill();
                 u32 d = S.dist[(u32)br.buf & ((1u << FASTF_TPS_DBITS) - 1u)];
-                if ((d & 15u) == 0) d = fastf_tps_walk<FASTF_TPS_DBITS>(br.buf, S.dist_cnt, dist_sorted, FASTF_ALPHA_DIST);
+                if ((d & 15u) == 0) d = fastf_tps_long<FASTF_TPS_DBITS>(d, br.buf, S.dist_cnt, dist_sorted, lit_sorted + 320 + 1024, FASTF_ALPHA_DIST);
                 if (((d >> 4) & 3u) != FASTF_T16_SYM) err = FASTF_ST_BAD_SYMBOL;
                 else {
                     br.drop(d & 15u);
