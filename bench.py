@@ -6,10 +6,12 @@ reference's CPU path timed beside it.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (BASELINE.json configs[2]): synthetic 10x-v3 BAM, 10k cells, 36k genes, `-c 1.0 -r 0.3 -s 926`, R reads per GPU
-(default 500M).  The BAM is a zlib-6 BGZF image of B reads (default 8M, ~1.2 GB compressed / 3.3 GB inflated, generated on
-the host cores at start-up) whose record blocks are streamed T = ceil(R/B) times through the same job; the MT19937 draw
-ordinal keeps running across tiles, so every tile keeps a different 30 % of its reads.  One step = one whole job
-(begin -> feed all tiles -> sample -> sort -> dedup/count -> COO on the host).
+(default 500M).  The BAM is a zlib-6 BGZF image of B DISTINCT reads per rank (--base-reads; default 0 = as many as the host
+cores of this rank generate in ~90 s, between 8 M and 64 M: 64 M reads = 9.6 GB compressed / 26 GB inflated; data seed
+DATA_SEED + rank) whose record blocks are cycled T = ceil(R/B) times through the same job -- 5e8 distinct reads would take
+~12 min of host zlib time per GPU.  The MT19937 draw ordinal keeps running across cycles, so every cycle keeps a different
+30 % of its reads.  One step = one whole job (begin -> feed all cycles -> sample -> sort -> dedup/count -> COO on the host).
+Before timing, the job's counters and COO of a bounded prefix (--check-reads) are compared with the oracle's.
 
   value : reads/s with the compressed bytes + block index already resident in HBM (fastf_bam2db_feed_device)
   e2e   : the same job fed from pinned HOST memory through fastf_bam2db_feed (H2D of every compressed byte inside the timed
@@ -37,6 +39,16 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N_CELLS, N_GENES, RATE_CELL, RATE_DEPTH, SEED, DATA_SEED = 10000, 36000, 1.0, 0.3, 926, 11
+# DRAM bytes of ONE launch of the inflate kernel on a full chunk of 2 x 148 x 224 BGZF blocks (ncu --set full, not a bench run)
+INFLATE_TRAFFIC = (26.606e9 + 4.572e9, "profiles/r02_ncu_inflate_crc_parse.txt (26.606 GB read + 4.572 GB written per launch over one 66304-block chunk, 4.31 GB inflated: "
+                   "the LZ77 windows of 33152 concurrent streams (1 GB) do not fit the 126 MB L2, so most match sources are 32-byte sector reads from DRAM)")
+
+
+def inflate_kernel_name():
+    """Name of the instantiation the library launches, from its build record (streams / decoder lanes / service warps)."""
+    from fastf_b200 import _lib
+    info = _lib.build_info()
+    return "fastf_bgzf_inflate_tps_kernel<%s,%s> (%s streams per SM)" % (info.get("lanes", "?"), info.get("svc", "?"), info.get("streams", "?"))
 
 
 def log(*a):
@@ -546,10 +558,10 @@ def main():
                            "l2": "inputs larger than L2 (compressed segment >> 126 MB); no explicit flush", "timing": "CUDA events on the library's launching stream around the K timed jobs, barrier + synchronize on both sides; max over ranks",
                            "ms_per_step_wall": ms_step_wall, "ms_per_job_library_clock": ms_job_dev, "counters": {k: st.get(k) for k in ("total", "cb_valid", "sampled", "valid", "nnz", "n_blocks", "n_chunks", "exchanged_keys")},
                            "parallelism": ("single GPU" if world == 1 else f"{world} ranks: contiguous BGZF block shards, all-gather of counts, NCCL all-to-all of locally deduplicated keys by cell hash, gather of COO")},
-                "roofline": {"bound": "hbm", "kernel": "hardware decompression engine" if args.engine == "hw" else ("fastf_bgzf_inflate_tps_kernel<16,24>" if args.lanes == 0 else "inflate (--lanes %d)" % args.lanes),
+                "roofline": {"bound": "hbm", "kernel": "hardware decompression engine" if args.engine == "hw" else (inflate_kernel_name() if args.lanes == 0 else "inflate (--lanes %d)" % args.lanes),
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on a full chunk of 37888 blocks (ncu --set full, profiles/r01_v9_ncu_inflate_tps.txt)
-                             "traffic": 13.780e9 if (args.engine == "sm" and args.lanes == 0 and chunk == 0) else None, "traffic_source": "profiles/r01_v9_ncu_inflate_tps.txt (11.257 GB read + 2.523 GB written per launch over one 37888-block chunk, 2.46 GB inflated)",
+                             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on a full chunk (ncu --set full)
+                             "traffic": INFLATE_TRAFFIC[0] if (args.engine == "sm" and args.lanes == 0 and chunk == 0) else None, "traffic_source": INFLATE_TRAFFIC[1],
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_launch, "ms_per_launch": infl_ms_launch},
                 "stages": stages, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "inflate_engine": args.engine, "hw_decompress_engine": hw_extra}
         if sweep is not None:
@@ -751,7 +763,7 @@ def bench_tags(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{args.workload} ({TAGS_CMD[args.workload]}) on the synthetic 10x-v3 BAM: {n_reads} reads, {N_CELLS} cells, {N_GENES} genes (SURVEY 8f)",
                        "l2": "inputs larger than L2", "counters": {k: st[k] for k in ("n_records", "n_hits", "n_groups", "n_blocks", "hash_rounds")}},
-            "roofline": {"bound": "hbm", "kernel": "fastf_bgzf_inflate_tps_kernel<16,24>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": inflate_kernel_name(), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg, "ms_per_launch": st["ms_inflate"]},
             "stages": {k: {"ms": round(st["ms_" + k], 3)} for k in ("inflate", "tags", "sort", "rle")}, "gpu_launches": launches, "clocks": clocks,
             "e2e": {"value": n_reads / (wall / args.steps), "unit": "reads/s", "h2d_bytes_per_step": int(bam.size), "d2h_bytes_per_step": int(st["n_groups"] * 40 + st["strings_bytes"]),

@@ -92,10 +92,7 @@
 #define FASTF_TPS_FAR_LEN 32u         // longest match handled in the far group (32 or 64: one or two bytes per lane)
 #endif
 #ifndef FASTF_TPS_SLOW_UNROLL
-#define FASTF_TPS_SLOW_UNROLL 0      // long non-overlapping matches: four pieces' loads in flight
-#endif
-#ifndef FASTF_TPS_WAVES
-#define FASTF_TPS_WAVES 0            // service copy in waves of independent matches (long far matches as pieces, near matches grouped)
+#define FASTF_TPS_SLOW_UNROLL 1      // long non-overlapping matches: four pieces' loads in flight (+1 %)
 #endif
 #ifndef FASTF_TPS_FAR
 #define FASTF_TPS_FAR 4              // far matches whose source loads are in flight together
@@ -134,7 +131,7 @@ struct FastfTpsStream {
     alignas(8) u16 dist_cnt[FASTF_TPS_WALK_U16(FASTF_TPS_DBITS)];
     u32 ring[FASTF_TPS_RING];
     // control block (volatile accesses; every hand-over is fenced)
-    u32 state, wr, rd, last;
+    u32 state, wr, rd, last;         // state, wr, rd: polled as ctl[0..2] by the service warps
     u32 bitpos_lo, bitpos_hi;        // absolute bit offset of the next unread bit inside `comp`
     u32 pos, isize;                  // decoder's output position / block size
     u32 spare0, spare1;
@@ -146,26 +143,9 @@ struct FastfTpsStream {
 #endif
 };
 
-// Staged LZ77 (FASTF_TPS_STAGED): a service warp assembles the output of a token batch in shared memory -- literals, then the
-// matches whose source lies before the batch (global memory, all loads of a group in flight together), then in token order the
-// ones that read the batch's own bytes (shared memory latency instead of an L2 round trip each) -- and writes it out as whole
-// aligned words.  The staging area doubles as the scratch of stream set-up (a warp does one or the other).
-#ifndef FASTF_TPS_STAGED
-#define FASTF_TPS_STAGED 0
-#endif
-#ifndef FASTF_TPS_SB
-#define FASTF_TPS_SB 768u             // staging bytes per service warp (>= 3 + 258: one token always fits)
-#endif
+// scratch of one service warp while it sets a stream up
 struct FastfTpsSvc {
-    union {
-        struct { u8 lens[320]; u16 scratch[32]; u8 submax[256]; } setup;   // code lengths of the block being set up; first[16], start[16] while building; longest code per table prefix
-#if FASTF_TPS_STAGED
-        alignas(16) u8 sb[FASTF_TPS_SB + 8];
-#endif
-    };
-#if FASTF_TPS_STAGED
-    alignas(8) u32 farlist[32][2];   // (token, offset in the batch) of the short far matches, compacted
-#endif
+    struct { u8 lens[320]; u16 scratch[32]; u8 submax[256]; } setup;   // code lengths of the block being set up; first[16], start[16] while building; longest code per table prefix
 };
 struct FastfTpsShared {
     u32 lenK[32], distK[32];         // base << 8 | extra bits
@@ -181,6 +161,40 @@ struct FastfTpsShared {
 #define FASTF_SMEM_ORDER() ((void)0)
 #else
 #define FASTF_SMEM_ORDER() __asm__ __volatile__("" ::: "memory")
+#endif
+// FASTF_TPS_PROF: where the lane-rounds of the decoders and the cycles of the service warps go (debug builds only; read with
+// fastf_debug_tps_prof).  [0] decoder lane-rounds decoded, [1] skipped with a full ring, [2] skipped waiting for set-up,
+// [3] service passes, [4] passes without work, [5] cycles in copies, [6] cycles in set-up, [7] cycles in passes without work,
+// [8] batches, [9] tokens, [10] total service cycles
+#ifndef FASTF_TPS_PROF
+#define FASTF_TPS_PROF 0
+#endif
+#if FASTF_TPS_PROF
+__device__ unsigned long long g_fastf_tps_prof[16];
+#define FASTF_PROF(x) x
+#else
+#define FASTF_PROF(x)
+#endif
+// control-block words polled in a loop: a 32-bit shared-memory address the compiler cannot re-derive (it would rebuild it from the
+// thread index in every pass), read with volatile shared loads
+#ifdef FASTF_EMU
+typedef const u32 *fastf_ctl_ptr;
+static inline fastf_ctl_ptr fastf_ctl_of(const u32 *p) { return p; }
+static inline u32 fastf_ctl_ld(fastf_ctl_ptr p, u32 word) { return *(const volatile u32 *)(p + word); }
+#else
+typedef u32 fastf_ctl_ptr;
+__device__ __forceinline__ fastf_ctl_ptr fastf_ctl_of(const u32 *p)
+{
+    u32 a = (u32)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ u32 fastf_ctl_ld(fastf_ctl_ptr a, u32 word)
+{
+    u32 v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a + 4u * word) : "memory");
+    return v;
+}
 #endif
 // the sorted-symbol lists live in global memory, are rewritten for every deflate block by a service warp and read by another warp
 // of the same CTA: read them through L2 (ld.cg), never through a possibly stale L1 line
@@ -515,65 +529,6 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
     // one at a time in token order behind a __syncwarp.  A far match never reads what a later-handled one writes, and the
     // bytes a slow match reads lie before its own position, so handling the far ones first preserves the result.
     // (Synthetic 10x BAM: a batch of 32 tokens holds ~10 matches of 12 bytes on average, 9 % longer than 32, 14 % closer than 200.)
-#if FASTF_TPS_WAVES
-    // Waves of independent copies (FASTF_TPS_WAVES): a set of non-overlapping matches (dist >= len) whose sources are final is cut into
-    // pieces of <= 32 bytes; the source loads of FASTF_TPS_FAR pieces are in flight together, then stored.  Wave 0 = every match
-    // whose source lies before the batch, whatever its length (a 64-byte match is two pieces, not a trip of its own).  The rest is
-    // taken in token order: all remaining non-overlapping matches whose source ends at or before the destination of the FIRST
-    // remaining one read only bytes that are already stored -- one wave, one round trip; a match that overlaps itself goes alone.
-    const u32 mlen = tok & 511u, mdist = (tok >> 9) & 0xffffu;
-    u32 wavem = __ballot_sync(FASTF_FULL_MASK, is_match && off + mlen <= mdist);
-    u32 restm = __ballot_sync(FASTF_FULL_MASK, is_match && !(off + mlen <= mdist));
-    if (FASTF_TPS_NOCOPY) wavem = restm = 0;
-    __syncwarp();
-    for (;;) {
-        u32 c_o = 0, c_len = 0, c_dist = 0, c_k = 0;   // the match being cut into pieces (warp-uniform)
-        while (wavem || c_k < c_len) {
-            u32 dpos[FASTF_TPS_FAR], dlen[FASTF_TPS_FAR], dbyte[FASTF_TPS_FAR];
-#pragma unroll
-            for (int u = 0; u < FASTF_TPS_FAR; u++) {
-                dlen[u] = 0; dpos[u] = 0; dbyte[u] = 0;
-                if (c_k >= c_len && wavem) {
-                    const u32 m = (u32)__ffs((int)wavem) - 1u;
-                    wavem &= wavem - 1u;
-                    const u32 t = __shfl_sync(FASTF_FULL_MASK, tok, (int)m);
-                    c_o = __shfl_sync(FASTF_FULL_MASK, off, (int)m);
-                    c_len = t & 511u; c_dist = (t >> 9) & 0xffffu; c_k = 0;
-                }
-                if (c_k < c_len) {
-                    dpos[u] = opos + c_o + c_k;
-                    dlen[u] = c_len - c_k < 32u ? c_len - c_k : 32u;
-                    if (lane < dlen[u]) dbyte[u] = out[dpos[u] - c_dist + lane];
-                    c_k += 32u;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < FASTF_TPS_FAR; u++)
-                if (lane < dlen[u]) out[dpos[u] + lane] = (u8)dbyte[u];
-        }
-        if (!restm) break;
-        const u32 m0 = (u32)__ffs((int)restm) - 1u;
-        const u32 d0 = __shfl_sync(FASTF_FULL_MASK, off, (int)m0);
-        wavem = __ballot_sync(FASTF_FULL_MASK, ((restm >> lane) & 1u) && mdist >= mlen && off + mlen <= mdist + d0);
-        __syncwarp();   // everything stored so far in this batch is ordered before the next loads
-        if (wavem) { restm &= ~wavem; continue; }
-        // the first remaining match overlaps itself: the pattern src[0..dist) repeats; j % dist by a reciprocal multiply (exact for j < 258)
-        restm &= restm - 1u;
-        const u32 t = __shfl_sync(FASTF_FULL_MASK, tok, (int)m0);
-        const u32 len = t & 511u, dist = (t >> 9) & 0xffffu, dst = opos + d0;
-        const u8 *src = out + dst - dist;
-        const u32 rcp = (u32)(1048576.0f * __frcp_rn((float)dist)) + 2u;
-        for (u32 k = 0; k < len; k += 32) {
-            const u32 j = k + lane;
-            if (j < len) {
-                const u32 q = (j * rcp) >> 20;
-                u32 r = j - q * dist;
-                if (r >= dist) r += dist;   // q overshoots by at most one
-                out[dst + j] = src[r];
-            }
-        }
-    }
-#else
     u32 farm, slowm;
     {
         const u32 len = tok & 511u, dist = (tok >> 9) & 0xffffu;
@@ -649,7 +604,6 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
             }
         }
     }
-#endif
     u32 consumed = ntok;
     u32 new_opos = opos + total;
     if (endm) {
@@ -668,162 +622,6 @@ __device__ __forceinline__ u32 fastf_tps_copy(const FastfTpsArgs &A, FastfTpsStr
     return consumed;
 }
 
-#if FASTF_TPS_STAGED
-// four bytes from an arbitrary address (two aligned words and a funnel shift; the bytes around the range are read and ignored)
-__device__ __forceinline__ u32 fastf_ld4_unaligned(const u8 *p)
-{
-    const u32 al = (u32)(uintptr_t)p & 3u;
-    const u32 *w = reinterpret_cast<const u32 *>(p - al);
-    const u32 w0 = w[0], w1 = w[1];
-#ifdef FASTF_EMU
-    return al ? (w0 >> (8u * al)) | (w1 << (32u - 8u * al)) : w0;
-#else
-    return __funnelshift_r(w0, w1, 8u * al);
-#endif
-}
-__device__ __forceinline__ void fastf_sts_bytes(u8 *d, u32 v, u32 nb)
-{
-    if (nb > 0u) d[0] = (u8)v;
-    if (nb > 1u) d[1] = (u8)(v >> 8);
-    if (nb > 2u) d[2] = (u8)(v >> 16);
-    if (nb > 3u) d[3] = (u8)(v >> 24);
-}
-
-// LZ77 resolution of up to 32 tokens of one stream by a whole warp, through the warp's staging area.  Returns the tokens consumed.
-__device__ __forceinline__ u32 fastf_tps_copy_staged(const FastfTpsArgs &A, FastfTpsStream &S, FastfTpsSvc &W, u32 rd, u32 n, u32 lane)
-{
-    u8 *out = A.out + (((u64)S.obase_hi << 32) | S.obase_lo);
-    const u32 opos = S.opos;
-    const u32 a = (S.obase_lo + opos) & 3u;   // the batch starts at byte a of an aligned global word; staging byte i <-> global byte opos - a + i
-    u8 *sb = W.sb;
-    u32 tok = (lane < n) ? fastf_ldv(&S.ring[(rd + lane) & (FASTF_TPS_RING - 1u)]) : FASTF_TOK_END;
-    const u32 endm = __ballot_sync(FASTF_FULL_MASK, lane < n && (tok >> 30) == 2u);
-    u32 ntok = n;
-    if (endm) ntok = (u32)__ffs((int)endm) - 1u;
-    u32 mylen = 0;
-    if (lane < ntok) mylen = (tok >> 30) == 0u ? ((tok >> 24) & 3u) : (tok & 511u);
-    u32 inc = mylen;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        u32 t = __shfl_up_sync(FASTF_FULL_MASK, inc, o);
-        if ((int)lane >= o) inc += t;
-    }
-    // only what fits the staging area is taken now (a batch is ~130 bytes on BAM data; the cap matters for runs of long matches)
-    const u32 nfit = (u32)__popc(__ballot_sync(FASTF_FULL_MASK, lane < ntok && a + inc <= FASTF_TPS_SB));
-    const bool ended = endm != 0u && nfit == ntok;
-    ntok = nfit;
-    const u32 off = inc - mylen;
-    const u32 total = ntok ? __shfl_sync(FASTF_FULL_MASK, inc, (int)(ntok - 1u)) : 0u;
-    const bool is_lit = lane < ntok && (tok >> 30) == 0u;
-    const bool is_match = lane < ntok && (tok >> 30) == 1u;
-    const u32 len = tok & 511u, dist = (tok >> 9) & 0xffffu;
-    if (is_lit && FASTF_TPS_NOCOPY < 2) fastf_sts_bytes(sb + a + off, tok, mylen);
-    // "far" = the whole source lies before the batch: final bytes in global memory, no dependency on anything in the batch
-    const bool far = is_match && dist >= off + len;
-    const u32 far32m = FASTF_TPS_NOCOPY ? 0u : __ballot_sync(FASTF_FULL_MASK, far && len <= 32u);
-    u32 farlongm = FASTF_TPS_NOCOPY ? 0u : __ballot_sync(FASTF_FULL_MASK, far && len > 32u);
-    u32 nearm = FASTF_TPS_NOCOPY ? 0u : __ballot_sync(FASTF_FULL_MASK, is_match && !far);
-    if (far && len <= 32u) {
-        const u32 r = (u32)__popc(far32m & ((1u << lane) - 1u));
-        W.farlist[r][0] = tok; W.farlist[r][1] = off;
-    }
-    __syncwarp();
-    // short far matches: eight lanes x four bytes each, four matches per step, two steps in flight
-    const u32 nfar = (u32)__popc(far32m);
-    const u32 sub = (lane & 7u) * 4u;
-    for (u32 i = 0; i < nfar; i += 8u) {
-        u32 v[2], nb[2], dpos[2];
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const u32 idx = i + 4u * (u32)u + (lane >> 3);
-            nb[u] = 0; v[u] = 0; dpos[u] = 0;
-            if (idx < nfar) {
-                const uint2 e = *reinterpret_cast<const uint2 *>(W.farlist[idx]);
-                const u32 l = e.x & 511u, d = (e.x >> 9) & 0xffffu;
-                if (sub < l) {
-                    nb[u] = l - sub < 4u ? l - sub : 4u;
-                    dpos[u] = a + e.y + sub;
-                    v[u] = fastf_ld4_unaligned(out + (opos + e.y + sub) - d);
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; u++) fastf_sts_bytes(sb + dpos[u], v[u], nb[u]);
-    }
-    // long far matches (up to 258 bytes): 32 lanes x four bytes per step
-    while (farlongm) {
-        const u32 m = (u32)__ffs((int)farlongm) - 1u;
-        farlongm &= farlongm - 1u;
-        const u32 t = __shfl_sync(FASTF_FULL_MASK, tok, (int)m), o = __shfl_sync(FASTF_FULL_MASK, off, (int)m);
-        const u32 l = t & 511u, d = (t >> 9) & 0xffffu;
-        u32 v[3], nb[3];
-#pragma unroll
-        for (int u = 0; u < 3; u++) {
-            const u32 j = lane * 4u + 128u * (u32)u;
-            nb[u] = 0; v[u] = 0;
-            if (j < l) {
-                nb[u] = l - j < 4u ? l - j : 4u;
-                v[u] = fastf_ld4_unaligned(out + (opos + o + j) - d);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 3; u++) fastf_sts_bytes(sb + a + o + lane * 4u + 128u * (u32)u, v[u], nb[u]);
-    }
-    // the rest reads bytes of this batch (or overlaps itself): token order, out of the staging area; what lies before the batch
-    // comes from global memory
-    while (nearm) {
-        const u32 m = (u32)__ffs((int)nearm) - 1u;
-        nearm &= nearm - 1u;
-        const u32 t = __shfl_sync(FASTF_FULL_MASK, tok, (int)m), o = __shfl_sync(FASTF_FULL_MASK, off, (int)m);
-        const u32 l = t & 511u, d = (t >> 9) & 0xffffu;
-        __syncwarp();   // everything staged so far is ordered before these loads
-        // source byte r of the match sits at batch offset o - d + r; an overlapping match (d < l) repeats its first d bytes
-        const u32 rcp = (u32)(1048576.0f * __frcp_rn((float)d)) + 2u;
-        for (u32 k = 0; k < l; k += 32u) {
-            const u32 j = k + lane;
-            if (j < l) {
-                u32 r = j;
-                if (d < l) {
-                    const u32 q = (j * rcp) >> 20;   // j / d for j < 258, off by at most one
-                    r = j - q * d;
-                    if (r >= d) r += d;
-                }
-                const i32 sp = (i32)(o + r) - (i32)d;
-                sb[a + o + j] = sp < 0 ? out[(i32)opos + sp] : sb[a + (u32)sp];
-            }
-        }
-    }
-    __syncwarp();
-    // write the batch out: whole aligned words, single bytes at the two ends
-    if (FASTF_TPS_NOCOPY < 2) {
-        u8 *gbase = out + opos - a;
-        const u32 hi = a + total;
-        for (u32 w = lane * 4u; w < hi; w += 128u) {
-            if (w >= a && w + 4u <= hi) *reinterpret_cast<u32 *>(gbase + w) = *reinterpret_cast<const u32 *>(sb + w);
-            else {
-#pragma unroll
-                for (u32 b = 0; b < 4u; b++)
-                    if (w + b >= a && w + b < hi) gbase[w + b] = sb[w + b];
-            }
-        }
-    }
-    u32 consumed = ntok;
-    const u32 new_opos = opos + total;
-    if (ended) {
-        const u32 e = __shfl_sync(FASTF_FULL_MASK, tok, (int)ntok) & 0xffffu;
-        if (lane == 0) A.status[S.blk] = e | ((e == 0 && new_opos != S.isize) ? (u32)FASTF_ST_SIZE_MISMATCH : 0u);
-        consumed = ntok + 1;
-    }
-    __syncwarp();   // the staging area and the stores of this batch are done before the next batch starts
-    if (lane == 0) {
-        S.opos = new_opos;
-        FASTF_SMEM_ORDER();
-        fastf_stv(&S.rd, rd + consumed);
-    }
-    __syncwarp();
-    return consumed;
-}
-#endif
 
 // ------------------------------------------------------------------------------------------------------------------
 // decoder side (one thread = one stream)
@@ -947,11 +745,12 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
         u32 wr = 0, rd_cache = 0, pos = 0, isize = 0, last = 0;
         u64 in_end = 0;
         const u8 *obase = A.out;
+        FASTF_PROF(u32 p_dec = 0; u32 p_full = 0; u32 p_wait = 0;)
         for (;;) {
             if (!have) {
                 const u32 st = fastf_ldv(&S.state);
                 if (st == FASTF_TPS_DONE) break;
-                if (st != FASTF_TPS_RUN) { fastf_spin_poll(); continue; }
+                if (st != FASTF_TPS_RUN) { FASTF_PROF(p_wait++;) fastf_spin_poll(); continue; }
                 __threadfence_block();
                 br.init(A.comp, A.comp_total, ((u64)S.bitpos_hi << 32) | S.bitpos_lo);
                 pos = S.pos; isize = S.isize; last = S.last;
@@ -963,8 +762,9 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
             // a round stores up to FASTF_TPS_TRIPLES + 1 tokens
             if (wr - rd_cache > FASTF_TPS_RING - (FASTF_TPS_TRIPLES + 1u)) {
                 rd_cache = fastf_ldv(&S.rd);
-                if (wr - rd_cache > FASTF_TPS_RING - (FASTF_TPS_TRIPLES + 1u)) { fastf_stv(&S.wr, wr); fastf_spin_poll(); continue; }
+                if (wr - rd_cache > FASTF_TPS_RING - (FASTF_TPS_TRIPLES + 1u)) { FASTF_PROF(p_full++;) fastf_stv(&S.wr, wr); fastf_spin_poll(); continue; }
             }
+            FASTF_PROF(p_dec++;)
             // ---- one round: up to two literal tokens (three literals each) and the match behind them ----
             // Both the literal and the match path of a warp run in every round anyway (some lane always needs each), so a lane
             // walks through both: literals first, then the match that ends the literal run.  Only the first symbol of a round may
@@ -1093,6 +893,9 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
             fastf_stv(&S.state, end_stream ? (u32)FASTF_TPS_NEXT : (u32)FASTF_TPS_BUILD);
             have = false;
         }
+#if FASTF_TPS_PROF
+        atomicAdd(&g_fastf_tps_prof[0], (unsigned long long)p_dec); atomicAdd(&g_fastf_tps_prof[1], (unsigned long long)p_full); atomicAdd(&g_fastf_tps_prof[2], (unsigned long long)p_wait);
+#endif
     } else {
         // ---------------- service: lock-step warp, owns the streams sw, sw + SVC, sw + 2 SVC, ... ----------------
         // One poll pass costs a handful of instructions: lane k looks at the control block of the k-th stream of this warp, a
@@ -1106,24 +909,28 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
         const u32 first_sidx = sw * Q + (sw < R ? sw : R), n_mine = Q + (sw < R ? 1u : 0u);
         const u32 my_sidx = first_sidx + lane;
         const bool mine = lane < n_mine;
-        FastfTpsStream &MS = streams[mine ? my_sidx : first_sidx];
+        // The poll pass is the hottest loop of the service side (one pass per batch on average), so it is written to stay at a
+        // dozen instructions: the address of the control block is made opaque to the compiler (it recomputed it from the thread
+        // index in every pass otherwise), and the states are numbered so that "needs service" is one test -- NEXT and BUILD (even)
+        // always do, RUN and DONE (odd) only with a batch of tokens waiting (DONE never has one).
+        static_assert((FASTF_TPS_NEXT & 1) == 0 && (FASTF_TPS_BUILD & 1) == 0 && (FASTF_TPS_RUN & 1) == 1 && (FASTF_TPS_DONE & 1) == 1, "state parity");
+        const fastf_ctl_ptr ctl = fastf_ctl_of(&streams[mine ? my_sidx : first_sidx].state);
+        FASTF_PROF(u64 p_pass = 0; u64 p_empty = 0; u64 p_ccopy = 0; u64 p_csetup = 0; u64 p_cempty = 0; u64 p_batches = 0; u64 p_tokens = 0; const long long p_t00 = clock64();)
         for (;;) {
-            u32 st = FASTF_TPS_DONE, rd = 0, avail = 0;
-            if (mine) {
-                st = fastf_ldv(&MS.state);   // volatile shared-memory reads stay in program order: once the state says the
-                const u32 wr = fastf_ldv(&MS.wr);   // decoder handed the stream over, wr is final
-                rd = fastf_ldv(&MS.rd);
-                avail = wr - rd;
+            FASTF_PROF(const long long p_t0 = clock64(); p_pass++;)
+            const u32 st = fastf_ctl_ld(ctl, 0);  // volatile shared-memory reads stay in program order: once the state says the
+            const u32 wr = fastf_ctl_ld(ctl, 1);  // decoder handed the stream over, wr is final
+            const u32 rd = fastf_ctl_ld(ctl, 2);
+            const u32 avail = wr - rd;
+            const bool need = mine && (((st & 1u) == 0) || avail >= FASTF_TPS_BATCH_MIN);
+            u32 m = __ballot_sync(FASTF_FULL_MASK, need);
+            if (!m) {
+                if (__ballot_sync(FASTF_FULL_MASK, mine && st != FASTF_TPS_DONE) == 0) break;
+                fastf_spin_pause();   // nothing to copy or set up: leave the issue slots to the decoders
+                FASTF_PROF(p_empty++; p_cempty += (u64)(clock64() - p_t0);)
+                continue;
             }
-            u32 work = 0;
-            if (st != FASTF_TPS_DONE) {
-                if (avail >= FASTF_TPS_BATCH_MIN || (avail > 0 && st != FASTF_TPS_RUN)) work = 1;
-                else if (avail == 0 && st == FASTF_TPS_NEXT) work = 2;
-                else if (avail == 0 && st == FASTF_TPS_BUILD) work = 3;
-            }
-            if (__ballot_sync(FASTF_FULL_MASK, st != FASTF_TPS_DONE) == 0) break;
-            u32 m = __ballot_sync(FASTF_FULL_MASK, work != 0);
-            if (!m) { fastf_spin_pause(); continue; }   // nothing to copy or set up: leave the issue slots to the decoders
+            const u32 work = avail ? 1u : (st == FASTF_TPS_NEXT ? 2u : 3u);
             while (m) {
                 const u32 k = (u32)__ffs((int)m) - 1u;
                 m &= m - 1u;
@@ -1133,12 +940,10 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
                 const u32 sidx = first_sidx + k;
                 FastfTpsStream &S = streams[sidx];
                 u16 *ssorted = sorted_base + (size_t)sidx * FASTF_TPS_SORTED_U16;
+                FASTF_PROF(const long long p_t1 = clock64();)
                 if (w == 1) {
-#if FASTF_TPS_STAGED
-                    fastf_tps_copy_staged(A, S, G.svc[sw], krd, kav < 32u ? kav : 32u, lane);
-#else
+                    FASTF_PROF(p_batches++; p_tokens += kav < 32u ? kav : 32u;)
                     fastf_tps_copy(A, S, krd, kav < 32u ? kav : 32u, lane);
-#endif
                 } else if (w == 2) {
                     // fetch the next BGZF block for this stream
                     u32 b = 0;
@@ -1161,7 +966,15 @@ __global__ void __launch_bounds__(FASTF_TPS_THREADS_OF(L, SVC), 1) fastf_bgzf_in
                 } else {
                     fastf_tps_setup(A, S, ssorted, G, sw, lane);
                 }
+                FASTF_PROF(if (w == 1) p_ccopy += (u64)(clock64() - p_t1); else p_csetup += (u64)(clock64() - p_t1);)
             }
         }
+#if FASTF_TPS_PROF
+        if (lane == 0) {
+            atomicAdd(&g_fastf_tps_prof[3], p_pass); atomicAdd(&g_fastf_tps_prof[4], p_empty); atomicAdd(&g_fastf_tps_prof[5], p_ccopy);
+            atomicAdd(&g_fastf_tps_prof[6], p_csetup); atomicAdd(&g_fastf_tps_prof[7], p_cempty); atomicAdd(&g_fastf_tps_prof[8], p_batches);
+            atomicAdd(&g_fastf_tps_prof[9], p_tokens); atomicAdd(&g_fastf_tps_prof[10], (u64)(clock64() - p_t00));
+        }
+#endif
     }
 }

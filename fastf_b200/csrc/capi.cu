@@ -230,10 +230,19 @@ extern "C" int fastf_abi_version(void) { return FASTF_ABI_VERSION; }
 #endif
 #define FASTF_STR2(x) #x
 #define FASTF_STR(x) FASTF_STR2(x)
+#if FASTF_TPS_PROF
+// debug builds only (-DFASTF_TPS_PROF=1, scripts/inflate_ab.py): the kernel's role counters, see bgzf_inflate_tps.cuh
+extern "C" int fastf_debug_tps_prof(unsigned long long *out16, int reset)
+{
+    if (out16 && cudaMemcpyFromSymbol(out16, g_fastf_tps_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+    if (reset) { unsigned long long z[16] = {0}; if (cudaMemcpyToSymbol(g_fastf_tps_prof, z, sizeof z) != cudaSuccess) return 1; }
+    return 0;
+}
+#endif
 extern "C" const char *fastf_build_info(void)
 {
     return "streams=" FASTF_STR(FASTF_TPS_STREAMS) " lanes=" FASTF_STR(FASTF_TPS_LANES) " svc=" FASTF_STR(FASTF_TPS_SVC_WARPS) " lbits=" FASTF_STR(FASTF_TPS_LBITS) " dbits=" FASTF_STR(FASTF_TPS_DBITS)
-           " ring=" FASTF_STR(FASTF_TPS_RING) " staged=" FASTF_STR(FASTF_TPS_STAGED) " src=" FASTF_SRC_HASH;
+           " ring=" FASTF_STR(FASTF_TPS_RING) " src=" FASTF_SRC_HASH;
 }
 
 static char g_create_err[512] = "";

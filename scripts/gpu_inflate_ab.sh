@@ -11,7 +11,7 @@ for lib in fastf_b200/_build/variants/*.so; do
   NOCRC=""; case "$lib" in *nocopy*|*_l1*) NOCRC=1;; esac
   LL="0"; case "$(basename $lib)" in zz*) LL="$LANES";; esac
   for l in $LL; do
-    FASTF_AB_NOCRC=$NOCRC FASTF_GPU_LIB=$PWD/$lib python scripts/inflate_ab.py --lanes $l 2>gpurun_out/ab_err.txt >> $LOG || { echo "FAILED $lib lanes $l" >> $LOG; tail -2 gpurun_out/ab_err.txt >> $LOG; }
+    FASTF_AB_NOCRC=$NOCRC FASTF_GPU_LIB=$PWD/$lib timeout 200 python scripts/inflate_ab.py --lanes $l 2>gpurun_out/ab_err.txt >> $LOG || { echo "FAILED $lib lanes $l" >> $LOG; tail -2 gpurun_out/ab_err.txt >> $LOG; }
   done
 done
 for spec in "$@"; do
