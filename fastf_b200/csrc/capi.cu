@@ -32,9 +32,11 @@
 #include <vector>
 #include <unordered_map>
 #include <string>
+#include <chrono>
 #ifndef FASTF_EMU
 #include <cuda.h>   // driver API: cuMemBatchDecompressAsync (Blackwell hardware decompression engine)
 #endif
+static double wall_seconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 #define FASTF_ABI_VERSION 1
 
@@ -53,6 +55,9 @@ struct fastf_ctx {
     // size-bucketed caches of device / pinned allocations: a job's buffers are recycled by the next job on the same
     // context, so steady-state calls do not pay cudaMalloc / cudaMallocHost (both synchronise the device)
     std::vector<PoolEntry> *dev_pool, *pin_pool;
+    // Sizes the buffers of the last bam2db job ended with.  A buffer that grows in mid-job drains every stream (dev_reserve) and
+    // leaves the device idle while the host queues the next chunk, so the next job starts its growing buffers at these sizes.
+    size_t hint_cand = 0, hint_keepbits = 0, hint_ring = 0;
 };
 
 static int ctx_fail(fastf_ctx *ctx, const char *fmt, ...)
@@ -741,9 +746,24 @@ static int index_reserve(fastf_ctx *ctx, BlockIndexDev &I, u32 nb)
     I.h_isize = (u32 *)h;
     return 0;
 }
+// The block index of a chunk (a few MB) is PULLED by a kernel out of the pinned host arrays instead of being pushed through the
+// copy engine: there it queues behind the bulk H2D copies of the next chunks' compressed bytes (FIFO per direction) and the inflate
+// that waits for it starts up to three copies late (measured: the first inflate of a host-fed job 90 ms after its bytes arrived).
+__global__ void __launch_bounds__(256) fastf_pull_words_kernel(u32 *__restrict__ dst, const u32 *__restrict__ src_host, u64 n_words)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (u64)gridDim.x * blockDim.x) dst[i] = src_host[i];
+}
 static int index_upload(fastf_ctx *ctx, BlockIndexDev &I, cudaStream_t s)
 {
-    CK(cudaMemcpyAsync(I.buf.p, I.host.p, index_bytes_up(I.cap_blocks), cudaMemcpyHostToDevice, s));
+    const size_t bytes = index_bytes_up(I.cap_blocks);
+#ifdef FASTF_EMU
+    CK(cudaMemcpyAsync(I.buf.p, I.host.p, bytes, cudaMemcpyHostToDevice, s));
+#else
+    void *src = nullptr;
+    CK(cudaHostGetDevicePointer(&src, I.host.p, 0));
+    FASTF_LAUNCH(fastf_pull_words_kernel, 2 * ctx->n_sm, 256, 0, s, I.buf.as<u32>(), (const u32 *)src, (u64)(bytes / 4));
+    CKL("pull_index");
+#endif
     return 0;
 }
 static void index_release(fastf_ctx *ctx, BlockIndexDev &I) { dev_release(ctx, I.buf); pin_release(ctx, I.host); I.cap_blocks = 0; }
@@ -780,6 +800,14 @@ struct fastf_bam2db_job {
     // anything and overlaps the inflate of chunks i-2 and i-1
     struct CompRing { DevBuf buf; cudaEvent_t ev_copy = nullptr, ev_free = nullptr; bool used = false; } comp_ring[3];
     u32 comp_seq = 0;
+    u64 ring_estimate = 0;
+    // FASTF_FEED_TIMING=1: where a host-fed job spends its time (stderr at finish): H2D copies by CUDA events, host waits by wall clock
+    bool feed_timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ft_copy_ev, ft_infl_ev;
+    std::vector<cudaEvent_t> ft_parse_ev;
+    std::vector<double> ft_host_submit;
+    u64 ft_copy_bytes = 0;
+    double ft_wait_s = 0, ft_index_s = 0, ft_feed_s = 0;
     // Blocks wait here until a chunk is full, ACROSS feed calls: the persistent inflate kernel keeps n_sm x FASTF_TPS_STREAMS blocks
     // in flight, so a launch over an exact multiple of that many blocks has no half-empty last round (measured: +11 % inflate
     // throughput over 2 GiB chunks cut at the feed boundaries).
@@ -815,6 +843,7 @@ struct fastf_bam2db_job {
     RleScratch rleS;
     // stats
     u64 n_blocks = 0, comp_bytes = 0, infl_bytes = 0;
+    u64 n_blocks_fed = 0, n_blocks_done = 0;   // blocks handed to run_blocks / blocks whose candidate counts have come back
     u32 launches0 = 0, n_chunks = 0;
     Timer t_infl[2], t_crc[2], t_parse[2], t_gather[2], t_mt[2], t_sample, t_sort, t_count;
     u32 mt_launches = 0;
@@ -843,6 +872,9 @@ extern "C" void fastf_bam2db_job_free(fastf_bam2db_job *job)
         if (S.ev_done) cudaEventDestroy(S.ev_done);
         job->t_infl[i].destroy(); job->t_crc[i].destroy(); job->t_parse[i].destroy(); job->t_gather[i].destroy();
     }
+    ctx->hint_cand = std::max(ctx->hint_cand, job->cand.cap);
+    ctx->hint_keepbits = std::max(ctx->hint_keepbits, job->keepbits.cap);
+    for (auto &R : job->comp_ring) ctx->hint_ring = std::max(ctx->hint_ring, R.buf.cap);
     for (auto &R : job->comp_ring) {
         dev_release(ctx, R.buf);
         if (R.ev_copy) cudaEventDestroy(R.ev_copy);
@@ -868,6 +900,7 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
     if (!p || (p->n_cells && (!p->cell_keys || !p->cell_off)) || (p->n_genes && (!p->gene_keys || !p->gene_off))) return ctx_fail(ctx, "bam2db_begin: null table pointers");
     if (p->keep_threshold > 4294967296ull) return ctx_fail(ctx, "bam2db_begin: keep_threshold > 2^32");
     fastf_bam2db_job *job = new fastf_bam2db_job();
+    { const char *e = getenv("FASTF_FEED_TIMING"); job->feed_timing = e && *e && *e != '0'; }
     job->ctx = ctx;
     job->prm = *p;
     job->launches0 = ctx->launches;
@@ -938,7 +971,7 @@ static int mt_extend(fastf_bam2db_job *job, u64 n_draws)
     const size_t need = (size_t)pairs * 39 * sizeof(u32);
     if (need > job->keepbits.cap) {
         // grow geometrically; the copy keeps the bits produced so far
-        size_t want = std::max(need + need / 2, (size_t)(64u << 20));
+        size_t want = std::max(std::max(need + need / 2, (size_t)(64u << 20)), ctx->hint_keepbits);
         TRY(dev_reserve(ctx, job->keepbits, want, (size_t)job->mt_pairs_done * 39 * sizeof(u32), ctx->mt));
     }
     Timer &tm = job->t_mt[job->mt_launches++ & 1u];   // the launch two extensions back has long finished
@@ -1037,9 +1070,12 @@ static int finalize_slot(fastf_bam2db_job *job, u32 si)
     fastf_ctx *ctx = job->ctx;
     ChunkSlot &S = job->slot[si];
     if (!S.pending) return 0;
+    const double ft_w0 = job->feed_timing ? wall_seconds() : 0;
     CK(cudaEventSynchronize(S.ev_done));
+    if (job->feed_timing) job->ft_wait_s += wall_seconds() - ft_w0;
     const u64 *snap = S.snap.as<u64>();
     const u64 n_records = snap[0], n_cand = snap[1];
+    job->n_blocks_done += S.nblocks;
     job->status |= (u32)snap[2];
     if (job->status) {
         char buf[256];
@@ -1049,6 +1085,9 @@ static int finalize_slot(fastf_bam2db_job *job, u32 si)
     }
     if (n_cand > job->cand_cap) {
         u64 want = std::max<u64>(n_cand + n_cand / 2, 1u << 20);
+        want = std::max<u64>(want, ctx->hint_cand / sizeof(u64));
+        // the blocks already handed to the job will bring candidates at the rate seen so far
+        if (job->n_blocks_done) want = std::max<u64>(want, (u64)((double)n_cand * (double)job->n_blocks_fed / (double)job->n_blocks_done * 1.03) + (1u << 16));
         TRY(dev_reserve(ctx, job->cand, want * sizeof(u64), job->n_cand * sizeof(u64), ctx->compute));
         job->cand_cap = job->cand.cap / sizeof(u64);
     }
@@ -1123,8 +1162,11 @@ static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb
     TRY(index_upload(ctx, S.idx, ctx->infl));
     job->t_infl[si].collect(&job->ms_inflate);
     job->t_infl[si].start(ctx->infl);
+    cudaEvent_t fti0 = nullptr, fti1 = nullptr;
+    if (job->feed_timing && ring) { CK(cudaEventCreate(&fti0)); CK(cudaEventCreate(&fti1)); CK(cudaEventRecord(fti0, ctx->infl)); job->ft_host_submit.push_back(wall_seconds()); }
     TRY(launch_inflate(ctx, job->lanes, comp_dev, comp_total, S.idx.in_off, S.idx.in_len, S.idx.out_off, S.idx.isize, nb, S.infl.as<u8>(), S.idx.st_infl, ctx->infl, &S.de, S.idx.h_in_off,
                        S.idx.h_in_len, S.idx.h_out_off, S.idx.h_isize));
+    if (fti0) { CK(cudaEventRecord(fti1, ctx->infl)); job->ft_infl_ev.push_back({fti0, fti1}); }
     job->t_infl[si].stop(ctx->infl);
     CK(cudaEventRecord(S.ev_infl, ctx->infl));
     CK(cudaStreamWaitEvent(ctx->compute, S.ev_infl, 0));
@@ -1158,6 +1200,7 @@ static int run_chunk(fastf_bam2db_job *job, const FastfBgzfBlock *blocks, u32 nb
     job->t_parse[si].stop(ctx->compute);
     CK(cudaMemcpyAsync(S.snap.p, job->counters.p, 4 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->compute));
     CK(cudaEventRecord(S.ev_done, ctx->compute));
+    if (job->feed_timing && ring) { cudaEvent_t e = nullptr; CK(cudaEventCreate(&e)); CK(cudaEventRecord(e, ctx->compute)); job->ft_parse_ev.push_back(e); }
     S.nblocks = nb;
     S.pending = true;
     job->n_blocks += nb;
@@ -1194,9 +1237,15 @@ static int stage_host_bytes(fastf_bam2db_job *job, const u8 *host_base, u64 lo, 
         if (P.ring->used) CK(cudaStreamWaitEvent(ctx->copy, P.ring->ev_free, 0));
     }
     const u64 bytes = hi - lo, padded = (bytes + 3) & ~3ull;
-    // growing moves the buffer: the bytes staged so far travel along (dev_reserve drains the streams before it lets go of the old one)
-    TRY(dev_reserve(ctx, P.ring->buf, P.fill + padded + 16, P.fill, ctx->copy));
+    // growing moves the buffer: the bytes staged so far travel along (dev_reserve drains the streams before it lets go of the old one),
+    // so an entry starts at the size a whole chunk is expected to need
+    u64 want = P.fill + padded + 16;
+    if (want > P.ring->buf.cap) want = std::max<u64>(want, std::max<u64>(ctx->hint_ring, job->ring_estimate));
+    TRY(dev_reserve(ctx, P.ring->buf, want, P.fill, ctx->copy));
+    cudaEvent_t ft0 = nullptr, ft1 = nullptr;
+    if (job->feed_timing) { CK(cudaEventCreate(&ft0)); CK(cudaEventCreate(&ft1)); CK(cudaEventRecord(ft0, ctx->copy)); }
     CK(cudaMemcpyAsync(P.ring->buf.as<u8>() + P.fill, host_base + lo, bytes, cudaMemcpyHostToDevice, ctx->copy));
+    if (job->feed_timing) { CK(cudaEventRecord(ft1, ctx->copy)); job->ft_copy_ev.push_back({ft0, ft1}); job->ft_copy_bytes += bytes; }
     *at = P.fill;
     P.fill += padded;
     return 0;
@@ -1209,6 +1258,15 @@ static int run_blocks(fastf_bam2db_job *job, const std::vector<FastfBgzfBlock> &
     fastf_bam2db_job::PendingChunk &P = job->pending;
     const size_t n = blocks.size();
     size_t i = 0;
+    job->n_blocks_fed += n;
+    // compressed bytes a full chunk of this feed will stage (ring entries are sized once, see stage_host_bytes): never more than the feed holds
+    if (host_base && n) {
+        u64 isz = 0;
+        for (size_t k = 0; k < n; k++) isz += blocks[k].isize;
+        const double span = (double)(blocks[n - 1].in_off + blocks[n - 1].in_len + 8 - blocks[0].in_off);
+        const double per_chunk = std::min<double>((double)job->chunk_blocks, (double)job->chunk_bytes / std::max<double>((double)isz / (double)n, 1.0));
+        job->ring_estimate = (u64)std::min<double>(span, span / (double)n * 1.03 * per_chunk) + (1u << 20);
+    }
     while (i < n) {
         // a chunk reads its compressed bytes from one buffer: blocks of another device buffer (or of the other kind of feed) start a new one
         if (!P.blocks.empty() && (host_base ? P.ring == nullptr : (P.ring != nullptr || P.comp_dev != comp_dev))) TRY(submit_pending(job));
@@ -1244,6 +1302,7 @@ extern "C" int fastf_bam2db_feed(fastf_bam2db_job *job, const void *host_bytes, 
     fastf_ctx *ctx = job->ctx;
     CK(cudaSetDevice(ctx->device));
     if (job->sampled_done) return ctx_fail(ctx, "bam2db_feed: job already sampled");
+    struct FeedClock { fastf_bam2db_job *j; double t0; ~FeedClock() { if (j->feed_timing) j->ft_feed_s += wall_seconds() - t0; } } feed_clock{job, job->feed_timing ? wall_seconds() : 0};
     const u8 *p = (const u8 *)host_bytes;
     job->comp_bytes += n;
     std::vector<FastfBgzfBlock> blocks;
@@ -1487,6 +1546,35 @@ extern "C" int fastf_bam2db_finish(fastf_bam2db_job *job, fastf_bam2db_result *r
     CK(cudaSetDevice(ctx->device));
     memset(res, 0, sizeof *res);
     if (!job->sampled_done) TRY(fastf_bam2db_sample(job, 0));
+    if (job->feed_timing && !job->ft_copy_ev.empty()) {
+        CK(cudaStreamSynchronize(ctx->copy));
+        double ms = 0, span = 0;
+        for (auto &e : job->ft_copy_ev) { float t = 0; cudaEventElapsedTime(&t, e.first, e.second); ms += t; }
+        { float t = 0; cudaEventElapsedTime(&t, job->ft_copy_ev.front().first, job->ft_copy_ev.back().second); span = t; }
+        fprintf(stderr, "[fastf feed timing] H2D %zu copies, %.2f GB in %.1f ms of copy time = %.1f GB/s (first start to last end %.1f ms); host: %.1f ms inside feed calls, of which %.1f ms waiting for chunks to finish\n",
+                job->ft_copy_ev.size(), job->ft_copy_bytes / 1e9, ms, job->ft_copy_bytes / 1e6 / std::max(ms, 1e-3), span, 1e3 * job->ft_feed_s, 1e3 * job->ft_wait_s);
+        CK(cudaDeviceSynchronize());
+        {
+            // per chunk, ms since the first copy started: inflate start / end, parse end, and when the host submitted it
+            cudaEvent_t o = job->ft_copy_ev.front().first;
+            fprintf(stderr, "[fastf feed timing] chunk: host-submit | inflate start..end | parse end   (ms since the first H2D started; copies: start..end)\n");
+            for (size_t k = 0; k < job->ft_infl_ev.size(); k++) {
+                float a = 0, b = 0, c = 0;
+                cudaEventElapsedTime(&a, o, job->ft_infl_ev[k].first); cudaEventElapsedTime(&b, o, job->ft_infl_ev[k].second);
+                if (k < job->ft_parse_ev.size()) cudaEventElapsedTime(&c, o, job->ft_parse_ev[k]);
+                fprintf(stderr, "[fastf feed timing]   %2zu: host %.1f | %.1f..%.1f | %.1f\n", k, 1e3 * (job->ft_host_submit[k] - job->ft_host_submit[0]), a, b, c);
+            }
+            for (size_t k = 0; k < job->ft_copy_ev.size(); k++) {
+                float a = 0, b = 0;
+                cudaEventElapsedTime(&a, o, job->ft_copy_ev[k].first); cudaEventElapsedTime(&b, o, job->ft_copy_ev[k].second);
+                fprintf(stderr, "[fastf feed timing]   copy %2zu: %.1f..%.1f\n", k, a, b);
+            }
+        }
+        for (auto &e : job->ft_copy_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        for (auto &e : job->ft_infl_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        for (auto &e : job->ft_parse_ev) cudaEventDestroy(e);
+        job->ft_copy_ev.clear(); job->ft_infl_ev.clear(); job->ft_parse_ev.clear();
+    }
     const u64 n = job->n_valid;
     const FastfKeyLayout &L = job->L;
     if (job->prm.want_rows) {
