@@ -186,6 +186,23 @@ static void pools_trim(fastf_ctx *ctx)
 // Large results go to pageable host memory the caller owns (malloc'ed result arrays).  A plain cudaMemcpy into pageable memory is
 // staged by the driver at a few GB/s; here the bytes cross PCIe into two pinned bounce buffers (from the context's pool) while
 // the host copies the previous piece out, so the transfer runs at memcpy speed.  Synchronous: dst is complete on return.
+// memcpy of a bounce piece into the caller's (fresh, never touched) pageable memory: page faults and a single core's copy rate
+// would otherwise bound the D2H of a few hundred MB of results, so a few threads take a slice each
+static void par_memcpy(void *dst, const void *src, size_t n)
+{
+    const size_t SLICE = (size_t)4 << 20;
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nt = std::min<size_t>(std::min<size_t>(hw > 1 ? hw / 2 : 1, 8), n / SLICE);
+    if (nt < 2) { memcpy(dst, src, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = ((n + nt - 1) / nt + 4095) & ~(size_t)4095;
+    for (size_t t = 1; t < nt; t++) {
+        const size_t o = t * per;
+        if (o < n) th.emplace_back([=] { memcpy((u8 *)dst + o, (const u8 *)src + o, std::min(per, n - o)); });
+    }
+    memcpy(dst, src, std::min(per, n));
+    for (auto &x : th) x.join();
+}
 static int d2h_pageable(fastf_ctx *ctx, void *dst, const void *src_dev, size_t bytes, cudaStream_t s)
 {
     if (bytes == 0) return 0;
@@ -208,7 +225,7 @@ static int d2h_pageable(fastf_ctx *ctx, void *dst, const void *src_dev, size_t b
         if (k > 0 && !rc) {
             const size_t o = (k - 1) * PIECE, m = std::min(PIECE, bytes - o);
             if (cudaEventSynchronize(ev[(k - 1) & 1]) != cudaSuccess) rc = ctx_fail(ctx, "d2h: copy failed");
-            else memcpy((u8 *)dst + o, bounce[(k - 1) & 1].p, m);
+            else par_memcpy((u8 *)dst + o, bounce[(k - 1) & 1].p, m);
         }
     }
     cudaStreamSynchronize(s);
