@@ -248,9 +248,43 @@ __device__ __forceinline__ u32 fastf_parse_record(const Acc &A, u64 rec, u64 ren
     return 1;
 }
 
-// ---- thread-per-record variants (no warp collectives): lane i of the warp walks record i of the staged batch ----
-template <class Acc>
-__device__ __forceinline__ u32 fastf_table_lookup_lane(const FastfStrTableView &T, const Acc &A, u64 s, u32 len)
+// ---- thread-per-record variant (no warp collectives): lane i of the warp walks record i of the staged batch ----
+// Everything a lane touches lies in its warp's shared-memory window, so positions are 32-bit offsets from the start of the window:
+// the 64-bit stream offsets of the generic accessors doubled the address arithmetic of what is an instruction-bound kernel.
+struct FastfWin32 {
+    const u8 *W;   // 16-byte aligned; readable FASTF_PARSE_PAD bytes beyond the staged bytes
+    __device__ __forceinline__ u32 byte(u32 o) const { return W[o]; }
+    __device__ __forceinline__ u32 word(u32 o) const { return *reinterpret_cast<const u32 *>(W + (o & ~3u)); }
+    // the four bytes at o .. o+3, any alignment: two aligned words and a funnel shift (an aligned o reads the same word twice)
+    __device__ __forceinline__ u32 bytes4(u32 o) const
+    {
+        const u32 lo = word(o), hi = word(o + 3u), sh = 8u * (o & 3u);
+#ifdef FASTF_EMU
+        return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#else
+        return __funnelshift_r(lo, hi, sh);
+#endif
+    }
+    __device__ __forceinline__ u32 u16at(u32 o) const { return bytes4(o) & 0xffffu; }
+};
+#define FASTF_PARSE_PAD 16u
+// position of the first NUL byte in [s, rend), or rend if there is none: four bytes per load
+__device__ __forceinline__ u32 fastf_find_nul32(const FastfWin32 &A, u32 s, u32 rend)
+{
+    u32 a = s & ~3u;
+    u32 w = A.word(a) | ((1u << (8u * (s & 3u))) - 1u);   // bytes in front of s do not count
+    for (;;) {
+        const u32 z = (w - 0x01010101u) & ~w & 0x80808080u;   // 0x80 in every byte that is zero
+        if (z) {
+            const u32 p = a + (((u32)__ffs((int)z) - 1u) >> 3);
+            return p < rend ? p : rend;
+        }
+        a += 4u;
+        if (a >= rend) return rend;
+        w = A.word(a);
+    }
+}
+__device__ __forceinline__ u32 fastf_table_lookup_lane(const FastfStrTableView &T, const FastfWin32 &A, u32 s, u32 len)
 {
     u32 h1 = 0, h2 = 0;
     u32 c = 0;
@@ -275,10 +309,10 @@ __device__ __forceinline__ u32 fastf_table_lookup_lane(const FastfStrTableView &
             const u32 *pw = reinterpret_cast<const u32 *>(T.pool + raw.y);
             bool same = true;
             u32 i = 0;
-            for (; i + 4 <= len && same; i += 4) same = pw[i >> 2] == fastf_acc_4bytes(A, s + i);
+            for (; i + 4 <= len && same; i += 4) same = pw[i >> 2] == A.bytes4(s + i);
             if (same && i < len) {
-                const u32 w = pw[i >> 2];
-                for (u32 b = 0; i + b < len; b++) same = same && (((w >> (8u * b)) & 255u) == A.byte(s + i + b));
+                const u32 keep = (1u << (8u * (len - i))) - 1u;   // 1..3 trailing bytes
+                same = ((pw[i >> 2] ^ A.bytes4(s + i)) & keep) == 0;
             }
             if (same) return raw.w;
         }
@@ -286,31 +320,28 @@ __device__ __forceinline__ u32 fastf_table_lookup_lane(const FastfStrTableView &
     }
 }
 
-// scalar twin of fastf_parse_record (same decisions, one thread)
-template <class Acc>
-__device__ __forceinline__ u32 fastf_parse_record_lane(const Acc &A, u64 rec, u64 rend, u32 bs, const FastfStrTableView &cells, const FastfStrTableView &genes, const FastfKeyLayout &L,
+// scalar twin of fastf_parse_record (same decisions, one thread); rec / rend are offsets into the window, bs = rend - rec
+__device__ __forceinline__ u32 fastf_parse_record_lane(const FastfWin32 &A, u32 rec, u32 rend, u32 bs, const FastfStrTableView &cells, const FastfStrTableView &genes, const FastfKeyLayout &L,
                                                        u32 *status, u64 *key_out)
 {
-    const u32 l_read_name = A.byte(rec + 8);
-    const u32 n_cigar = fastf_acc_u16(A, rec + 12);
-    const i32 l_seq = (i32)fastf_acc_u32(A, rec + 16);
+    const u32 l_read_name = A.byte(rec + 8u);
+    const u32 n_cigar = A.u16at(rec + 12u);
+    const i32 l_seq = (i32)A.bytes4(rec + 16u);
     const i64 aoff = 32 + (i64)l_read_name + 4 * (i64)n_cigar + (((i64)l_seq + 1) >> 1) + (i64)l_seq;
     if (l_seq < 0 || aoff > (i64)bs) { *status |= FASTF_ST_REC_CORRUPT; return 2; }
-    FastfAuxHit cb = {0, 0, 0}, xf = {0, 0, 0}, gx = {0, 0, 0}, ub = {0, 0, 0};
+    u32 cb_off = 0, cb_len = 0, cb_type = 0, xf_off = 0, xf_type = 0, gx_off = 0, gx_len = 0, gx_type = 0, ub_off = 0, ub_len = 0, ub_type = 0;
     u32 found = 0;
-    u64 q = rec + (u64)aoff;
-    while (rend - q >= 3 && found != 15u) {
-        u32 t0, t1, ty;
-        if (rend - q >= 4) { const u32 hd = fastf_acc_4bytes(A, q); t0 = hd & 255u; t1 = (hd >> 8) & 255u; ty = (hd >> 16) & 255u; }
-        else { t0 = A.byte(q); t1 = A.byte(q + 1); ty = A.byte(q + 2); }
-        const u64 v = q + 3;
-        u64 next;
-        u32 vlen = 0;
+    u32 q = rec + (u32)aoff;
+    while (rend - q >= 3u && found != 15u) {
+        const u32 hd = A.bytes4(q);   // tag, tag, type (+ one byte that may lie behind the record: read, not used)
+        const u32 tag = hd & 0xffffu, ty = (hd >> 16) & 255u;
+        const u32 v = q + 3u;
+        u32 next, vlen = 0;
         if (ty == 'Z' || ty == 'H') {
-            const u64 s = fastf_find_nul(A, v, rend);
+            const u32 s = fastf_find_nul32(A, v, rend);
             if (s >= rend) break;   // unterminated: this and every later tag is invisible (htslib)
-            vlen = (u32)(s - v);
-            next = s + 1;
+            vlen = s - v;
+            next = s + 1u;
         } else {
             u64 sz;
             switch (ty) {
@@ -319,59 +350,60 @@ __device__ __forceinline__ u32 fastf_parse_record_lane(const Acc &A, u64 rec, u6
             case 'i': case 'I': case 'f': sz = 4; break;
             case 'd': sz = 8; break;
             case 'B': {
-                if (rend - v < 5) { sz = ~0ull; break; }
-                u32 sub = A.byte(v);
-                u64 cnt = fastf_acc_u32(A, v + 1);
-                u64 es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
+                if (rend - v < 5u) { sz = ~0ull; break; }
+                const u32 sub = A.byte(v);
+                const u64 cnt = A.bytes4(v + 1u);
+                const u64 es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
                 sz = es ? 5 + es * cnt : ~0ull;
                 break;
             }
             default: sz = ~0ull;
             }
-            if (sz == ~0ull || sz > rend - v) break;
-            next = v + sz;
+            if (sz == ~0ull || sz > (u64)(rend - v)) break;
+            next = v + (u32)sz;
         }
-        if (t0 == 'C' && t1 == 'B' && !(found & 1u)) { cb.off = v; cb.len = vlen; cb.type = ty; found |= 1u; }
-        else if (t0 == 'x' && t1 == 'f' && !(found & 2u)) { xf.off = v; xf.type = ty; found |= 2u; }
-        else if (t0 == 'G' && t1 == 'X' && !(found & 4u)) { gx.off = v; gx.len = vlen; gx.type = ty; found |= 4u; }
-        else if (t0 == 'U' && t1 == 'B' && !(found & 8u)) { ub.off = v; ub.len = vlen; ub.type = ty; found |= 8u; }
+        if (tag == ('C' | ('B' << 8)) && !(found & 1u)) { cb_off = v; cb_len = vlen; cb_type = ty; found |= 1u; }
+        else if (tag == ('x' | ('f' << 8)) && !(found & 2u)) { xf_off = v; xf_type = ty; found |= 2u; }
+        else if (tag == ('G' | ('X' << 8)) && !(found & 4u)) { gx_off = v; gx_len = vlen; gx_type = ty; found |= 4u; }
+        else if (tag == ('U' | ('B' << 8)) && !(found & 8u)) { ub_off = v; ub_len = vlen; ub_type = ty; found |= 8u; }
         q = next;
     }
-    if (!(found & 1u) || !(cb.type == 'Z' || cb.type == 'H')) return 0;
-    const u32 cidx = fastf_table_lookup_lane(cells, A, cb.off, cb.len);
+    if (!(found & 1u) || !(cb_type == 'Z' || cb_type == 'H')) return 0;
+    const u32 cidx = fastf_table_lookup_lane(cells, A, cb_off, cb_len);
     if (cidx == 0) return 0;
     u64 key = FASTF_INVALID_KEY;
     i64 xfv = 0;
     if (found & 2u) {
-        const u64 x = xf.off;
-        switch (xf.type) {
+        const u32 x = xf_off;
+        switch (xf_type) {
         case 'c': xfv = (i64)(int8_t)A.byte(x); break;
         case 'C': xfv = A.byte(x); break;
-        case 's': xfv = (i64)(int16_t)fastf_acc_u16(A, x); break;
-        case 'S': xfv = fastf_acc_u16(A, x); break;
-        case 'i': xfv = (i64)(i32)fastf_acc_u32(A, x); break;
-        case 'I': xfv = fastf_acc_u32(A, x); break;
+        case 's': xfv = (i64)(int16_t)A.u16at(x); break;
+        case 'S': xfv = A.u16at(x); break;
+        case 'i': xfv = (i64)(i32)A.bytes4(x); break;
+        case 'I': xfv = A.bytes4(x); break;
         default: xfv = 0;
         }
     }
     const int xfi = (int)xfv;   // the reference stores bam_aux2i() in an int
-    if ((xfi == 25 || xfi == 17) && (found & 4u) && (gx.type == 'Z' || gx.type == 'H') && (found & 8u) && (ub.type == 'Z' || ub.type == 'H')) {
-        const u32 gidx = fastf_table_lookup_lane(genes, A, gx.off, gx.len);
+    if ((xfi == 25 || xfi == 17) && (found & 4u) && (gx_type == 'Z' || gx_type == 'H') && (found & 8u) && (ub_type == 'Z' || ub_type == 'H')) {
+        const u32 gidx = fastf_table_lookup_lane(genes, A, gx_off, gx_len);
         if (gidx != 0) {
-            if (ub.len > 4u * L.umi_max_bytes) {
+            if (ub_len > 4u * L.umi_max_bytes) {
                 *status |= FASTF_ST_UMI_TOO_LONG;
             } else {
+                // encode_DNA: A C G T -> 0 1 2 3 = bits 1 and 2 of the ASCII code, xor-ed; any other byte makes the UMI NULL
                 u32 hi = 0, anybad = 0;
-                for (u32 i = 0; i < ub.len; i++) {
-                    const u32 ch = A.byte(ub.off + i);
-                    const u32 code = ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
-                    anybad |= code > 3u;
-                    hi |= (code & 3u) << (30u - 2u * i);
+                for (u32 i = 0; i < ub_len; i++) {
+                    const u32 ch = A.byte(ub_off + i);
+                    const u32 code = ((ch >> 1) ^ (ch >> 2)) & 3u;
+                    anybad |= ch ^ ((0x54474341u >> (8u * code)) & 255u);
+                    hi |= code << (30u - 2u * i);
                 }
                 u64 ucode = 0;   // SQL NULL
                 if (!anybad) {
                     u64 content = (u64)(hi >> (32u - 8u * L.umi_max_bytes));
-                    u64 nbytes = (ub.len + 3u) >> 2;
+                    u64 nbytes = (ub_len + 3u) >> 2;
                     ucode = (1ull << (L.bits_umi - 1u)) | (content << 3) | nbytes;
                 }
                 key = ((u64)cidx << (L.bits_gene + L.bits_umi)) | ((u64)gidx << L.bits_umi) | ucode;
@@ -396,7 +428,7 @@ fastf_bam_parse_kernel(const u8 *__restrict__ infl, u64 infl_total, const u64 *_
                        FastfStrTableView cells, FastfStrTableView genes, FastfKeyLayout L,
                        const u64 *__restrict__ stage_off, u64 *__restrict__ stage, u32 *__restrict__ blk_nrec, u32 *__restrict__ blk_ncbv, u32 *__restrict__ blk_status)
 {
-    __shared__ __align__(16) u8 s_win[FASTF_PARSE_WARPS][FASTF_PARSE_WIN];
+    __shared__ __align__(16) u8 s_win[FASTF_PARSE_WARPS][FASTF_PARSE_WIN + FASTF_PARSE_PAD];
     __shared__ __align__(8) u64 s_mbar[FASTF_PARSE_WARPS];   // one TMA completion barrier per warp (its window is private)
     const u32 lane = threadIdx.x & 31u;
     const u32 b = blockIdx.x * FASTF_PARSE_WARPS + (threadIdx.x >> 5);
@@ -429,22 +461,23 @@ fastf_bam_parse_kernel(const u8 *__restrict__ infl, u64 infl_total, const u64 *_
             __syncwarp();
             wend = need;
         }
-        const FastfWinAcc WA = {W, wbase};
-        // (2) chain walk: up to 32 records that lie completely inside the window
-        u64 myrec = 0;
-        u32 mybs = 0, nb = 0, stop = 0;
-        u64 q = p;
-        while (nb < 32u && q < bend) {
-            if (bend - q < 4) { stop = FASTF_ST_REC_STRADDLE; break; }
-            if (q + 4 > wend) break;
-            const u32 bs = fastf_acc_u32(WA, q);
+        const FastfWin32 WA = {W};
+        // (2) chain walk: up to 32 records that lie completely inside the window (offsets from the start of the window)
+        u32 myrec = 0, mybs = 0, nb = 0, stop = 0;
+        const u32 wlen = (u32)(wend - wbase), brel = (u32)(bend - wbase);   // the block ends at most 64 KiB + 15 behind wbase
+        u32 qo = (u32)(p - wbase);
+        while (nb < 32u && qo < brel) {
+            if (brel - qo < 4u) { stop = FASTF_ST_REC_STRADDLE; break; }
+            if (qo + 4u > wlen) break;
+            const u32 bs = WA.bytes4(qo);
             if ((i32)bs < 32) { stop = FASTF_ST_REC_CORRUPT; break; }
-            if (q + 4 + (u64)bs > bend) { stop = FASTF_ST_REC_STRADDLE; break; }
-            if (q + 4 + (u64)bs > wend) break;
-            if (lane == nb) { myrec = q + 4; mybs = bs; }
+            if ((u64)qo + 4u + (u64)bs > (u64)brel) { stop = FASTF_ST_REC_STRADDLE; break; }
+            if (qo + 4u + bs > wlen) break;   // no overflow: bs <= brel < 2^17 here
+            if (lane == nb) { myrec = qo + 4u; mybs = bs; }
             nb++;
-            q += 4 + (u64)bs;
+            qo += 4u + bs;
         }
+        const u64 q = wbase + qo;
         if (nb == 0 && !stop) {
             // the record at p is larger than the window: warp-cooperative walk in global memory
             const u32 bs = fastf_ld_u32(infl + p);
