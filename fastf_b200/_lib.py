@@ -92,6 +92,7 @@ _SIGS = {
     "fastf_mt19937_host_from": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, c_u32p]),
     "fastf_mt19937_keepbits_host": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, c_u32p]),
     "fastf_sort_u64_host": (C.c_int, [C.c_void_p, c_u64p, c_u32p, C.c_uint64, C.c_uint32]),
+    "fastf_unique_counts_host": (C.c_int, [C.c_void_p, c_u64p, C.c_uint64, C.c_uint32, C.POINTER(c_u64p), C.POINTER(c_u32p), C.POINTER(C.c_uint64)]),
     "fastf_freq_gpu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.POINTER(FreqResult)]),
     "fastf_freq_gpu_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, c_u64p, c_u32p, c_u32p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(FreqResult)]),
     "fastf_freq_result_free": (None, [C.POINTER(FreqResult)]),

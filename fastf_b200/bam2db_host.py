@@ -336,7 +336,22 @@ def load_lists(db, lib, barcodes_file, features_file, rate_cell, seed):
     return inputs
 
 
-def write_outputs(db, bam_file, path_out, inputs, rate_cell, rate_depth, stats, out):
+def unique_counts(ctx, keys, key_bits):
+    """distinct keys (ascending) and their multiplicities through the device sort + run-length (fastf_unique_counts_host)"""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    ok, oc, nu = _lib.c_u64p(), _lib.c_u32p(), C.c_uint64()
+    ctx.check(ctx.lib.fastf_unique_counts_host(ctx.h, keys.ctypes.data_as(_lib.c_u64p), keys.size, key_bits, C.byref(ok), C.byref(oc), C.byref(nu)), "unique_counts")
+    n = nu.value
+    try:
+        uniq = np.ctypeslib.as_array(ok, shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+        counts = np.ctypeslib.as_array(oc, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+    finally:
+        ctx.lib.fastf_free(C.cast(ok, C.c_void_p))
+        ctx.lib.fastf_free(C.cast(oc, C.c_void_p))
+    return uniq, counts
+
+
+def write_outputs(db, bam_file, path_out, inputs, rate_cell, rate_depth, stats, out, ctx=None):
     """sqlite tables umi / mtx (/ numi) and the 10x .gz files from the device result (reference src/bam2db_ds.c:351-567)"""
     cell, gene, nbytes, content = decode_rows(out["row_keys"], stats["bits_gene"], stats["bits_umi"], stats["umi_max_bytes"])
     mb = stats["umi_max_bytes"]
@@ -375,7 +390,11 @@ def write_outputs(db, bam_file, path_out, inputs, rate_cell, rate_depth, stats, 
     print("features.tsv.gz is generated.")
     if _umi_copies_flag:
         # numi = copies per distinct (cell, gene, umi): GROUP BY cell_index, feature_index, encoded_umi (src/bam2db_ds.c:539-543)
-        uniq, counts = np.unique(out["row_keys"], return_counts=True)
+        # (sorted and run-length encoded on the device; without a context -- tests of the writers alone -- numpy does the same)
+        if ctx is not None:
+            uniq, counts = unique_counts(ctx, out["row_keys"], stats["bits_cell"] + stats["bits_gene"] + stats["bits_umi"])
+        else:
+            uniq, counts = np.unique(out["row_keys"], return_counts=True)
         c2, g2, nb2, ct2 = decode_rows(uniq, stats["bits_gene"], stats["bits_umi"], stats["umi_max_bytes"])
         db.execute("CREATE TABLE numi(\n  feature_index INT,\n  cell_index INT,\n  encoded_umi TEXT,\n  n_copy\n)")
         db.execute("BEGIN TRANSACTION")
@@ -413,7 +432,7 @@ def bam2db(bam_file, db_file, path_out, barcodes_file, features_file, rate_cell,
                     flags = BAM_STRADDLE   # not an htslib-written file: guess and verify the record starts per block (one chunk)
                 else:
                     raise
-        rc = write_outputs(db, bam_file, path_out, inputs, rate_cell, rate_depth, stats, out)
+        rc = write_outputs(db, bam_file, path_out, inputs, rate_cell, rate_depth, stats, out, ctx=ctx)
         db.close()
         return rc
     except (_lib.FastfError, ValueError, OSError, sqlite3.Error) as e:

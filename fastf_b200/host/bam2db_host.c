@@ -355,24 +355,22 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
     printf("features.tsv.gz is generated.\n");
     if (_umi_copies_flag) {
         /* numi: copies per distinct (cell, gene, umi) in (cell, gene, umi) order, NULL first (reference :527-556); decode_DNA(blob, 10) at :629.
-         * The rows are sorted on the device; the run lengths are counted here while the table and the text are laid out. */
-        uint64_t n = res.n_rows, *k = (uint64_t *)malloc(sizeof(uint64_t) * (n ? n : 1));
-        memcpy(k, res.row_keys, sizeof(uint64_t) * n);
-        if (fastf_sort_u64_host(ctx, k, NULL, n, res.bits_cell + res.bits_gene + res.bits_umi)) { free(k); fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
+         * The device sorts the rows and takes the run lengths (fastf_unique_counts_host); here the table and the text are laid out. */
+        uint64_t nu = 0, *k = NULL;
+        uint32_t *copies_of = NULL;
+        if (fastf_unique_counts_host(ctx, res.row_keys, res.n_rows, res.bits_cell + res.bits_gene + res.bits_umi, &k, &copies_of, &nu)) { fprintf(stderr, "\x1b[31mError:\x1b[0m %s\n", fastf_last_error(ctx)); goto done; }
         fastf_sqlite_bulk *bulk = fastf_sqlite_bulk_begin(db_file, root_numi);
-        if (!bulk) { free(k); fprintf(stderr, "SQL error: cannot append to table numi of %s\n", db_file); goto done; }
+        if (!bulk) { free(k); free(copies_of); fprintf(stderr, "SQL error: cannot append to table numi of %s\n", db_file); goto done; }
         fastf_textbuf tb = {0};
-        for (uint64_t i = 0; i < n;) {
-            uint64_t j = i;
-            while (j < n && k[j] == k[i]) j++;
+        for (uint64_t i = 0; i < nu; i++) {
             int64_t cell, gene;
             uint8_t blob[8];
             uint64_t content = 0;
             const int nb = key_fields(k[i], bu, bg, mb, &cell, &gene, blob, &content);
+            const int64_t copies = (int64_t)copies_of[i];
             /* columns: feature_index, cell_index, encoded_umi, n_copy -- the blob sits in the middle, so the row is laid out by hand */
             {
                 const int64_t head[2] = {gene, cell};
-                const int64_t copies = (int64_t)(j - i);
                 if (fastf_sqlite_bulk_row4(bulk, head, nb < 0 ? NULL : blob, nb < 0 ? 0u : (unsigned)nb, copies)) break;
             }
             char dec[16] = "NULL";
@@ -385,11 +383,11 @@ int bam2db(char *bam_file, char *db_file, char *path_out, char *barcodes_file, c
             q += fastf_fmt_i64(q, gene); *q++ = '\t';
             q += fastf_fmt_i64(q, cell); *q++ = '\t';
             size_t dl = strlen(dec); memcpy(q, dec, dl); q += dl; *q++ = '\t';
-            q += fastf_fmt_i64(q, (int64_t)(j - i)); *q++ = '\n';
+            q += fastf_fmt_i64(q, copies); *q++ = '\n';
             tb.n = (size_t)(q - tb.p);
-            i = j;
         }
         free(k);
+        free(copies_of);
         if (fastf_sqlite_bulk_end(bulk)) { fastf_textbuf_free(&tb); fprintf(stderr, "SQL error: writing table numi of %s failed\n", db_file); goto done; }
         snprintf(path, sizeof path, "%s/umi.tsv.gz", path_out);
         const int wrc = fastf_gz_write_parallel(path, tb.p, tb.n);

@@ -242,7 +242,7 @@ def bam2db_sharded(bam_file, db_file, path_out, barcodes_file, features_file, ra
         rc = 0
         if rank == 0:
             stats, out = res
-            rc = B.write_outputs(db, bam_file, path_out, inputs, rate_cell, rate_depth, stats, out)
+            rc = B.write_outputs(db, bam_file, path_out, inputs, rate_cell, rate_depth, stats, out, ctx=ctx)
             db.close()
         return rc
     except (_lib.FastfError, ValueError, OSError) as e:

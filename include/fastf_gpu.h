@@ -172,6 +172,10 @@ int fastf_mt19937_host(fastf_ctx *ctx, uint32_t seed, uint64_t n, uint32_t *out_
 int fastf_mt19937_host_from(fastf_ctx *ctx, uint32_t seed, uint64_t first, uint64_t n, uint32_t *out_words);
 int fastf_mt19937_keepbits_host(fastf_ctx *ctx, uint32_t seed, uint64_t n, uint64_t threshold, uint32_t *out_bits /* ceil(n/32) words */);
 int fastf_sort_u64_host(fastf_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t n, uint32_t key_bits);
+/* distinct keys (ascending) and their multiplicities: device sort + run-length heads.  Replaces `SELECT ..., COUNT(*) ... GROUP BY
+ * cell_index, feature_index, encoded_umi` of -u/--umicopies (reference src/bam2db_ds.c:527-530).  *out_keys / *out_counts are
+ * malloc'ed by the library: free() them. */
+int fastf_unique_counts_host(fastf_ctx *ctx, const uint64_t *keys, uint64_t n, uint32_t key_bits, uint64_t **out_keys, uint32_t **out_counts, uint64_t *n_unique);
 
 /* ---- freq hot path (reference src/count.c:3-21) ---- */
 typedef struct {

@@ -164,6 +164,18 @@ def test_radix_sort_is_a_stable_sort(gpu_ctx, n, bits):
     assert np.array_equal(k3, k2)
 
 
+@pytest.mark.parametrize("n,bits,distinct", [(0, 40, 1), (1, 64, 1), (5000, 30, 7), (1 << 20, 54, 90_000), (2_500_003, 58, 2_400_000)])
+def test_unique_counts_equal_numpy_unique(gpu_ctx, n, bits, distinct):
+    """copies per distinct key (what -u/--umicopies groups by, reference src/bam2db_ds.c:527-530): device sort + run-length heads"""
+    from fastf_b200 import bam2db_host
+    rng = np.random.default_rng(n + bits)
+    pool = rng.integers(0, 2**63, distinct, dtype=np.uint64) >> np.uint64(63 - min(bits, 63))
+    keys = pool[rng.integers(0, distinct, n)] if n else np.zeros(0, np.uint64)
+    uniq, counts = bam2db_host.unique_counts(gpu_ctx, keys, bits)
+    wu, wc = np.unique(keys, return_counts=True)
+    assert np.array_equal(uniq, wu) and np.array_equal(counts.astype(np.int64), wc)
+
+
 HW = 0x100   # FASTF_INFLATE_HW_ENGINE
 
 
