@@ -40,7 +40,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N_CELLS, N_GENES, RATE_CELL, RATE_DEPTH, SEED, DATA_SEED = 10000, 36000, 1.0, 0.3, 926, 11
 # DRAM bytes of ONE launch of the inflate kernel on a full chunk of 2 x 148 x 224 BGZF blocks (ncu --set full, not a bench run)
-INFLATE_TRAFFIC = (27.256e9 + 4.611e9, "profiles/r02b_ncu_inflate_crc_parse.txt (27.256 GB read + 4.611 GB written per launch over one 66304-block chunk, 4.31 GB inflated: "
+INFLATE_TRAFFIC = (27.272e9 + 4.611e9, "profiles/r02c_ncu_inflate_crc_parse.txt (27.272 GB read + 4.611 GB written per launch over one 66304-block chunk, 4.31 GB inflated: "
                    "the LZ77 windows of 33152 concurrent streams (1 GB) do not fit the 126 MB L2, so most match sources are 32-byte sector reads from DRAM)")
 
 
