@@ -184,11 +184,22 @@ def sharded_tail(ctx, job, dist, torch, device, rank, world, n_cells, want_rows=
         rows_all = dst[:sum(out_sizes)]
     if rank != 0:
         return None
-    g, c, v = (p.cpu().numpy().view(np.uint32) for p in pieces)
+    # rank 0 brings the gathered columns to the host: through the library's pinned bounce buffers (a torch .cpu() into pageable
+    # memory runs at a few GB/s, and the COO of N ranks' distinct cells is N times the single-GPU one)
+    def to_host(t, dtype):
+        if device == "cpu":
+            return t.numpy().view(dtype).copy()
+        a = np.empty(t.numel(), dtype=dtype)
+        if t.numel():
+            ctx.check(lib.fastf_memcpy_d2h(ctx.h, C.c_void_p(a.ctypes.data), C.c_void_p(t.data_ptr()), a.nbytes), "d2h of the gathered result")
+        return a
+    if device != "cpu":
+        torch.cuda.current_stream().synchronize()   # the collectives are ordered on torch's stream, the library copies on its own
+    g, c, v = (to_host(p, np.uint32) for p in pieces)
     stats = {"total": sum(x[0] for x in metas), "cb_valid": sum(x[1] for x in metas), "sampled": sum(x[2] for x in metas), "valid": sum(x[3] for x in metas),
              "nnz": int(g.size), "bits_cell": bits_cell, "bits_gene": bits_gene, "bits_umi": bits_umi, "umi_max_bytes": (bits_umi - 4) // 8,
              "exchanged_keys": sum(x[5] for x in metas)}
-    out = {"m_gene": g, "m_cell": c, "m_count": v, "row_keys": rows_all.cpu().numpy().view(np.uint64) if want_rows else np.zeros(0, np.uint64)}
+    out = {"m_gene": g, "m_cell": c, "m_count": v, "row_keys": to_host(rows_all, np.uint64) if want_rows else np.zeros(0, np.uint64)}
     return stats, out
 
 
