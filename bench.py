@@ -551,7 +551,7 @@ def main():
             stages[k] = {"ms": round(ms, 3), "alg_GBps": round(bytes_ / (ms * 1e-3) / 1e9, 1) if ms > 0 else None}
         line = {"metric": "bam2db reads/sec (device-timed)", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "timing": "value: device-timed (CUDA events), inputs resident in HBM; e2e: host wall clock from pinned host memory",
+                "timing": "value: device-timed (CUDA events), compressed bytes resident in HBM and the BGZF block index (header walk) precomputed on the host outside the timed region; e2e: host wall clock from pinned host memory, header walk and every H2D / D2H copy inside",
                 "config": {"workload": workload, "tiling": f"{base['reads']} DISTINCT reads per GPU (zlib-6 BGZF image, {base['compressed'] / 1e6:.0f} MB compressed, {base['inflated'] / 1e6:.0f} MB inflated; data seed {DATA_SEED}+rank) cycled {tiles}x per step "
                                      f"(5e8 distinct reads take ~12 min of host zlib time per GPU; the MT19937 draw ordinal keeps running, so every cycle keeps a different {RATE_DEPTH:.0%})",
                            "checks": dict(checks, per_job="total == tiles x reads, cb_valid == tiles x one-tile cb_valid, sampled within 6 sigma of Binomial(cb_valid, rate), status 0, steps agree"),
