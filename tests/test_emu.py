@@ -101,6 +101,25 @@ def test_emu_mt19937_jump_ahead(emu_lib):
     assert r.returncode == 0, r.stdout[-2000:]
 
 
+def test_emu_unique_counts(emu_lib):
+    """-u/--umicopies (reference src/bam2db_ds.c:527-530): distinct keys and their copies from the device sort + run-length heads"""
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from fastf_b200 import _lib, bam2db_host\n"
+        "ctx = _lib.Context(0)\n"
+        "for n, bits, distinct in ((0, 40, 1), (1, 64, 1), (3000, 30, 7), (20000, 54, 5000), (9000, 58, 8990)):\n"
+        "    rng = np.random.default_rng(n + bits)\n"
+        "    pool = rng.integers(0, 2**63, distinct, dtype=np.uint64) >> np.uint64(63 - min(bits, 63))\n"
+        "    keys = pool[rng.integers(0, distinct, n)] if n else np.zeros(0, np.uint64)\n"
+        "    u, c = bam2db_host.unique_counts(ctx, keys, bits)\n"
+        "    wu, wc = np.unique(keys, return_counts=True)\n"
+        "    assert np.array_equal(u, wu) and np.array_equal(c.astype(np.int64), wc), (n, bits)\n"
+    ) % (ROOT,)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, FASTF_GPU_LIB=emu_lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+
+
 def test_emu_bgzf_crc32_check(emu_lib):
     """warp-parallel CRC-32 (32 lane segments folded by GF(2) shifts) against zlib's for ragged block sizes; a flipped payload byte in
     a stored block (still valid deflate) and a wrong CRC field are reported as bgzf-crc32-mismatch"""
