@@ -4,28 +4,30 @@
 // ~50 instructions per symbol, and ncu shows it bound by instruction issue (77 % of issue slots, 1 % of DRAM).  This kernel
 // removes the redundancy by splitting the work by role inside one persistent CTA per SM:
 //
-//   decoder warps  (8 warps x 16 lanes)  lane = one BGZF block ("stream").  Pure scalar Huffman decoding out of that stream's
+//   decoder warps  (7 warps x 32 lanes)  lane = one BGZF block ("stream").  Pure scalar Huffman decoding out of that stream's
 //                                        own shared-memory tables; emits 4-byte TOKENS (up to three literals | match(len, dist)
 //                                        | end) into the stream's shared-memory ring.  No global stores, no warp collectives.
-//                                        One ROUND of a lane = up to two literal tokens plus the match that ends the literal
-//                                        run: the divergent paths of a warp execute one after the other and some lane always
-//                                        needs each of them, so every lane walks through both (ncu: 14.4 M rounds per 2 GiB
-//                                        against 26 M with one token per round).
-//   service warps  (24 warps, lock step) own 5-6 streams each; one poll pass looks at all of them (lane k reads the k-th
-//                                        stream's control block, a ballot picks the streams with work).  (a) LZ77: take up to
-//                                        32 tokens of one stream, prefix-sum their output lengths, store the literals and copy
-//                                        the matches with all 32 lanes (the source loads of several matches are issued before
-//                                        any is stored so the L2 round trips overlap).  (b) stream set-up: fetch the next BGZF
-//                                        block from a global counter, parse deflate block headers, copy stored blocks, build
-//                                        the Huffman tables cooperatively -- decoders never run that code.
+//                                        One ROUND of a lane = up to two literal tokens (decoded without inner branches) plus
+//                                        the match that ends the literal run: the divergent paths of a warp execute one after
+//                                        the other and some lane always needs each of them, so every lane walks through both.
+//                                        A match whose source lies more than 512 bytes back is prefetched into L2 on the spot.
+//   service warps  (25 warps, lock step) own 9 consecutive streams each; one poll pass looks at all of them (lane k reads the
+//                                        k-th stream's control block, a ballot picks the streams with work).  (a) LZ77: take up
+//                                        to 32 tokens of one stream, prefix-sum their output lengths, store the literals and
+//                                        copy the matches with all 32 lanes (the source loads of several matches, or of several
+//                                        pieces of a long one, are issued before any is stored so the L2 round trips overlap).
+//                                        (b) stream set-up: fetch the next BGZF block from a global counter, parse deflate block
+//                                        headers, copy stored blocks, build the Huffman tables cooperatively -- decoders never
+//                                        run that code.
 //
-// Tables per stream: 9-bit literal/length table and 7-bit distance table with 16-bit entries (code length, kind, symbol) and the
-// per-length code counts in shared memory; the canonical walk for longer codes fetches its symbol from a per-stream list in global
-// memory (L2); length/distance base+extra bits sit in a CTA-wide table.  128 streams x 1.6 KB fill the SM's shared memory.
-// What bounds it (profiles/README.md): every warp is a serial dependency chain issuing one instruction per ~9 cycles, so both
-// sides are latency-bound -- decoders at ~6.5 warp-instructions per symbol, service warps on the L2/DRAM round trips of match
-// sources (19 k streams x 32 KiB windows do not fit the 126 MB L2: 46 % hit rate).  More streams per SM made it slower
-// (8-bit tables, 160/192 streams: -10..-25 %), as did more loads in flight per service warp at the cost of registers.
+// Tables per stream: 8-bit literal/length table and 6-bit distance table with 16-bit entries (code length, kind, symbol) in shared
+// memory; a code longer than the table takes one lookup in the stream's second-level table in global memory (L2), with the
+// canonical walk (range limits in shared memory, symbol list in L2) as the fallback when the second level does not fit;
+// length/distance base+extra bits sit in a CTA-wide table.  224 streams x 0.9 KB + the set-up scratch fill the SM's shared memory.
+// What bounds it (profiles/r02_inflate_ab.md): a latency machine -- throughput = independent Huffman chains per SM / per-symbol
+// latency.  With 224 streams the LZ77 side co-limits: the service warps are busy 97 % of the time (5 700 cycles per batch of 22
+// tokens) and a third of the decoders' lane-rounds find their ring full; DRAM traffic is 5x the algorithmic bytes (the windows of
+// 33 152 resident streams do not fit the L2) but at 12 % of the bandwidth it is not the limit.
 #pragma once
 #include "bgzf_inflate.cuh"
 

@@ -145,7 +145,7 @@ extern "C" int fastf_bam2db_begin(fastf_ctx *ctx, const fastf_bam2db_params *p, 
     job->chunk_bytes = p->chunk_inflated_bytes ? std::max<u64>(p->chunk_inflated_bytes, 1u << 20) : FASTF_DEFAULT_CHUNK;
     // the persistent thread-per-stream kernel keeps 64 streams per SM busy: give every launch several blocks per stream
     if (!p->chunk_inflated_bytes && (job->lanes & 0xffu) >= 1 && (job->lanes & 0xffu) <= 4) {
-        u64 rounds = 2;   // full rounds of the persistent kernel per chunk (2 -> 37888 blocks, <= 2.4 GiB on 148 SMs)
+        u64 rounds = 2;   // full rounds of the persistent kernel per chunk (2 -> 66304 blocks, <= 4.3 GB on 148 SMs)
         if (const char *e = getenv("FASTF_CHUNK_ROUNDS")) { const long v = atol(e); if (v >= 1 && v <= 16) rounds = (u64)v; }
         job->chunk_blocks = rounds * (u64)ctx->n_sm * FASTF_TPS_STREAMS;
         job->chunk_bytes = job->chunk_blocks * 65536ull;
